@@ -1,0 +1,947 @@
+// bevy_ggrs_b200 engine: host logic of the rollback hot path + the C ABI of include/bevy_ggrs_b200.h.
+//
+// Host side restates, request by request, what handle_requests does to the frame resources
+// (reference src/schedule_systems.rs:189-270) and to the snapshot ring (src/snapshot/mod.rs:144-270),
+// compiles the whole request vector into a small op program, and launches ONE fused kernel
+// (kernels.cuh: k_particles_program) — or, for schemas/systems without a compiled bundle, one
+// generic kernel per request ("stepwise" path).  No CPU compute path exists: without a GPU every
+// entry point that touches state returns BGR_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <string>
+#include <vector>
+
+#include "../../include/bevy_ggrs_b200.h"
+#include "kernels.cuh"
+#include "ring.hpp"
+#include "seahash.cuh"
+
+using namespace bgr;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int status, const std::string& text) { g_err = text; return status; }
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t _e = (expr);                                                                    \
+        if (_e != cudaSuccess)                                                                      \
+            return fail(BGR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));          \
+    } while (0)
+
+struct Column {
+    std::string name;
+    uint32_t elem_bytes = 0, words = 0, first_plane = 0, strategy = 0;
+    uint32_t hash_kind = BGR_HASH_NONE, hash_off = 0, hash_len = 0, hash_flags = 0;
+    int ck_slot = -1;  // index among checksummed columns (registration order)
+};
+
+struct SystemReg {
+    uint32_t id = 0;
+    std::vector<uint32_t> cols, params;
+};
+
+constexpr uint32_t kReqAdvanceNoBump = 100;  // bgr_advance_world: caller already bumped RollbackFrameCount
+
+// Every host-side resource handle_requests / the schedules mutate.  A request vector is compiled
+// against a copy and committed only if the whole vector is valid.
+struct HostState {
+    SlotRing ring;
+    std::vector<uint32_t> slot_rows;        // RollbackOrdered::len() captured by each snapshot (mod.rs:339)
+    std::vector<uint64_t> slot_elapsed_ns;  // Time<GgrsTime> captured by each snapshot (time.rs:100)
+    int32_t frame_count = 0;                // RollbackFrameCount (mod.rs:66-67)
+    int32_t confirmed = 0;                  // ConfirmedFrameCount (mod.rs:76-77), init_resource -> 0
+    bool has_maxpred = false;               // MaxPredictionWindow inserted? (lib.rs:116-117)
+    uint32_t maxpred = 0;
+    uint64_t elapsed_ns = 0;                // Time<GgrsTime>::elapsed
+    uint32_t n_rows = 0;                    // RollbackOrdered::len()
+    uint32_t call_count = 0;                // un-rolled-back counter of BGR_SYS_U32_STORE_CALL_COUNT
+};
+
+struct Pending {
+    uint32_t buf = 0;
+    uint32_t n_saves = 0;
+    int32_t frames[kMaxSaves];
+    uint32_t totals[kMaxSaves];
+};
+
+float duration_as_secs_f32(uint64_t ns) {  // core::time::Duration::as_secs_f32
+    uint64_t secs = ns / 1000000000ULL;
+    uint32_t nanos = uint32_t(ns % 1000000000ULL);
+    return float(secs) + float(nanos) / 1000000000.0f;
+}
+uint32_t f32_bits(float f) { uint32_t b; std::memcpy(&b, &f, 4); return b; }
+
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v && *v ? std::atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct bgr_engine {
+    bgr_config cfg{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 0;
+
+    std::vector<Column> cols;
+    std::vector<SystemReg> systems;
+    uint32_t n_ck = 0;
+    bool built = false;
+
+    uint32_t epad = 0, words = 0;
+    size_t image_bytes = 0;
+    uint8_t* arena = nullptr;  // image 0 = live, image s+1 = slot s
+    uint8_t* d_kill = nullptr;
+
+    HostState st;
+
+    static constexpr int kBufs = 4;
+    unsigned long long* d_accum = nullptr;
+    unsigned int* d_ticket = nullptr;
+    unsigned long long* h_out[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* d_out[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    std::deque<Pending> pending;
+    uint32_t next_buf = 0;
+    std::vector<bgr_partial> last_partials;
+
+    uint64_t launches = 0;
+    bool last_fused = false;
+
+    // compiled bundle: particles (update_particles + despawn_particles)
+    bool bundle_particles = false;
+    uint32_t bt = 0, bv = 0, bl = 0;
+    std::vector<uint16_t> passive;
+    int tune_vec = 4, tune_block = 256, tune_bps = 0;
+    int occ_cache[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+
+    uint8_t* image(uint32_t idx) const { return arena + size_t(idx) * image_bytes; }
+    uint32_t grid_for(uint32_t n, uint32_t per_block) const {
+        uint32_t need = (n + per_block - 1) / per_block;
+        uint32_t cap = uint32_t(num_sms) * 8u;
+        return std::max(1u, std::min(need, cap));
+    }
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// compile: requests -> ops, mutating `s` exactly like handle_requests mutates the World
+// ---------------------------------------------------------------------------------------------
+struct Program {
+    Op ops[kMaxOps];
+    uint32_t n_ops = 0, n_saves = 0;
+    int32_t save_frames[kMaxSaves];
+    uint32_t save_totals[kMaxSaves];
+    uint32_t max_rows = 0, live_rows = 0;
+    bool has_load = false, has_advance = false, first_is_load = false;
+};
+
+int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, const bgr_request* reqs, uint32_t n,
+                     Program& pg) {
+    if (n > kMaxOps) return fail(BGR_ERR_CAPACITY, "too many requests in one handle_requests call");
+    pg.live_rows = s.n_rows;
+    pg.max_rows = s.n_rows;
+    uint32_t n_counter_systems = 0;
+    for (auto& sy : e->systems) n_counter_systems += (sy.id == BGR_SYS_U32_STORE_CALL_COUNT);
+    for (uint32_t i = 0; i < n; ++i) {
+        const bgr_request& rq = reqs[i];
+        // schedule_systems.rs:190-220 — resources recomputed from the session before every request
+        const int32_t current_frame = s.frame_count;
+        if (sess) {
+            switch (sess->kind) {
+            case BGR_SESSION_P2P:
+                s.has_maxpred = true; s.maxpred = sess->max_prediction;
+                s.confirmed = sess->confirmed_frame;
+                break;
+            case BGR_SESSION_SYNCTEST: {
+                s.has_maxpred = true; s.maxpred = sess->max_prediction;
+                int32_t cf = current_frame - int32_t(sess->check_distance);
+                if (cf >= 0) s.confirmed = cf;
+                break;
+            }
+            case BGR_SESSION_SPECTATOR:
+                s.has_maxpred = true; s.maxpred = 0;
+                s.confirmed = current_frame;
+                break;
+            default: break;
+            }
+        }
+        Op& op = pg.ops[pg.n_ops];
+        std::memset(&op, 0, sizeof op);
+        switch (rq.kind) {
+        case BGR_REQ_SAVE: {  // :223-237 -> SaveWorld: sync_depth, discard_old_snapshots, save (component_snapshot.rs:135-144)
+            if (pg.n_saves >= kMaxSaves) return fail(BGR_ERR_CAPACITY, "too many SaveGameState requests in one call");
+            if (s.has_maxpred) s.ring.set_depth(s.maxpred);
+            s.ring.confirm(s.confirmed);
+            uint32_t slot = s.ring.push(s.frame_count);
+            if (slot == SlotRing::kNoSlot)
+                return fail(BGR_ERR_CAPACITY, "snapshot ring needs more frame slots than bgr_config.max_depth");
+            op.kind = OP_SAVE;
+            if (slot == SlotRing::kNoSlot - 1) { op.flags |= OPF_NO_STORE; op.image = 0; }
+            else {
+                op.image = slot + 1;
+                s.slot_rows[slot] = s.n_rows;
+                s.slot_elapsed_ns[slot] = s.elapsed_ns;
+            }
+            op.n_rows = s.n_rows;
+            op.save_index = pg.n_saves;
+            pg.save_frames[pg.n_saves] = rq.frame;
+            pg.save_totals[pg.n_saves] = s.n_rows;
+            ++pg.n_saves;
+            break;
+        }
+        case BGR_REQ_LOAD: {  // :238-250 -> LoadWorld
+            s.frame_count = rq.frame;
+            std::string err;
+            if (!s.ring.rollback(rq.frame, &err)) return fail(BGR_ERR_NO_SNAPSHOT, err);
+            uint32_t slot = 0;
+            if (!s.ring.get(&slot, &err)) return fail(BGR_ERR_NO_SNAPSHOT, err);
+            s.n_rows = s.slot_rows[slot];
+            s.elapsed_ns = s.slot_elapsed_ns[slot];
+            op.kind = OP_LOAD;
+            op.image = slot + 1;
+            op.n_rows = s.n_rows;
+            if (pg.n_ops == 0) pg.first_is_load = true;
+            pg.has_load = true;
+            break;
+        }
+        case BGR_REQ_ADVANCE:
+        case kReqAdvanceNoBump: {  // :251-269 -> AdvanceWorld
+            if (rq.kind == BGR_REQ_ADVANCE) s.frame_count += 1;
+            if (rq.n_players > BGR_MAX_PLAYERS) return fail(BGR_ERR_INVALID_ARGUMENT, "n_players > BGR_MAX_PLAYERS");
+            // GgrsTimePlugin::update (time.rs:63-76): advance_to(frame * 1e9 / fps)
+            uint64_t runtime = uint64_t(int64_t(s.frame_count)) * 1000000000ULL / uint64_t(e->cfg.fps);
+            if (runtime < s.elapsed_ns)
+                return fail(BGR_ERR_STATE, "tried to move Time<GgrsTime> backwards (RollbackFrameCount went back without LoadWorld)");
+            uint64_t delta = runtime - s.elapsed_ns;
+            s.elapsed_ns = runtime;
+            op.kind = OP_ADVANCE;
+            op.dt_bits = f32_bits(duration_as_secs_f32(delta));
+            op.n_rows = s.n_rows;
+            op.call_count = s.call_count;
+            s.call_count += n_counter_systems;
+            for (uint32_t k = 0; k < 4 && k < rq.n_players; ++k) op.inputs[k] = rq.inputs[k];
+            pg.has_advance = true;
+            break;
+        }
+        default: return fail(BGR_ERR_INVALID_ARGUMENT, "unknown request kind");
+        }
+        pg.max_rows = std::max(pg.max_rows, op.n_rows);
+        ++pg.n_ops;
+    }
+    return BGR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch: fused bundle kernel
+// ---------------------------------------------------------------------------------------------
+template <int VEC, int BLOCK>
+int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int bi) {
+    if (e->occ_cache[vi][bi] == 0) {
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_particles_program<VEC, BLOCK>, BLOCK, 0));
+        e->occ_cache[vi][bi] = std::max(1, nb);
+    }
+    int bps = e->tune_bps > 0 ? std::min(e->tune_bps, e->occ_cache[vi][bi]) : e->occ_cache[vi][bi];
+    uint32_t n_groups = (pp.max_rows + VEC - 1) / VEC;
+    uint32_t need = (n_groups + BLOCK - 1) / BLOCK;
+    uint32_t grid = std::max(1u, std::min(need, uint32_t(e->num_sms * bps)));
+    k_particles_program<VEC, BLOCK><<<grid, BLOCK, 0, e->stream>>>(pp);
+    CUDA_TRY(cudaGetLastError());
+    e->launches += 1;
+    return BGR_OK;
+}
+
+int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
+    ProgramParams pp;
+    std::memset(&pp, 0, sizeof pp);
+    pp.arena = e->arena;
+    pp.image_bytes = e->image_bytes;
+    pp.order_base = e->cfg.order_base;
+    pp.accum = e->d_accum;
+    pp.out = e->d_out[buf];
+    pp.ticket = e->d_ticket;
+    pp.epad = e->epad; pp.words = e->words;
+    pp.n_ops = pg.n_ops; pp.n_saves = pg.n_saves;
+    pp.max_rows = pg.max_rows; pp.live_rows = pg.live_rows;
+    pp.flags = 0;
+    if (!pg.first_is_load) pp.flags |= PF_READ_LIVE;
+    if (pg.has_load || pg.has_advance) pp.flags |= PF_WRITE_LIVE_ACTIVE;
+    if (pg.has_load) pp.flags |= PF_WRITE_LIVE_PASSIVE;
+    const Column& ct = e->cols[e->bt]; const Column& cv = e->cols[e->bv];
+    if (ct.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_T; if (ct.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_CK_T_FINITE; pp.ck_t_slot = uint32_t(ct.ck_slot); }
+    if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_CK_V_FINITE; pp.ck_v_slot = uint32_t(cv.ck_slot); }
+    pp.t_plane = ct.first_plane; pp.v_plane = cv.first_plane; pp.l_plane = e->cols[e->bl].first_plane;
+    pp.n_passive = uint32_t(e->passive.size());
+    for (size_t i = 0; i < e->passive.size(); ++i) pp.passive[i] = e->passive[i];
+    std::memcpy(pp.ops, pg.ops, sizeof(Op) * pg.n_ops);
+    if (pp.max_rows == 0) pp.max_rows = 1;  // still run one group so the result block is published
+    int v = e->tune_vec, b = e->tune_block;
+    if (v == 1 && b == 128) return launch_particles<1, 128>(e, pp, 0, 0);
+    if (v == 1) return launch_particles<1, 256>(e, pp, 0, 1);
+    if (v == 2 && b == 128) return launch_particles<2, 128>(e, pp, 1, 0);
+    if (v == 2) return launch_particles<2, 256>(e, pp, 1, 1);
+    if (b == 128) return launch_particles<4, 128>(e, pp, 2, 0);
+    return launch_particles<4, 256>(e, pp, 2, 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch: stepwise path (generic schemas / systems)
+// ---------------------------------------------------------------------------------------------
+int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
+    uint32_t live_rows = pg.live_rows;
+    uint8_t* live = e->image(0);
+    for (uint32_t i = 0; i < pg.n_ops; ++i) {
+        const Op& op = pg.ops[i];
+        switch (op.kind) {
+        case OP_SAVE: {
+            unsigned long long* acc = e->d_accum + size_t(op.save_index) * kAccStride;
+            bool counted = false;
+            for (const Column& c : e->cols) {
+                if (c.hash_kind == BGR_HASH_NONE) continue;
+                k_checksum_column<<<e->grid_for(std::max(1u, op.n_rows), 256), 256, 0, e->stream>>>(
+                    live, e->epad, e->words, c.first_plane, c.hash_off, c.hash_len,
+                    c.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32, op.n_rows, e->cfg.order_base, acc,
+                    uint32_t(c.ck_slot), counted ? 0u : 1u, 1u);
+                counted = true;
+                e->launches += 1;
+            }
+            if (!counted) {
+                k_checksum_column<<<e->grid_for(std::max(1u, op.n_rows), 256), 256, 0, e->stream>>>(
+                    live, e->epad, e->words, 0, 0, 0, 0, op.n_rows, e->cfg.order_base, acc, 0, 1u, 0u);
+                e->launches += 1;
+            }
+            if (!(op.flags & OPF_NO_STORE) && op.n_rows > 0) {
+                k_copy_image<<<e->grid_for((op.n_rows + 3) / 4, 256), 256, 0, e->stream>>>(
+                    live, e->image(op.image), e->epad, e->words, op.n_rows, op.n_rows);
+                e->launches += 1;
+            }
+            break;
+        }
+        case OP_LOAD: {
+            uint32_t n_copy = std::max(op.n_rows, live_rows);
+            if (n_copy > 0) {
+                k_copy_image<<<e->grid_for((n_copy + 3) / 4, 256), 256, 0, e->stream>>>(
+                    e->image(op.image), live, e->epad, e->words, op.n_rows, n_copy);
+                e->launches += 1;
+            }
+            live_rows = op.n_rows;
+            break;
+        }
+        case OP_ADVANCE: {
+            bool any_despawn = false;
+            uint32_t counter = op.call_count;
+            uint32_t n = op.n_rows;
+            if (n == 0) break;
+            uint32_t grid = e->grid_for(n, 256);
+            for (const SystemReg& sy : e->systems) {
+                switch (sy.id) {
+                case BGR_SYS_PARTICLES_UPDATE:
+                    k_sys_particles_update<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane,
+                                                                          e->cols[sy.cols[1]].first_plane, n, op.dt_bits);
+                    break;
+                case BGR_SYS_PARTICLES_DESPAWN:
+                    k_sys_particles_despawn<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane, n, e->d_kill);
+                    any_despawn = true;
+                    break;
+                case BGR_SYS_U32_ADD:
+                    k_sys_u32_add<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1]);
+                    break;
+                case BGR_SYS_U32_SATSUB_DESPAWN:
+                    k_sys_u32_satsub_despawn<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1], e->d_kill);
+                    any_despawn = true;
+                    break;
+                case BGR_SYS_U32_STORE_CALL_COUNT:
+                    k_sys_u32_store<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, counter++);
+                    break;
+                default: return fail(BGR_ERR_UNSUPPORTED, "system has no GPU implementation yet");
+                }
+                e->launches += 1;
+            }
+            if (any_despawn) {
+                k_apply_despawns<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, n, e->d_kill);
+                e->launches += 1;
+            }
+            break;
+        }
+        default: break;
+        }
+    }
+    k_publish<<<1, 128, 0, e->stream>>>(e->d_accum, e->d_out[buf], std::max(1u, pg.n_saves) * kAccStride);
+    e->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    return BGR_OK;
+}
+
+int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs, uint32_t n) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    if (!e->built) return fail(BGR_ERR_STATE, "bgr_build has not been called");
+    if (e->pending.size() >= size_t(bgr_engine::kBufs)) return fail(BGR_ERR_STATE, "too many un-collected submits");
+    if (n && !reqs) return fail(BGR_ERR_INVALID_ARGUMENT, "null requests");
+    HostState s = e->st;
+    Program pg;
+    int rc = compile_requests(e, s, sess, reqs, n, pg);
+    if (rc != BGR_OK) return rc;  // nothing executed, nothing committed
+    uint32_t buf = e->next_buf;
+    bool fused = e->bundle_particles && !(e->cfg.flags & BGR_CFG_FORCE_STEPWISE);
+    rc = fused ? run_fused(e, pg, buf) : run_stepwise(e, pg, buf);
+    if (rc != BGR_OK) return rc;
+    CUDA_TRY(cudaEventRecord(e->ev[buf], e->stream));
+    e->last_fused = fused;
+    e->st = std::move(s);
+    Pending pd;
+    pd.buf = buf; pd.n_saves = pg.n_saves;
+    std::memcpy(pd.frames, pg.save_frames, sizeof(int32_t) * pg.n_saves);
+    std::memcpy(pd.totals, pg.save_totals, sizeof(uint32_t) * pg.n_saves);
+    e->pending.push_back(pd);
+    e->next_buf = (buf + 1) % bgr_engine::kBufs;
+    return BGR_OK;
+}
+
+void fold(const bgr_partial& p, bgr_checksum* out) {
+    // EntityChecksumPlugin::update (entity_checksum.rs:35-43)
+    uint64_t x = sea_hash_2xu64(p.active, p.total);
+    // ComponentChecksumPlugin: `result.hash(&mut hasher)` (component_checksum.rs:93-95), then
+    // ChecksumPlugin::update XORs every part (checksum.rs:88-99)
+    for (uint32_t c = 0; c < p.n_columns && c < BGR_MAX_CHECKSUM_COLUMNS; ++c) x ^= sea_hash_u64(p.xor_[c]);
+    out->frame = p.frame;
+    out->has_checksum = 1;
+    out->lo = x;
+    out->hi = 0;
+}
+
+int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    if (e->pending.empty()) return fail(BGR_ERR_STATE, "nothing to collect");
+    Pending pd = e->pending.front();
+    e->pending.pop_front();
+    CUDA_TRY(cudaEventSynchronize(e->ev[pd.buf]));
+    const unsigned long long* r = e->h_out[pd.buf];
+    e->last_partials.clear();
+    bool nonfinite = false;
+    for (uint32_t k = 0; k < pd.n_saves; ++k) {
+        bgr_partial p;
+        std::memset(&p, 0, sizeof p);
+        p.frame = pd.frames[k];
+        p.n_columns = e->n_ck;
+        p.active = r[k * kAccStride + 6];
+        p.total = pd.totals[k];
+        for (uint32_t c = 0; c < e->n_ck; ++c) p.xor_[c] = r[k * kAccStride + c];
+        if (r[k * kAccStride + 7] & 1ULL) nonfinite = true;
+        e->last_partials.push_back(p);
+    }
+    if (n_out) *n_out = pd.n_saves;
+    for (uint32_t k = 0; k < pd.n_saves && k < cap && out; ++k) {
+        if (e->cfg.flags & BGR_CFG_SHARDED) {
+            out[k].frame = pd.frames[k]; out[k].has_checksum = 0; out[k].lo = 0; out[k].hi = 0;
+        } else {
+            fold(e->last_partials[k], &out[k]);
+        }
+    }
+    if (nonfinite) return fail(BGR_ERR_NON_FINITE, "Hashing is not stable for NaN f32 values.");
+    return BGR_OK;
+}
+
+int drain(bgr_engine* e) {
+    while (!e->pending.empty()) {
+        int rc = collect(e, nullptr, 0, nullptr);
+        if (rc != BGR_OK && rc != BGR_ERR_NON_FINITE) return rc;
+    }
+    return BGR_OK;
+}
+
+// word w of a column element stored AoS on the host (handles elem_bytes not a multiple of 4)
+inline uint32_t host_word(const uint8_t* elem, uint32_t eb, uint32_t w) {
+    uint32_t v = 0;
+    uint32_t nb = std::min(4u, eb - 4u * w);
+    std::memcpy(&v, elem + 4u * w, nb);
+    return v;
+}
+
+int transfer_column(bgr_engine* e, uint32_t image_idx, uint32_t column, uint32_t first, uint32_t count, void* host,
+                    uint32_t stride, bool to_device) {
+    if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
+    if (column >= e->cols.size()) return fail(BGR_ERR_INVALID_ARGUMENT, "unknown column");
+    const Column& c = e->cols[column];
+    if (stride < c.elem_bytes) return fail(BGR_ERR_INVALID_ARGUMENT, "stride < elem_bytes");
+    if (uint64_t(first) + count > e->cfg.max_entities) return fail(BGR_ERR_CAPACITY, "row range exceeds max_entities");
+    if (count == 0) return BGR_OK;
+    int rc = drain(e);
+    if (rc != BGR_OK) return rc;
+    std::vector<uint32_t> plane(count);
+    uint8_t* img = e->image(image_idx);
+    for (uint32_t w = 0; w < c.words; ++w) {
+        uint8_t* dptr = img + size_t(c.first_plane + w) * e->epad * 4u + size_t(first) * 4u;
+        if (to_device) {
+            const uint8_t* src = static_cast<const uint8_t*>(host);
+            for (uint32_t i = 0; i < count; ++i) plane[i] = host_word(src + size_t(i) * stride, c.elem_bytes, w);
+            CUDA_TRY(cudaMemcpyAsync(dptr, plane.data(), size_t(count) * 4u, cudaMemcpyHostToDevice, e->stream));
+            CUDA_TRY(cudaStreamSynchronize(e->stream));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(plane.data(), dptr, size_t(count) * 4u, cudaMemcpyDeviceToHost, e->stream));
+            CUDA_TRY(cudaStreamSynchronize(e->stream));
+            uint8_t* dst = static_cast<uint8_t*>(host);
+            uint32_t nb = std::min(4u, c.elem_bytes - 4u * w);
+            for (uint32_t i = 0; i < count; ++i) std::memcpy(dst + size_t(i) * stride + 4u * w, &plane[i], nb);
+        }
+    }
+    return BGR_OK;
+}
+
+int read_alive_image(bgr_engine* e, uint32_t image_idx, uint32_t first, uint32_t count, uint32_t n_rows, uint8_t* dst) {
+    if (count == 0) return BGR_OK;
+    int rc = drain(e);
+    if (rc != BGR_OK) return rc;
+    if (uint64_t(first) + count > e->cfg.max_entities) return fail(BGR_ERR_CAPACITY, "row range exceeds max_entities");
+    const uint8_t* src = e->image(image_idx) + size_t(e->words) * e->epad * 4u + first;
+    CUDA_TRY(cudaMemcpyAsync(dst, src, count, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    for (uint32_t i = 0; i < count; ++i)
+        if (first + i >= n_rows) dst[i] = 0;
+    return BGR_OK;
+}
+
+void detect_bundles(bgr_engine* e) {
+    e->bundle_particles = false;
+    e->passive.clear();
+    if (e->systems.size() != 2) return;
+    const SystemReg* up = nullptr; const SystemReg* de = nullptr;
+    for (auto& s : e->systems) {
+        if (s.id == BGR_SYS_PARTICLES_UPDATE) up = &s;
+        if (s.id == BGR_SYS_PARTICLES_DESPAWN) de = &s;
+    }
+    if (!up || !de) return;
+    uint32_t t = up->cols[0], v = up->cols[1], l = de->cols[0];
+    if (t == v || t == l || v == l) return;
+    auto ck_ok = [&](const Column& c) {
+        return c.hash_kind == BGR_HASH_NONE || (c.hash_kind == BGR_HASH_BYTES && c.hash_off == 0 && c.hash_len == 12);
+    };
+    if (!ck_ok(e->cols[t]) || !ck_ok(e->cols[v])) return;
+    for (size_t i = 0; i < e->cols.size(); ++i)
+        if (i != t && i != v && e->cols[i].hash_kind != BGR_HASH_NONE) return;  // other checksums: generic path
+    // active planes: translation (3 words of Transform), velocity (3), ttl (2)
+    std::vector<uint8_t> active(e->words, 0);
+    for (uint32_t k = 0; k < 3; ++k) { active[e->cols[t].first_plane + k] = 1; active[e->cols[v].first_plane + k] = 1; }
+    for (uint32_t k = 0; k < 2; ++k) active[e->cols[l].first_plane + k] = 1;
+    for (uint32_t p = 0; p < e->words; ++p)
+        if (!active[p]) e->passive.push_back(uint16_t(p));
+    if (e->passive.size() > size_t(kMaxPassive)) { e->passive.clear(); return; }
+    e->bt = t; e->bv = v; e->bl = l;
+    e->bundle_particles = true;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+BGR_API uint32_t bgr_abi_version(void) { return BGR_ABI_VERSION; }
+BGR_API const char* bgr_last_error(void) { return g_err.c_str(); }
+
+BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
+    if (!cfg || !out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    if (cfg->abi_version != BGR_ABI_VERSION) return fail(BGR_ERR_INVALID_ARGUMENT, "ABI version mismatch");
+    if (cfg->max_entities == 0 || cfg->fps == 0) return fail(BGR_ERR_INVALID_ARGUMENT, "max_entities and fps must be > 0");
+    if (cfg->max_depth == 0 || cfg->max_depth > 64) return fail(BGR_ERR_INVALID_ARGUMENT, "max_depth must be in 1..64");
+    int n_dev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&n_dev);
+    if (ce != cudaSuccess || n_dev == 0)
+        return fail(BGR_ERR_CUDA, std::string("no CUDA device available (bevy_ggrs_b200 has no CPU fallback): ") + cudaGetErrorString(ce));
+    if (cfg->device < 0 || cfg->device >= n_dev) return fail(BGR_ERR_INVALID_ARGUMENT, "bad device ordinal");
+    CUDA_TRY(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10)
+        return fail(BGR_ERR_CUDA, "device is not sm_100 (Blackwell); this library only carries sm_100a code");
+    bgr_engine* e = new bgr_engine();
+    e->cfg = *cfg;
+    e->num_sms = prop.multiProcessorCount;
+    if (cfg->stream) { e->stream = static_cast<cudaStream_t>(cfg->stream); e->own_stream = false; }
+    else {
+        cudaError_t se = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking);
+        if (se != cudaSuccess) { delete e; return fail(BGR_ERR_CUDA, cudaGetErrorString(se)); }
+        e->own_stream = true;
+    }
+    e->tune_vec = env_int("BGR_TUNE_VEC", 4);
+    e->tune_block = env_int("BGR_TUNE_BLOCK", 256);
+    e->tune_bps = env_int("BGR_TUNE_BPS", 0);
+    if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 4;
+    if (e->tune_block != 128 && e->tune_block != 256) e->tune_block = 256;
+    e->st.confirmed = 0;
+    *out = e;
+    return BGR_OK;
+}
+
+BGR_API void bgr_engine_destroy(bgr_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (int i = 0; i < bgr_engine::kBufs; ++i) {
+        if (e->h_out[i]) cudaFreeHost(e->h_out[i]);
+        if (e->ev[i]) cudaEventDestroy(e->ev[i]);
+    }
+    if (e->arena) cudaFree(e->arena);
+    if (e->d_kill) cudaFree(e->d_kill);
+    if (e->d_accum) cudaFree(e->d_accum);
+    if (e->d_ticket) cudaFree(e->d_ticket);
+    if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+BGR_API int bgr_rollback_component(bgr_engine* e, const char* type_name, uint32_t elem_bytes, uint32_t strategy,
+                                   uint32_t* column_out) {
+    if (!e || !column_out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    if (e->built) return fail(BGR_ERR_STATE, "components must be registered before bgr_build");
+    if (elem_bytes == 0 || elem_bytes > 1024) return fail(BGR_ERR_INVALID_ARGUMENT, "elem_bytes must be in 1..1024");
+    if (strategy != BGR_STRATEGY_COPY && strategy != BGR_STRATEGY_CLONE)
+        return fail(BGR_ERR_UNSUPPORTED, "only Copy/Clone strategies of POD types are supported (ReflectStrategy is out of scope)");
+    Column c;
+    c.name = type_name ? type_name : "";
+    c.elem_bytes = elem_bytes;
+    c.words = (elem_bytes + 3) / 4;
+    c.strategy = strategy;
+    e->cols.push_back(c);
+    *column_out = uint32_t(e->cols.size() - 1);
+    return BGR_OK;
+}
+
+BGR_API int bgr_checksum_component(bgr_engine* e, uint32_t column, uint32_t hash_kind, uint32_t byte_offset,
+                                   uint32_t byte_len, uint32_t flags) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    if (e->built) return fail(BGR_ERR_STATE, "checksums must be registered before bgr_build");
+    if (column >= e->cols.size()) return fail(BGR_ERR_INVALID_ARGUMENT, "unknown column");
+    Column& c = e->cols[column];
+    if (hash_kind != BGR_HASH_BYTES) return fail(BGR_ERR_INVALID_ARGUMENT, "unknown hash kind");
+    if (uint64_t(byte_offset) + byte_len > c.elem_bytes) return fail(BGR_ERR_INVALID_ARGUMENT, "hash range exceeds element");
+    if ((flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) && ((byte_offset | byte_len) & 3u))
+        return fail(BGR_ERR_INVALID_ARGUMENT, "finite-f32 assertion needs a 4-byte aligned range");
+    c.hash_kind = hash_kind; c.hash_off = byte_offset; c.hash_len = byte_len; c.hash_flags = flags;
+    return BGR_OK;
+}
+
+BGR_API int bgr_add_system(bgr_engine* e, uint32_t system, const uint32_t* columns, uint32_t n_columns,
+                           const uint32_t* params, uint32_t n_params) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    if (e->built) return fail(BGR_ERR_STATE, "systems must be added before bgr_build");
+    SystemReg s;
+    s.id = system;
+    for (uint32_t i = 0; i < n_columns; ++i) {
+        if (columns[i] >= e->cols.size()) return fail(BGR_ERR_INVALID_ARGUMENT, "system binds an unknown column");
+        s.cols.push_back(columns[i]);
+    }
+    for (uint32_t i = 0; i < n_params; ++i) s.params.push_back(params[i]);
+    auto need = [&](size_t nc, size_t np) { return s.cols.size() == nc && s.params.size() >= np; };
+    auto eb = [&](size_t i) { return e->cols[s.cols[i]].elem_bytes; };
+    switch (system) {
+    case BGR_SYS_PARTICLES_UPDATE:
+        if (!need(2, 0) || eb(0) != 40 || eb(1) != 12)
+            return fail(BGR_ERR_INVALID_ARGUMENT, "update_particles binds {Transform(40B), Velocity(12B)}");
+        break;
+    case BGR_SYS_PARTICLES_DESPAWN:
+        if (!need(1, 0) || eb(0) != 8) return fail(BGR_ERR_INVALID_ARGUMENT, "despawn_particles binds {Ttl(8B)}");
+        break;
+    case BGR_SYS_U32_ADD:
+    case BGR_SYS_U32_SATSUB_DESPAWN:
+        if (!need(1, 2) || (s.params[0] & 3u) || s.params[0] + 4 > eb(0))
+            return fail(BGR_ERR_INVALID_ARGUMENT, "u32 system binds {C} with params {aligned byte_offset, k}");
+        break;
+    case BGR_SYS_U32_STORE_CALL_COUNT:
+        if (!need(1, 1) || (s.params[0] & 3u) || s.params[0] + 4 > eb(0))
+            return fail(BGR_ERR_INVALID_ARGUMENT, "store_call_count binds {C} with params {aligned byte_offset}");
+        break;
+    case BGR_SYS_BOX_MOVE:
+        return fail(BGR_ERR_UNSUPPORTED, "move_cube_system (box_game) runs on the CPU plumbing config only; no GPU system yet");
+    default: return fail(BGR_ERR_INVALID_ARGUMENT, "unknown system id");
+    }
+    e->systems.push_back(std::move(s));
+    return BGR_OK;
+}
+
+BGR_API int bgr_build(bgr_engine* e) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    if (e->built) return fail(BGR_ERR_STATE, "bgr_build called twice");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    uint32_t plane = 0;
+    e->n_ck = 0;
+    for (Column& c : e->cols) {
+        c.first_plane = plane;
+        plane += c.words;
+        if (c.hash_kind != BGR_HASH_NONE) {
+            if (e->n_ck >= BGR_MAX_CHECKSUM_COLUMNS) return fail(BGR_ERR_CAPACITY, "too many checksummed columns");
+            c.ck_slot = int(e->n_ck++);
+        }
+    }
+    e->words = plane;
+    e->epad = (e->cfg.max_entities + 255u) & ~255u;
+    e->image_bytes = ((size_t(e->epad) * (size_t(e->words) * 4u + 1u)) + 255u) & ~size_t(255);
+    size_t total = e->image_bytes * (size_t(e->cfg.max_depth) + 1u);
+    CUDA_TRY(cudaMalloc(&e->arena, total));
+    CUDA_TRY(cudaMemsetAsync(e->arena, 0, total, e->stream));
+    CUDA_TRY(cudaMalloc(&e->d_kill, e->epad));
+    CUDA_TRY(cudaMemsetAsync(e->d_kill, 0, e->epad, e->stream));
+    CUDA_TRY(cudaMalloc(&e->d_accum, sizeof(unsigned long long) * kMaxSaves * kAccStride));
+    CUDA_TRY(cudaMemsetAsync(e->d_accum, 0, sizeof(unsigned long long) * kMaxSaves * kAccStride, e->stream));
+    CUDA_TRY(cudaMalloc(&e->d_ticket, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(e->d_ticket, 0, sizeof(unsigned int), e->stream));
+    for (int i = 0; i < bgr_engine::kBufs; ++i) {
+        CUDA_TRY(cudaHostAlloc(&e->h_out[i], sizeof(unsigned long long) * kMaxSaves * kAccStride, cudaHostAllocMapped));
+        std::memset(e->h_out[i], 0, sizeof(unsigned long long) * kMaxSaves * kAccStride);
+        CUDA_TRY(cudaHostGetDevicePointer(&e->d_out[i], e->h_out[i], 0));
+        CUDA_TRY(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
+    }
+    e->st.ring.reset(e->cfg.max_depth);
+    e->st.slot_rows.assign(e->cfg.max_depth, 0);
+    e->st.slot_elapsed_ns.assign(e->cfg.max_depth, 0);
+    detect_bundles(e);
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->built = true;
+    return BGR_OK;
+}
+
+BGR_API int bgr_spawn(bgr_engine* e, uint32_t count, uint32_t* first_row_out) {
+    if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
+    int rc = drain(e);
+    if (rc != BGR_OK) return rc;
+    if (uint64_t(e->st.n_rows) + count > e->cfg.max_entities) return fail(BGR_ERR_CAPACITY, "spawn exceeds max_entities");
+    uint32_t first = e->st.n_rows;
+    if (count) {
+        uint8_t* live = e->image(0);
+        for (uint32_t p = 0; p < e->words; ++p)
+            CUDA_TRY(cudaMemsetAsync(live + size_t(p) * e->epad * 4u + size_t(first) * 4u, 0, size_t(count) * 4u, e->stream));
+        CUDA_TRY(cudaMemsetAsync(live + size_t(e->words) * e->epad * 4u + first, 1, count, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    }
+    e->st.n_rows += count;
+    if (first_row_out) *first_row_out = first;
+    return BGR_OK;
+}
+
+BGR_API int bgr_despawn(bgr_engine* e, uint32_t row) {
+    if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
+    int rc = drain(e);
+    if (rc != BGR_OK) return rc;
+    if (row >= e->st.n_rows) return fail(BGR_ERR_INVALID_ARGUMENT, "row out of range");
+    CUDA_TRY(cudaMemsetAsync(e->image(0) + size_t(e->words) * e->epad * 4u + row, 0, 1, e->stream));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return BGR_OK;
+}
+
+BGR_API int bgr_row_count(bgr_engine* e, uint32_t* rows_out) {
+    if (!e || !rows_out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *rows_out = e->st.n_rows;
+    return BGR_OK;
+}
+
+BGR_API int bgr_active_count(bgr_engine* e, uint64_t* active_out) {
+    if (!e || !e->built || !active_out) return fail(BGR_ERR_STATE, "engine not built");
+    std::vector<uint8_t> a(e->st.n_rows);
+    int rc = read_alive_image(e, 0, 0, e->st.n_rows, e->st.n_rows, a.data());
+    if (rc != BGR_OK) return rc;
+    uint64_t n = 0;
+    for (uint8_t v : a) n += v ? 1 : 0;
+    *active_out = n;
+    return BGR_OK;
+}
+
+BGR_API int bgr_write_component(bgr_engine* e, uint32_t column, uint32_t first_row, uint32_t count, const void* host_src,
+                                uint32_t stride) {
+    if (!host_src && count) return fail(BGR_ERR_INVALID_ARGUMENT, "null host buffer");
+    return transfer_column(e, 0, column, first_row, count, const_cast<void*>(host_src), stride, true);
+}
+
+BGR_API int bgr_read_component(bgr_engine* e, uint32_t column, uint32_t first_row, uint32_t count, void* host_dst,
+                               uint32_t stride) {
+    if (!host_dst && count) return fail(BGR_ERR_INVALID_ARGUMENT, "null host buffer");
+    return transfer_column(e, 0, column, first_row, count, host_dst, stride, false);
+}
+
+BGR_API int bgr_read_alive(bgr_engine* e, uint32_t first_row, uint32_t count, uint8_t* host_dst) {
+    if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
+    return read_alive_image(e, 0, first_row, count, e->st.n_rows, host_dst);
+}
+
+BGR_API int bgr_rollback_frame_count(bgr_engine* e, int32_t* out) {
+    if (!e || !out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = e->st.frame_count; return BGR_OK;
+}
+BGR_API int bgr_set_rollback_frame_count(bgr_engine* e, int32_t frame) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    e->st.frame_count = frame; return BGR_OK;
+}
+BGR_API int bgr_confirmed_frame_count(bgr_engine* e, int32_t* out) {
+    if (!e || !out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = e->st.confirmed; return BGR_OK;
+}
+BGR_API int bgr_max_prediction_window(bgr_engine* e, uint32_t* out) {
+    if (!e || !out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = e->st.has_maxpred ? e->st.maxpred : 0; return BGR_OK;
+}
+
+BGR_API int bgr_set_depth(bgr_engine* e, uint32_t depth) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    e->st.has_maxpred = true; e->st.maxpred = depth;  // MaxPredictionWindow: sync_depth applies it before every save
+    e->st.ring.set_depth(depth);
+    return BGR_OK;
+}
+BGR_API int bgr_confirm(bgr_engine* e, int32_t confirmed_frame) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    e->st.confirmed = confirmed_frame;
+    e->st.ring.confirm(confirmed_frame);
+    return BGR_OK;
+}
+BGR_API int bgr_snapshot_frames(bgr_engine* e, int32_t* frames_out, uint32_t cap, uint32_t* n_out) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    std::vector<int32_t> f;
+    e->st.ring.frames(&f);
+    for (uint32_t i = 0; i < f.size() && i < cap && frames_out; ++i) frames_out[i] = f[i];
+    if (n_out) *n_out = uint32_t(f.size());
+    return BGR_OK;
+}
+
+BGR_API int bgr_peek(bgr_engine* e, int32_t frame, uint32_t column, uint32_t first_row, uint32_t count, void* host_dst,
+                     uint32_t stride, uint8_t* alive_dst, int32_t* found) {
+    if (!e || !e->built || !found) return fail(BGR_ERR_STATE, "engine not built");
+    uint32_t slot = 0;
+    if (!e->st.ring.peek(frame, &slot)) { *found = 0; return BGR_OK; }
+    *found = 1;
+    int rc = transfer_column(e, slot + 1, column, first_row, count, host_dst, stride, false);
+    if (rc != BGR_OK) return rc;
+    if (alive_dst) return read_alive_image(e, slot + 1, first_row, count, e->st.slot_rows[slot], alive_dst);
+    return BGR_OK;
+}
+
+BGR_API int bgr_submit_requests(bgr_engine* e, const bgr_session_info* session, const bgr_request* requests,
+                                uint32_t n_requests) {
+    return submit(e, session, requests, n_requests);
+}
+
+BGR_API int bgr_collect(bgr_engine* e, bgr_checksum* checksums_out, uint32_t checksums_cap, uint32_t* n_checksums_out) {
+    return collect(e, checksums_out, checksums_cap, n_checksums_out);
+}
+
+BGR_API int bgr_handle_requests(bgr_engine* e, const bgr_session_info* session, const bgr_request* requests,
+                                uint32_t n_requests, bgr_checksum* checksums_out, uint32_t checksums_cap,
+                                uint32_t* n_checksums_out) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    int rc = drain(e);
+    if (rc != BGR_OK) return rc;
+    rc = submit(e, session, requests, n_requests);
+    if (rc != BGR_OK) return rc;
+    return collect(e, checksums_out, checksums_cap, n_checksums_out);
+}
+
+BGR_API int bgr_save_world(bgr_engine* e, bgr_checksum* checksum_out) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    bgr_request rq;
+    std::memset(&rq, 0, sizeof rq);
+    rq.kind = BGR_REQ_SAVE; rq.frame = e->st.frame_count;
+    uint32_t n = 0;
+    return bgr_handle_requests(e, nullptr, &rq, 1, checksum_out, checksum_out ? 1 : 0, &n);
+}
+
+BGR_API int bgr_load_world(bgr_engine* e) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    bgr_request rq;
+    std::memset(&rq, 0, sizeof rq);
+    rq.kind = BGR_REQ_LOAD; rq.frame = e->st.frame_count;
+    uint32_t n = 0;
+    return bgr_handle_requests(e, nullptr, &rq, 1, nullptr, 0, &n);
+}
+
+BGR_API int bgr_advance_world(bgr_engine* e, const uint8_t* inputs, const uint8_t* status, uint32_t n_players) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    if (n_players > BGR_MAX_PLAYERS) return fail(BGR_ERR_INVALID_ARGUMENT, "n_players > BGR_MAX_PLAYERS");
+    bgr_request rq;
+    std::memset(&rq, 0, sizeof rq);
+    rq.kind = kReqAdvanceNoBump; rq.n_players = n_players;
+    for (uint32_t i = 0; i < n_players; ++i) { rq.inputs[i] = inputs ? inputs[i] : 0; rq.status[i] = status ? status[i] : 0; }
+    uint32_t n = 0;
+    return bgr_handle_requests(e, nullptr, &rq, 1, nullptr, 0, &n);
+}
+
+BGR_API int bgr_last_partials(bgr_engine* e, bgr_partial* out, uint32_t cap, uint32_t* n_out) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    for (uint32_t i = 0; i < e->last_partials.size() && i < cap && out; ++i) out[i] = e->last_partials[i];
+    if (n_out) *n_out = uint32_t(e->last_partials.size());
+    return BGR_OK;
+}
+
+BGR_API int bgr_fold_partials(const bgr_partial* combined, bgr_checksum* out) {
+    if (!combined || !out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    fold(*combined, out);
+    return BGR_OK;
+}
+
+BGR_API uint32_t bgr_ggrs_time_delta_bits(uint32_t fps, int32_t frame) {
+    if (fps == 0) return 0;
+    uint64_t f = uint64_t(int64_t(frame));
+    uint64_t now = f * 1000000000ULL / fps, prev = (f - 1) * 1000000000ULL / fps;
+    return f32_bits(duration_as_secs_f32(now - prev));
+}
+
+BGR_API int bgr_launch_count(bgr_engine* e, uint64_t* out) {
+    if (!e || !out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = e->launches; return BGR_OK;
+}
+BGR_API int bgr_slot_bytes(bgr_engine* e, uint64_t* out) {
+    if (!e || !out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = uint64_t(e->st.n_rows) * (uint64_t(e->words) * 4u + 1u); return BGR_OK;
+}
+BGR_API int bgr_last_path(bgr_engine* e, uint32_t* fused_out) {
+    if (!e || !fused_out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *fused_out = e->last_fused ? 1u : 0u; return BGR_OK;
+}
+BGR_API int bgr_synchronize(bgr_engine* e) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return BGR_OK;
+}
+
+// ---- host-side ring bookkeeping on its own (pure host logic; used by the "not gpu" KAT tests) ----
+struct bgr_ring { SlotRing r; };
+BGR_API bgr_ring* bgr_ring_create(uint32_t n_slots) { auto* r = new bgr_ring(); r->r.reset(n_slots); return r; }
+BGR_API void bgr_ring_destroy(bgr_ring* r) { delete r; }
+BGR_API uint32_t bgr_ring_depth(bgr_ring* r) { return r->r.depth(); }
+BGR_API int bgr_ring_set_depth(bgr_ring* r, uint32_t depth) { r->r.set_depth(depth); return BGR_OK; }
+BGR_API int bgr_ring_push(bgr_ring* r, int32_t frame, uint32_t* slot_out) {
+    uint32_t s = r->r.push(frame);
+    if (s == SlotRing::kNoSlot) return fail(BGR_ERR_CAPACITY, "ring out of slots");
+    if (slot_out) *slot_out = s;
+    return BGR_OK;
+}
+BGR_API int bgr_ring_confirm(bgr_ring* r, int32_t frame) { r->r.confirm(frame); return BGR_OK; }
+BGR_API int bgr_ring_rollback(bgr_ring* r, int32_t frame, uint32_t* slot_out) {
+    std::string err;
+    if (!r->r.rollback(frame, &err)) return fail(BGR_ERR_NO_SNAPSHOT, err);
+    uint32_t s = 0;
+    r->r.get(&s, nullptr);
+    if (slot_out) *slot_out = s;
+    return BGR_OK;
+}
+BGR_API int bgr_ring_get(bgr_ring* r, uint32_t* slot_out) {
+    std::string err;
+    uint32_t s = 0;
+    if (!r->r.get(&s, &err)) return fail(BGR_ERR_NO_SNAPSHOT, err);
+    if (slot_out) *slot_out = s;
+    return BGR_OK;
+}
+BGR_API int bgr_ring_peek(bgr_ring* r, int32_t frame, uint32_t* slot_out, int32_t* found) {
+    uint32_t s = 0;
+    bool ok = r->r.peek(frame, &s);
+    if (found) *found = ok ? 1 : 0;
+    if (ok && slot_out) *slot_out = s;
+    return BGR_OK;
+}
+
+}  // extern "C"

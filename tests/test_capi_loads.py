@@ -1,0 +1,65 @@
+"""CPU-only checks of the C-ABI library: it loads, exports every symbol the header declares, its
+host-only entry points work, and it refuses to run without a GPU instead of falling back."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from bevy_ggrs_b200 import capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_loads_and_binds_all_prototypes():
+    lib = capi.load_library()
+    assert lib.bgr_abi_version() == capi.BGR_ABI_VERSION
+
+
+def test_every_header_symbol_is_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "bevy_ggrs_b200.h")).read()
+    declared = set(re.findall(r"BGR_API\s+[\w\s\*]+?\b(bgr_\w+)\s*\(", hdr))
+    assert len(declared) >= 40
+    lib = capi.load_library()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(capi.PROTOTYPES), declared ^ set(capi.PROTOTYPES)
+
+
+def test_struct_layouts_match_the_header():
+    assert C.sizeof(capi.bgr_request) == 28
+    assert C.sizeof(capi.bgr_session_info) == 16
+    assert C.sizeof(capi.bgr_checksum) == 24
+    assert C.sizeof(capi.bgr_partial) == 24 + 8 * capi.BGR_MAX_CHECKSUM_COLUMNS
+    assert C.sizeof(capi.bgr_config) == 40
+
+
+def test_ggrs_time_delta_bits_matches_oracle(oracle_lib):
+    lib = capi.load_library()
+    for fps in (30, 60, 144):
+        for frame in range(1, 400):
+            assert lib.bgr_ggrs_time_delta_bits(fps, frame) == oracle_lib.orc_ggrs_time_delta_bits(fps, frame)
+
+
+def test_fold_partials_matches_golden_composition():
+    """checksum = entity_part ^ part(col0) ^ part(col1) with SURVEY §8c vectors."""
+    lib = capi.load_library()
+    p = capi.bgr_partial()
+    p.frame, p.n_columns, p.active, p.total = 7, 1, 2, 2
+    p.xor_[0] = 0x27EA43A38B7BD31A  # per-entity hash of translation (1,2,3), order 0
+    cs = capi.bgr_checksum()
+    assert lib.bgr_fold_partials(C.byref(p), C.byref(cs)) == 0
+    assert cs.hi == 0 and cs.frame == 7
+    assert cs.lo == 0x92B817690FA6BA0D ^ 0xC91E3FA134760483
+    p.n_columns = 0
+    lib.bgr_fold_partials(C.byref(p), C.byref(cs))
+    assert cs.lo == 0x92B817690FA6BA0D
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="GPU present")
+def test_no_gpu_fails_loudly_no_cpu_fallback():
+    from bevy_ggrs_b200.engine import Engine
+    with pytest.raises(capi.BgrError) as ei:
+        Engine(max_entities=16)
+    assert ei.value.status == capi.BGR_ERR_CUDA
+    assert "no CPU fallback" in str(ei.value)
