@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — rollback frames/s of the snapshot + checksum + re-simulation hot path.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (CUDA engine through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle port) on host cores
+
+Metric (BASELINE.json): "rollback frames/sec at 1M entities x 8-frame window".
+One step = one SyncTest tick of the stress-test world at steady state: the request vector
+[Load(f-8), Adv, Save, Adv, ..., Save(f), Adv] = 1 LoadGameState + 8 SaveGameState (each with its
+desync checksum) + 9 AdvanceFrame, i.e. 9 rollback frames per step.
+
+    value        device throughput: K ticks enqueued back to back (state resident in HBM), CUDA events
+    e2e          the same metric through the synchronous C-ABI call a user makes
+                 (bgr_handle_requests: host request array in, host checksums out, every tick)
+    roofline     the fused kernel k_particles_program against the measured HBM copy bandwidth
+    cpu_baseline the oracle port (faithful restatement of the reference's data structures) on host cores
+
+N > 1 (torchrun): entity-range shards, one engine per GPU, 1M entities PER GPU (weak scaling);
+the only exchange is an NCCL all_gather of the per-save checksum partials (XOR has no NCCL reduce op).
+value = N x ticks/s x 9 = 1M-entity rollback frames per second summed over the shards.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENTITIES = 1_000_000
+CHECK_DISTANCE = 8
+MAX_PREDICTION = 9       # ggrs requires check_distance < max_prediction
+SEED = 0xB200
+WORKLOADS = {
+    # name: (entities, check_distance, max_prediction)
+    "stress_1m_d8": (1_000_000, 8, 9),
+    "stress_100k_d8": (100_000, 8, 9),
+    "stress_1m_d16": (1_000_000, 16, 17),
+    "stress_10m_d32": (10_000_000, 32, 33),
+}
+
+
+def measured_hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_world(world, n, d, seed):
+    from bevy_ggrs_b200.stress import populate, register_particles, synth_particles
+    cols = register_particles(world)
+    world.build()
+    tf, vel, ttl = synth_particles(n, seed, 300 + d + 100000, 300 + d + 100000)  # nothing despawns inside the run
+    populate(world, cols, tf, vel, ttl)
+    return cols
+
+
+def pregenerate_ticks(n_ticks, d, maxp, players=2):
+    """Request vectors of a SyncTest session (they do not depend on checksum values unless a
+    mismatch occurs, which is checked afterwards)."""
+    from bevy_ggrs_b200 import capi
+    from bevy_ggrs_b200.session import SAVE, SyncTestSession, count_advances
+    sess = SyncTestSession(players, d, maxp, input_delay=2)
+    ticks = []
+    for t in range(n_ticks):
+        for h in range(players):
+            sess.add_local_input(h, (1 << 5) if (t + h) % 3 == 0 else 0)  # INPUT_NOOP schedule
+        reqs = sess.advance_frame()
+        for r in reqs:
+            if r.kind == SAVE:
+                sess.save_cell(r.frame, 0)
+        ticks.append((capi.make_requests(reqs), len(reqs), count_advances(reqs), capi.make_session_info(sess.info()),
+                      [r.frame for r in reqs if r.kind == SAVE]))
+    return ticks
+
+
+def check_synctest_consistency(history):
+    """SyncTest property: every re-save of a frame reports the checksum first recorded for it."""
+    first = {}
+    for frame, cs in history:
+        if first.setdefault(frame, cs) != cs:
+            return False
+    return True
+
+
+# =================================================================================================
+# our arm
+# =================================================================================================
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from bevy_ggrs_b200 import capi
+    from bevy_ggrs_b200.engine import Engine, fold_partials
+
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world_size != args.gpus and world_size > 1:
+        args.gpus = world_size
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, d, maxp = WORKLOADS[args.workload]
+    K, W = args.steps, max(3, args.warmup)
+    stream = torch.cuda.Stream(device=dev)
+    sharded = world_size > 1
+    eng = Engine(max_entities=n, max_depth=maxp, fps=60, device=local_rank,
+                 flags=capi.BGR_CFG_SHARDED if sharded else 0, order_base=rank * n, stream=stream.cuda_stream)
+    build_world(eng, n, d, SEED + rank)
+    slot_bytes = eng.slot_bytes()
+
+    fill = d + 2                      # ticks until the request vector has its steady-state shape
+    ticks = pregenerate_ticks(fill + W + K + K, d, maxp)
+    history = []
+
+    def fold_all(partials_list):
+        """cross-shard fold: all_gather the raw partials (u64 XORs + counts) over NCCL, fold locally."""
+        out = []
+        if not sharded:
+            return partials_list
+        k = len(partials_list)
+        cols = capi.BGR_MAX_CHECKSUM_COLUMNS
+        import numpy as np
+        buf = np.zeros((k, cols + 2), dtype=np.int64)
+        for i, p in enumerate(partials_list):
+            buf[i, :cols] = np.array([p.xor_[c] for c in range(cols)], dtype=np.uint64).view(np.int64)
+            buf[i, cols] = p.active
+            buf[i, cols + 1] = p.total
+        t = torch.from_numpy(buf).to(dev, non_blocking=False)
+        g = torch.empty((world_size,) + tuple(t.shape), dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(g, t)
+        gh = g.cpu().numpy().view(np.uint64)
+        for i, p in enumerate(partials_list):
+            q = capi.bgr_partial()
+            q.frame, q.n_columns = p.frame, p.n_columns
+            q.active = int(gh[:, i, cols].sum())
+            q.total = int(gh[:, i, cols + 1].sum())
+            for c in range(cols):
+                q.xor_[c] = int(np.bitwise_xor.reduce(gh[:, i, c]))
+            out.append((p.frame, fold_partials(q)))
+        return out
+
+    def collect_one():
+        cs = eng.collect()
+        if sharded:
+            history.extend(fold_all(eng.last_partials()))
+        else:
+            history.extend(cs)
+
+    def run_pipelined(tick_list):
+        inflight = 0
+        for arr, nreq, _, info, _ in tick_list:
+            eng.submit_prepared(info, arr, nreq)
+            inflight += 1
+            if inflight > 2:
+                collect_one()
+                inflight -= 1
+        while inflight:
+            collect_one()
+            inflight -= 1
+
+    def barrier():
+        torch.cuda.synchronize()
+        if sharded:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        run_pipelined(ticks[:fill + W])           # ring fill + warm-up (>= 3 steady-state ticks)
+        barrier()
+        # ---------------- value: device-timed, K ticks back to back ----------------
+        timed = ticks[fill + W: fill + W + K]
+        adv_per_tick = timed[0][2]
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        l0 = eng.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        run_pipelined(timed)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        launches = eng.launch_count() - l0
+        clocks = sampler.stop() if rank == 0 else None
+        if sharded:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        # ---------------- e2e: synchronous bgr_handle_requests per tick, host buffers ----------------
+        e2e_ticks = ticks[fill + W + K: fill + W + K + K]
+        lib = capi.load_library()
+        out = (capi.bgr_checksum * capi.BGR_MAX_REQUESTS)()
+        nout = C.c_uint32()
+        barrier()
+        t0 = time.perf_counter()
+        for arr, nreq, _, info, _ in e2e_ticks:
+            st = lib.bgr_handle_requests(eng._h, C.byref(info), arr, nreq, out, capi.BGR_MAX_REQUESTS, C.byref(nout))
+            if st != 0:
+                raise RuntimeError(lib.bgr_last_error().decode())
+            if sharded:
+                history.extend(fold_all(eng.last_partials()))
+            else:
+                history.extend((out[i].frame, (out[i].hi << 64) | out[i].lo) for i in range(nout.value))
+        e2e_s = time.perf_counter() - t0
+        if sharded:
+            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        h2d = C.sizeof(capi.bgr_request) * e2e_ticks[0][1] + C.sizeof(capi.bgr_session_info)
+        d2h = 64 * len(e2e_ticks[0][4])  # one 8 x u64 result row per SaveGameState, written to pinned host memory
+
+    consistent = check_synctest_consistency(history)
+    fused = eng.last_path_fused()
+
+    # ---------------- roofline of the dominant (only) kernel ----------------
+    ms_per_step = ms / K
+    alg_bytes = (d + 2) * slot_bytes          # read 1 slot + write d slots + write live
+    achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    peak, peak_src = measured_hbm_peak()
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get(args.workload)
+        except Exception:
+            traffic = None
+
+    # ---------------- CPU baseline (rank 0, N == 1 only): oracle port on host cores ----------------
+    cpu = None
+    if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
+        cpu = run_cpu_sample(n, d, maxp, rollback_ticks=3)
+
+    if rank == 0:
+        value = world_size * adv_per_tick * K / (ms * 1e-3)
+        line = {
+            "metric": "rollback frames/sec at 1M entities x 8-frame window (SyncTest: 1 Load + 8 Save+checksum + 9 Advance per tick)",
+            "value": value, "unit": "rollback frames/s", "n_gpus": world_size, "steps": K, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 (seahash) + f32 (particles, no FMA) + u8 copy", "data": "synthetic (numpy PCG64 seed 0xB200; BASELINE.md shapes)",
+            "config": {"workload": args.workload, "entities_per_gpu": n, "check_distance": d, "max_prediction": maxp,
+                       "columns": "Transform40+Velocity12+Ttl8+alive1 = 61 B/entity/slot", "checksum": "every saved frame",
+                       "advances_per_step": adv_per_tick, "l2": "inputs larger than L2: each tick reads 1 slot and writes 9 images of "
+                       f"{slot_bytes/1e6:.0f} MB (ring {maxp} slots)", "path": "fused" if fused else "stepwise",
+                       "sharding": f"entity-range x{world_size}, all_gather of checksum partials" if sharded else "none"},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "e2e": {"value": world_size * adv_per_tick * K / e2e_s, "unit": "rollback frames/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "note": "bgr_handle_requests per tick: request vector from host memory, checksums to host memory; "
+                            "component columns live in HBM by design and never cross"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_particles_program",
+                         "algorithmic_bytes_per_launch": alg_bytes},
+            "synctest_consistent": consistent,
+        }
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if sharded:
+        dist.destroy_process_group()
+    if not consistent:
+        sys.exit(3)
+
+
+# =================================================================================================
+# the reference's CPU path (oracle port) — test infrastructure timed as the baseline
+# =================================================================================================
+def run_cpu_sample(n, d, maxp, rollback_ticks, entities=None, warm_ticks=0):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_backend import OracleWorld
+    from bevy_ggrs_b200.session import SAVE, SyncTestSession, count_advances
+    e = entities or n
+    threads = max(1, min(os.cpu_count() or 1, 8))
+    orc = OracleWorld(fps=60, save_threads=threads)
+    build_world(orc, e, d, SEED)
+    sess = SyncTestSession(2, d, maxp, input_delay=2)
+    total_ns, total_adv, timed = 0, 0, 0
+    t = 0
+    while timed < rollback_ticks:
+        for h in range(2):
+            sess.add_local_input(h, (1 << 5) if (t + h) % 3 == 0 else 0)
+        reqs = sess.advance_frame()
+        cs = orc.handle_requests(sess.info(), reqs)
+        for frame, c in cs:
+            sess.save_cell(frame, c)
+        if reqs[0].kind == 1:  # steady-state rollback tick
+            if warm_ticks > 0:
+                warm_ticks -= 1
+            else:
+                total_ns += orc.last_elapsed_ns
+                total_adv += count_advances(reqs)
+                timed += 1
+        t += 1
+    orc.close()
+    fps = total_adv / (total_ns * 1e-9)
+    scaled = fps * (e / n)
+    return {"value": scaled, "unit": "rollback frames/s", "cores": threads, "kind": "port",
+            "sample": f"{timed} steady-state SyncTest ticks (d={d}) of the oracle port at {e} entities"
+                      + ("" if e == n else f", scaled by {e}/{n} to the {n}-entity metric")
+                      + "; per-type save/checksum systems overlapped on the stated cores like Bevy's multithreaded executor, "
+                        "AdvanceWorld single-threaded (lib.rs:237)",
+            "seconds_per_tick": total_ns * 1e-9 / timed}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n, d, maxp = WORKLOADS[args.workload]
+    K, W = args.steps, args.warmup
+    # bound the whole run to a few minutes: ~2.8 s per 1M-entity tick on 8 cores
+    budget_s = 150.0
+    est = 3.0 * (K + W) + 6.0
+    e = n if est <= budget_s else max(50_000, int(n * budget_s / est) // 1000 * 1000)
+    r = run_cpu_sample(n, d, maxp, rollback_ticks=K, entities=e, warm_ticks=W)
+    line = {
+        "impl": "reference",
+        "metric": "rollback frames/sec at 1M entities x 8-frame window (SyncTest: 1 Load + 8 Save+checksum + 9 Advance per tick)",
+        "value": r["value"], "unit": "rollback frames/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+        "ms_per_step": r["seconds_per_tick"] * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (seahash) + f32 + bytes", "data": "synthetic (same generator and seed as the GPU arm)",
+        "config": {"workload": args.workload, "entities_per_gpu": n, "check_distance": d, "max_prediction": maxp,
+                   "note": "/root/reference is Rust and cannot be built in this image (no rustc/cargo): this arm times the "
+                           "oracle port, a faithful CPU restatement of the reference's data structures and loops"},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": r["value"], "unit": "rollback frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="stress_1m_d8", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
