@@ -20,6 +20,7 @@
 #include "kernels.cuh"
 #include "ring.hpp"
 #include "seahash.cuh"
+#include "tma_copy.cuh"
 
 using namespace bgr;
 
@@ -121,6 +122,8 @@ struct bgr_engine {
     uint32_t bt = 0, bv = 0, bl = 0;
     std::vector<uint16_t> passive;
     int tune_vec = 4, tune_block = 256, tune_bps = 0;
+    int tune_tma = 1;          // stepwise Save/Load through the TMA-staged bulk-copy kernel
+    uint32_t tma_tile = 0;     // rows per TMA tile (0: schema too wide for 3 stages of shared memory)
     int occ_cache[3][2] = {{0, 0}, {0, 0}, {0, 0}};
 
     uint8_t* image(uint32_t idx) const { return arena + size_t(idx) * image_bytes; }
@@ -295,6 +298,37 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// launch: TMA-staged image copy (+ fused checksum for a Save)
+// ---------------------------------------------------------------------------------------------
+int launch_tma(bgr_engine* e, const uint8_t* src, uint8_t* dst, uint32_t n_rows_src, uint32_t n_rows_copy, bool save,
+               unsigned long long* acc, bool store) {
+    TmaCopyParams tp;
+    std::memset(&tp, 0, sizeof tp);
+    tp.src = src; tp.dst = dst;
+    tp.order_base = e->cfg.order_base;
+    tp.accum = save ? acc : nullptr;
+    tp.out = nullptr; tp.ticket = e->d_ticket;
+    tp.epad = e->epad; tp.words = e->words; tp.tile_rows = e->tma_tile;
+    tp.n_rows_src = n_rows_src; tp.n_rows_copy = n_rows_copy;
+    tp.count_alive = save ? 1u : 0u;
+    tp.store = store ? 1u : 0u;
+    if (save)
+        for (const Column& c : e->cols)
+            if (c.hash_kind != BGR_HASH_NONE) {
+                HashSpec& h = tp.hash[tp.n_hash++];
+                h.first_plane = c.first_plane; h.off = c.hash_off; h.len = c.hash_len;
+                h.finite = c.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32; h.slot = uint32_t(c.ck_slot);
+            }
+    uint32_t n_tiles = (n_rows_copy + e->tma_tile - 1) / e->tma_tile;
+    uint32_t grid = std::max(1u, std::min(n_tiles, uint32_t(e->num_sms)));
+    size_t smem = size_t(kTmaStages) * e->tma_tile * (size_t(e->words) * 4u + 1u);
+    k_image_tma<<<grid, kTmaBlock, smem, e->stream>>>(tp);
+    CUDA_TRY(cudaGetLastError());
+    e->launches += 1;
+    return BGR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // launch: stepwise path (generic schemas / systems)
 // ---------------------------------------------------------------------------------------------
 int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
@@ -305,6 +339,11 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
         switch (op.kind) {
         case OP_SAVE: {
             unsigned long long* acc = e->d_accum + size_t(op.save_index) * kAccStride;
+            if (e->tune_tma && e->tma_tile) {
+                int rc = launch_tma(e, live, e->image(op.image), op.n_rows, op.n_rows, true, acc, !(op.flags & OPF_NO_STORE));
+                if (rc != BGR_OK) return rc;
+                break;
+            }
             bool counted = false;
             for (const Column& c : e->cols) {
                 if (c.hash_kind == BGR_HASH_NONE) continue;
@@ -329,7 +368,10 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
         }
         case OP_LOAD: {
             uint32_t n_copy = std::max(op.n_rows, live_rows);
-            if (n_copy > 0) {
+            if (n_copy > 0 && e->tune_tma && e->tma_tile) {
+                int rc = launch_tma(e, e->image(op.image), live, op.n_rows, n_copy, false, nullptr, true);
+                if (rc != BGR_OK) return rc;
+            } else if (n_copy > 0) {
                 k_copy_image<<<e->grid_for((n_copy + 3) / 4, 256), 256, 0, e->stream>>>(
                     e->image(op.image), live, e->epad, e->words, op.n_rows, n_copy);
                 e->launches += 1;
@@ -576,6 +618,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_vec = env_int("BGR_TUNE_VEC", 4);
     e->tune_block = env_int("BGR_TUNE_BLOCK", 256);
     e->tune_bps = env_int("BGR_TUNE_BPS", 0);
+    e->tune_tma = env_int("BGR_TUNE_TMA", 1);
     if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 4;
     if (e->tune_block != 128 && e->tune_block != 256) e->tune_block = 256;
     e->st.confirmed = 0;
@@ -704,6 +747,16 @@ BGR_API int bgr_build(bgr_engine* e) {
     e->st.slot_rows.assign(e->cfg.max_depth, 0);
     e->st.slot_elapsed_ns.assign(e->cfg.max_depth, 0);
     detect_bundles(e);
+    {   // TMA tile: 3 stages of (4*W+1) bytes per row must fit ~200 KB of shared memory
+        size_t per_row = size_t(e->words) * 4u + 1u;
+        size_t rows = (200u * 1024u) / (size_t(kTmaStages) * per_row);
+        rows = std::min<size_t>(rows & ~size_t(255), 2048);
+        e->tma_tile = uint32_t(rows);
+        if (e->tma_tile) {
+            size_t smem = size_t(kTmaStages) * e->tma_tile * per_row;
+            CUDA_TRY(cudaFuncSetAttribute(k_image_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        }
+    }
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->built = true;
     return BGR_OK;
