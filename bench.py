@@ -172,30 +172,8 @@ def run_ours(args):
 
     def fold_all(partials_list):
         """cross-shard fold: all_gather the raw partials (u64 XORs + counts) over NCCL, fold locally."""
-        out = []
-        if not sharded:
-            return partials_list
-        k = len(partials_list)
-        cols = capi.BGR_MAX_CHECKSUM_COLUMNS
-        import numpy as np
-        buf = np.zeros((k, cols + 2), dtype=np.int64)
-        for i, p in enumerate(partials_list):
-            buf[i, :cols] = np.array([p.xor_[c] for c in range(cols)], dtype=np.uint64).view(np.int64)
-            buf[i, cols] = p.active
-            buf[i, cols + 1] = p.total
-        t = torch.from_numpy(buf).to(dev, non_blocking=False)
-        g = torch.empty((world_size,) + tuple(t.shape), dtype=torch.int64, device=dev)
-        dist.all_gather_into_tensor(g, t)
-        gh = g.cpu().numpy().view(np.uint64)
-        for i, p in enumerate(partials_list):
-            q = capi.bgr_partial()
-            q.frame, q.n_columns = p.frame, p.n_columns
-            q.active = int(gh[:, i, cols].sum())
-            q.total = int(gh[:, i, cols + 1].sum())
-            for c in range(cols):
-                q.xor_[c] = int(np.bitwise_xor.reduce(gh[:, i, c]))
-            out.append((p.frame, fold_partials(q)))
-        return out
+        from bevy_ggrs_b200.sharded import all_fold
+        return all_fold(partials_list, device=dev)
 
     def collect_one():
         cs = eng.collect()
@@ -288,6 +266,10 @@ def run_ours(args):
     cpu = None
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         cpu = run_cpu_sample(n, d, maxp, rollback_ticks=3)
+    snap = None
+    if rank == 0 and world_size == 1:
+        eng.close()
+        snap = snapshot_bench(n, maxp, local_rank)
 
     if rank == 0:
         value = world_size * adv_per_tick * K / (ms * 1e-3)
@@ -314,12 +296,59 @@ def run_ours(args):
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if snap:
+            line["snapshot_save_restore"] = snap
         print(json.dumps(line), flush=True)
     eng.close()
     if sharded:
         dist.destroy_process_group()
     if not consistent:
         sys.exit(3)
+
+
+def snapshot_bench(n, maxp, device_index, iters=50):
+    """M2 of BASELINE.md: snapshot save + restore GB/s = 4*S*E / (t_save + t_load), one request per launch.
+    Two implementations of the same C-ABI calls are timed: the fused program kernel with a one-op
+    program, and the TMA-staged (cp.async.bulk) image copy of the stepwise path."""
+    import torch
+    from bevy_ggrs_b200 import capi
+    from bevy_ggrs_b200.engine import Engine
+    from bevy_ggrs_b200.session import LOAD, SAVE, Request
+    out = {}
+    peak, _ = measured_hbm_peak()
+    for name, flags in (("fused_program", 0), ("tma_bulk_copy", capi.BGR_CFG_FORCE_STEPWISE)):
+        stream = torch.cuda.Stream()
+        eng = Engine(max_entities=n, max_depth=2, fps=60, device=device_index, flags=flags, stream=stream.cuda_stream)
+        build_world(eng, n, 8, SEED)
+        info = capi.make_session_info((0, 0, 0, 0))
+        save = capi.make_requests([Request(SAVE, 0)])
+        load = capi.make_requests([Request(LOAD, 0)])
+        res = {}
+        with torch.cuda.stream(stream):
+            for label, arr in (("save", save), ("load", load)):
+                for _ in range(5):
+                    eng.submit_prepared(info, arr, 1); eng.collect()
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+                inflight = 0
+                for _ in range(iters):
+                    eng.submit_prepared(info, arr, 1)
+                    inflight += 1
+                    if inflight > 2:
+                        eng.collect(); inflight -= 1
+                while inflight:
+                    eng.collect(); inflight -= 1
+                e1.record(stream)
+                torch.cuda.synchronize()
+                res[label + "_us"] = e0.elapsed_time(e1) * 1e3 / iters
+        sb = eng.slot_bytes()
+        gbps = 4 * sb / ((res["save_us"] + res["load_us"]) * 1e-6) / 1e9
+        res.update({"gb_per_s": gbps, "frac_of_measured_hbm": gbps / peak, "slot_bytes": sb,
+                    "note": "2*S*E bytes per save (with checksum) and per load; 61 MB images fit L2 (126 MB): see ncu dram bytes"})
+        out[name] = res
+        eng.close()
+    return out
 
 
 # =================================================================================================

@@ -97,10 +97,12 @@ struct bgr_engine {
     uint32_t n_ck = 0;
     bool built = false;
 
-    uint32_t epad = 0, words = 0;
+    uint32_t epad = 0, words = 0, tile_bytes = 0, n_tiles_cap = 0;
     size_t image_bytes = 0;
-    uint8_t* arena = nullptr;  // image 0 = live, image s+1 = slot s
+    uint8_t* arena = nullptr;  // image 0 = live, image s+1 = slot s (tile-planar, kernels.cuh)
     uint8_t* d_kill = nullptr;
+    uint8_t* d_stage = nullptr;  // device staging for ECS column <-> image transposition
+    size_t stage_cap = 0;
 
     HostState st;
 
@@ -121,12 +123,17 @@ struct bgr_engine {
     bool bundle_particles = false;
     uint32_t bt = 0, bv = 0, bl = 0;
     std::vector<uint16_t> passive;
-    int tune_vec = 4, tune_block = 256, tune_bps = 0;
+    std::vector<PassiveRun> runs;
+    uint32_t passive_bytes = 0;
+    bool bundle_static_ck = false;  // both columns checksummed with the finite assertion: fully specialised kernel
+    int tune_vec = 2, tune_minb = 1, tune_bps = 0, tune_passive_tma = 1;
     int tune_tma = 1;          // stepwise Save/Load through the TMA-staged bulk-copy kernel
-    uint32_t tma_tile = 0;     // rows per TMA tile (0: schema too wide for 3 stages of shared memory)
-    int occ_cache[3][2] = {{0, 0}, {0, 0}, {0, 0}};
+    uint32_t tma_stage_tiles = 0;  // tiles per TMA stage (0: schema too wide for 3 stages of shared memory)
+    int occ_cache[3][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
 
     uint8_t* image(uint32_t idx) const { return arena + size_t(idx) * image_bytes; }
+    uint32_t image_off256(uint32_t idx) const { return uint32_t((size_t(idx) * image_bytes) >> 8); }
+    uint32_t tiles_for(uint32_t rows) const { return (rows + kTileRows - 1) / kTileRows; }
     uint32_t grid_for(uint32_t n, uint32_t per_block) const {
         uint32_t need = (n + per_block - 1) / per_block;
         uint32_t cap = uint32_t(num_sms) * 8u;
@@ -189,9 +196,9 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
             if (slot == SlotRing::kNoSlot)
                 return fail(BGR_ERR_CAPACITY, "snapshot ring needs more frame slots than bgr_config.max_depth");
             op.kind = OP_SAVE;
-            if (slot == SlotRing::kNoSlot - 1) { op.flags |= OPF_NO_STORE; op.image = 0; }
+            if (slot == SlotRing::kNoSlot - 1) { op.flags |= OPF_NO_STORE; op.image_off256 = 0; }
             else {
-                op.image = slot + 1;
+                op.image_off256 = e->image_off256(slot + 1);
                 s.slot_rows[slot] = s.n_rows;
                 s.slot_elapsed_ns[slot] = s.elapsed_ns;
             }
@@ -211,7 +218,7 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
             s.n_rows = s.slot_rows[slot];
             s.elapsed_ns = s.slot_elapsed_ns[slot];
             op.kind = OP_LOAD;
-            op.image = slot + 1;
+            op.image_off256 = e->image_off256(slot + 1);
             op.n_rows = s.n_rows;
             if (pg.n_ops == 0) pg.first_is_load = true;
             pg.has_load = true;
@@ -247,18 +254,21 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
 // ---------------------------------------------------------------------------------------------
 // launch: fused bundle kernel
 // ---------------------------------------------------------------------------------------------
-template <int VEC, int BLOCK>
-int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int bi) {
-    if (e->occ_cache[vi][bi] == 0) {
+template <int VEC, bool STATIC_CK, int MINB>
+int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int mi) {
+    auto kern = k_particles_program<VEC, STATIC_CK, MINB>;
+    constexpr int BLOCK = kTileRows / VEC;
+    const size_t smem = (pp.flags & PF_PASSIVE_TMA) ? size_t(2) * pp.passive_bytes : 0;
+    if (e->occ_cache[vi][si][mi] == 0) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_particles_program<VEC, BLOCK>, BLOCK, 0));
-        e->occ_cache[vi][bi] = std::max(1, nb);
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BLOCK, smem));
+        e->occ_cache[vi][si][mi] = std::max(1, nb);
     }
-    int bps = e->tune_bps > 0 ? std::min(e->tune_bps, e->occ_cache[vi][bi]) : e->occ_cache[vi][bi];
-    uint32_t n_groups = (pp.max_rows + VEC - 1) / VEC;
-    uint32_t need = (n_groups + BLOCK - 1) / BLOCK;
-    uint32_t grid = std::max(1u, std::min(need, uint32_t(e->num_sms * bps)));
-    k_particles_program<VEC, BLOCK><<<grid, BLOCK, 0, e->stream>>>(pp);
+    int bps = e->occ_cache[vi][si][mi];
+    if (e->tune_bps > 0) bps = std::min(e->tune_bps, bps);
+    uint32_t grid = std::max(1u, std::min(pp.n_tiles, uint32_t(e->num_sms * bps)));
+    kern<<<grid, BLOCK, smem, e->stream>>>(pp);
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
     return BGR_OK;
@@ -268,33 +278,47 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
     ProgramParams pp;
     std::memset(&pp, 0, sizeof pp);
     pp.arena = e->arena;
-    pp.image_bytes = e->image_bytes;
     pp.order_base = e->cfg.order_base;
     pp.accum = e->d_accum;
     pp.out = e->d_out[buf];
     pp.ticket = e->d_ticket;
-    pp.epad = e->epad; pp.words = e->words;
+    pp.words = e->words; pp.tile_bytes = e->tile_bytes;
+    pp.n_tiles = std::max(1u, e->tiles_for(pg.max_rows));  // at least one tile so the result block is published
     pp.n_ops = pg.n_ops; pp.n_saves = pg.n_saves;
-    pp.max_rows = pg.max_rows; pp.live_rows = pg.live_rows;
+    pp.live_rows = pg.live_rows;
     pp.flags = 0;
     if (!pg.first_is_load) pp.flags |= PF_READ_LIVE;
     if (pg.has_load || pg.has_advance) pp.flags |= PF_WRITE_LIVE_ACTIVE;
     if (pg.has_load) pp.flags |= PF_WRITE_LIVE_PASSIVE;
+    uint32_t n_loads = 0;
+    for (uint32_t i = 0; i < pg.n_ops; ++i) n_loads += (pg.ops[i].kind == OP_LOAD);
+    const bool simple = n_loads == 0 || (n_loads == 1 && pg.first_is_load);
+    if (simple && e->tune_passive_tma && !e->runs.empty() && 2u * e->passive_bytes <= 96u * 1024u) pp.flags |= PF_PASSIVE_TMA;
     const Column& ct = e->cols[e->bt]; const Column& cv = e->cols[e->bv];
-    if (ct.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_T; if (ct.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_CK_T_FINITE; pp.ck_t_slot = uint32_t(ct.ck_slot); }
-    if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_CK_V_FINITE; pp.ck_v_slot = uint32_t(cv.ck_slot); }
-    pp.t_plane = ct.first_plane; pp.v_plane = cv.first_plane; pp.l_plane = e->cols[e->bl].first_plane;
+    if (ct.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_T; if (ct.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_CK_FIN; pp.ck_t_slot = uint32_t(ct.ck_slot); }
+    if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_CK_FIN; pp.ck_v_slot = uint32_t(cv.ck_slot); }
+    pp.t_off = ct.first_plane * kPlaneBytes; pp.v_off = cv.first_plane * kPlaneBytes;
+    pp.l_off = e->cols[e->bl].first_plane * kPlaneBytes; pp.alive_off = e->words * kPlaneBytes;
+    pp.n_runs = uint32_t(e->runs.size()); pp.passive_bytes = e->passive_bytes;
+    for (size_t i = 0; i < e->runs.size(); ++i) pp.runs[i] = e->runs[i];
     pp.n_passive = uint32_t(e->passive.size());
     for (size_t i = 0; i < e->passive.size(); ++i) pp.passive[i] = e->passive[i];
     std::memcpy(pp.ops, pg.ops, sizeof(Op) * pg.n_ops);
-    if (pp.max_rows == 0) pp.max_rows = 1;  // still run one group so the result block is published
-    int v = e->tune_vec, b = e->tune_block;
-    if (v == 1 && b == 128) return launch_particles<1, 128>(e, pp, 0, 0);
-    if (v == 1) return launch_particles<1, 256>(e, pp, 0, 1);
-    if (v == 2 && b == 128) return launch_particles<2, 128>(e, pp, 1, 0);
-    if (v == 2) return launch_particles<2, 256>(e, pp, 1, 1);
-    if (b == 128) return launch_particles<4, 128>(e, pp, 2, 0);
-    return launch_particles<4, 256>(e, pp, 2, 1);
+    const int v = e->tune_vec;
+    const bool st = e->bundle_static_ck;
+    const bool hi = e->tune_minb > 1;
+#define BGR_LAUNCH(VEC, VI, MINB_HI)                                                                       \
+    if (v == VEC) {                                                                                        \
+        if (st && hi) return launch_particles<VEC, true, MINB_HI>(e, pp, VI, 1, 1);                        \
+        if (st) return launch_particles<VEC, true, 1>(e, pp, VI, 1, 0);                                    \
+        if (hi) return launch_particles<VEC, false, MINB_HI>(e, pp, VI, 0, 1);                             \
+        return launch_particles<VEC, false, 1>(e, pp, VI, 0, 0);                                           \
+    }
+    BGR_LAUNCH(1, 0, 2)
+    BGR_LAUNCH(4, 2, 6)
+    BGR_LAUNCH(2, 1, 4)
+#undef BGR_LAUNCH
+    return fail(BGR_ERR_STATE, "bad BGR_TUNE_VEC");
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -307,9 +331,9 @@ int launch_tma(bgr_engine* e, const uint8_t* src, uint8_t* dst, uint32_t n_rows_
     tp.src = src; tp.dst = dst;
     tp.order_base = e->cfg.order_base;
     tp.accum = save ? acc : nullptr;
-    tp.out = nullptr; tp.ticket = e->d_ticket;
-    tp.epad = e->epad; tp.words = e->words; tp.tile_rows = e->tma_tile;
-    tp.n_rows_src = n_rows_src; tp.n_rows_copy = n_rows_copy;
+    tp.words = e->words; tp.tile_bytes = e->tile_bytes; tp.stage_tiles = e->tma_stage_tiles;
+    tp.n_tiles = e->tiles_for(n_rows_copy);
+    tp.n_rows_src = n_rows_src;
     tp.count_alive = save ? 1u : 0u;
     tp.store = store ? 1u : 0u;
     if (save)
@@ -319,9 +343,9 @@ int launch_tma(bgr_engine* e, const uint8_t* src, uint8_t* dst, uint32_t n_rows_
                 h.first_plane = c.first_plane; h.off = c.hash_off; h.len = c.hash_len;
                 h.finite = c.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32; h.slot = uint32_t(c.ck_slot);
             }
-    uint32_t n_tiles = (n_rows_copy + e->tma_tile - 1) / e->tma_tile;
-    uint32_t grid = std::max(1u, std::min(n_tiles, uint32_t(e->num_sms)));
-    size_t smem = size_t(kTmaStages) * e->tma_tile * (size_t(e->words) * 4u + 1u);
+    uint32_t n_chunks = (tp.n_tiles + tp.stage_tiles - 1) / tp.stage_tiles;
+    uint32_t grid = std::max(1u, std::min(n_chunks, uint32_t(e->num_sms)));
+    size_t smem = size_t(kTmaStages) * e->tma_stage_tiles * e->tile_bytes;
     k_image_tma<<<grid, kTmaBlock, smem, e->stream>>>(tp);
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
@@ -339,8 +363,8 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
         switch (op.kind) {
         case OP_SAVE: {
             unsigned long long* acc = e->d_accum + size_t(op.save_index) * kAccStride;
-            if (e->tune_tma && e->tma_tile) {
-                int rc = launch_tma(e, live, e->image(op.image), op.n_rows, op.n_rows, true, acc, !(op.flags & OPF_NO_STORE));
+            if (e->tune_tma && e->tma_stage_tiles) {
+                int rc = launch_tma(e, live, e->arena + (size_t(op.image_off256) << 8), op.n_rows, op.n_rows, true, acc, !(op.flags & OPF_NO_STORE));
                 if (rc != BGR_OK) return rc;
                 break;
             }
@@ -348,7 +372,7 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
             for (const Column& c : e->cols) {
                 if (c.hash_kind == BGR_HASH_NONE) continue;
                 k_checksum_column<<<e->grid_for(std::max(1u, op.n_rows), 256), 256, 0, e->stream>>>(
-                    live, e->epad, e->words, c.first_plane, c.hash_off, c.hash_len,
+                    live, e->words, c.first_plane, c.hash_off, c.hash_len,
                     c.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32, op.n_rows, e->cfg.order_base, acc,
                     uint32_t(c.ck_slot), counted ? 0u : 1u, 1u);
                 counted = true;
@@ -356,24 +380,26 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
             }
             if (!counted) {
                 k_checksum_column<<<e->grid_for(std::max(1u, op.n_rows), 256), 256, 0, e->stream>>>(
-                    live, e->epad, e->words, 0, 0, 0, 0, op.n_rows, e->cfg.order_base, acc, 0, 1u, 0u);
+                    live, e->words, 0, 0, 0, 0, op.n_rows, e->cfg.order_base, acc, 0, 1u, 0u);
                 e->launches += 1;
             }
             if (!(op.flags & OPF_NO_STORE) && op.n_rows > 0) {
-                k_copy_image<<<e->grid_for((op.n_rows + 3) / 4, 256), 256, 0, e->stream>>>(
-                    live, e->image(op.image), e->epad, e->words, op.n_rows, op.n_rows);
+                uint32_t nt = e->tiles_for(op.n_rows);
+                k_copy_image<<<e->grid_for(uint32_t(size_t(nt) * e->tile_bytes / 16u), 256), 256, 0, e->stream>>>(
+                    live, e->arena + (size_t(op.image_off256) << 8), e->words, nt, op.n_rows);
                 e->launches += 1;
             }
             break;
         }
         case OP_LOAD: {
             uint32_t n_copy = std::max(op.n_rows, live_rows);
-            if (n_copy > 0 && e->tune_tma && e->tma_tile) {
-                int rc = launch_tma(e, e->image(op.image), live, op.n_rows, n_copy, false, nullptr, true);
+            if (n_copy > 0 && e->tune_tma && e->tma_stage_tiles) {
+                int rc = launch_tma(e, e->arena + (size_t(op.image_off256) << 8), live, op.n_rows, n_copy, false, nullptr, true);
                 if (rc != BGR_OK) return rc;
             } else if (n_copy > 0) {
-                k_copy_image<<<e->grid_for((n_copy + 3) / 4, 256), 256, 0, e->stream>>>(
-                    e->image(op.image), live, e->epad, e->words, op.n_rows, n_copy);
+                uint32_t nt = e->tiles_for(n_copy);
+                k_copy_image<<<e->grid_for(uint32_t(size_t(nt) * e->tile_bytes / 16u), 256), 256, 0, e->stream>>>(
+                    e->arena + (size_t(op.image_off256) << 8), live, e->words, nt, op.n_rows);
                 e->launches += 1;
             }
             live_rows = op.n_rows;
@@ -388,29 +414,29 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
             for (const SystemReg& sy : e->systems) {
                 switch (sy.id) {
                 case BGR_SYS_PARTICLES_UPDATE:
-                    k_sys_particles_update<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane,
+                    k_sys_particles_update<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane,
                                                                           e->cols[sy.cols[1]].first_plane, n, op.dt_bits);
                     break;
                 case BGR_SYS_PARTICLES_DESPAWN:
-                    k_sys_particles_despawn<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane, n, e->d_kill);
+                    k_sys_particles_despawn<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane, n, e->d_kill);
                     any_despawn = true;
                     break;
                 case BGR_SYS_U32_ADD:
-                    k_sys_u32_add<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1]);
+                    k_sys_u32_add<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1]);
                     break;
                 case BGR_SYS_U32_SATSUB_DESPAWN:
-                    k_sys_u32_satsub_despawn<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1], e->d_kill);
+                    k_sys_u32_satsub_despawn<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1], e->d_kill);
                     any_despawn = true;
                     break;
                 case BGR_SYS_U32_STORE_CALL_COUNT:
-                    k_sys_u32_store<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, counter++);
+                    k_sys_u32_store<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, counter++);
                     break;
                 default: return fail(BGR_ERR_UNSUPPORTED, "system has no GPU implementation yet");
                 }
                 e->launches += 1;
             }
             if (any_despawn) {
-                k_apply_despawns<<<grid, 256, 0, e->stream>>>(live, e->epad, e->words, n, e->d_kill);
+                k_apply_despawns<<<grid, 256, 0, e->stream>>>(live, e->words, n, e->d_kill);
                 e->launches += 1;
             }
             break;
@@ -501,14 +527,18 @@ int drain(bgr_engine* e) {
     return BGR_OK;
 }
 
-// word w of a column element stored AoS on the host (handles elem_bytes not a multiple of 4)
-inline uint32_t host_word(const uint8_t* elem, uint32_t eb, uint32_t w) {
-    uint32_t v = 0;
-    uint32_t nb = std::min(4u, eb - 4u * w);
-    std::memcpy(&v, elem + 4u * w, nb);
-    return v;
+int ensure_stage(bgr_engine* e, size_t bytes) {
+    if (bytes <= e->stage_cap) return BGR_OK;
+    if (e->d_stage) CUDA_TRY(cudaFree(e->d_stage));
+    e->d_stage = nullptr; e->stage_cap = 0;
+    size_t cap = std::max<size_t>(bytes, 1u << 20);
+    CUDA_TRY(cudaMalloc(&e->d_stage, cap));
+    e->stage_cap = cap;
+    return BGR_OK;
 }
 
+// ECS column (array of T, `stride` bytes apart) <-> tile-planar image: one H2D/D2H copy of the AoS
+// bytes + one transposition kernel (k_scatter_column / k_gather_column).
 int transfer_column(bgr_engine* e, uint32_t image_idx, uint32_t column, uint32_t first, uint32_t count, void* host,
                     uint32_t stride, bool to_device) {
     if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
@@ -519,22 +549,24 @@ int transfer_column(bgr_engine* e, uint32_t image_idx, uint32_t column, uint32_t
     if (count == 0) return BGR_OK;
     int rc = drain(e);
     if (rc != BGR_OK) return rc;
-    std::vector<uint32_t> plane(count);
+    const size_t bytes = size_t(count) * stride;
+    rc = ensure_stage(e, bytes);
+    if (rc != BGR_OK) return rc;
     uint8_t* img = e->image(image_idx);
-    for (uint32_t w = 0; w < c.words; ++w) {
-        uint8_t* dptr = img + size_t(c.first_plane + w) * e->epad * 4u + size_t(first) * 4u;
-        if (to_device) {
-            const uint8_t* src = static_cast<const uint8_t*>(host);
-            for (uint32_t i = 0; i < count; ++i) plane[i] = host_word(src + size_t(i) * stride, c.elem_bytes, w);
-            CUDA_TRY(cudaMemcpyAsync(dptr, plane.data(), size_t(count) * 4u, cudaMemcpyHostToDevice, e->stream));
-            CUDA_TRY(cudaStreamSynchronize(e->stream));
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(plane.data(), dptr, size_t(count) * 4u, cudaMemcpyDeviceToHost, e->stream));
-            CUDA_TRY(cudaStreamSynchronize(e->stream));
-            uint8_t* dst = static_cast<uint8_t*>(host);
-            uint32_t nb = std::min(4u, c.elem_bytes - 4u * w);
-            for (uint32_t i = 0; i < count; ++i) std::memcpy(dst + size_t(i) * stride + 4u * w, &plane[i], nb);
-        }
+    uint32_t grid = e->grid_for(uint32_t(std::min<size_t>(size_t(count) * c.words, 0x7fffffffu)), 256);
+    if (to_device) {
+        CUDA_TRY(cudaMemcpyAsync(e->d_stage, host, bytes, cudaMemcpyHostToDevice, e->stream));
+        k_scatter_column<<<grid, 256, 0, e->stream>>>(img, e->words, c.first_plane, c.words, c.elem_bytes, first, count, e->d_stage, stride);
+        e->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+    } else {
+        if (stride != c.elem_bytes) CUDA_TRY(cudaMemcpyAsync(e->d_stage, host, bytes, cudaMemcpyHostToDevice, e->stream));  // keep the caller's padding bytes
+        k_gather_column<<<grid, 256, 0, e->stream>>>(img, e->words, c.first_plane, c.words, c.elem_bytes, first, count, e->d_stage, stride);
+        e->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaMemcpyAsync(host, e->d_stage, bytes, cudaMemcpyDeviceToHost, e->stream));
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
     }
     return BGR_OK;
 }
@@ -544,11 +576,13 @@ int read_alive_image(bgr_engine* e, uint32_t image_idx, uint32_t first, uint32_t
     int rc = drain(e);
     if (rc != BGR_OK) return rc;
     if (uint64_t(first) + count > e->cfg.max_entities) return fail(BGR_ERR_CAPACITY, "row range exceeds max_entities");
-    const uint8_t* src = e->image(image_idx) + size_t(e->words) * e->epad * 4u + first;
-    CUDA_TRY(cudaMemcpyAsync(dst, src, count, cudaMemcpyDeviceToHost, e->stream));
+    rc = ensure_stage(e, count);
+    if (rc != BGR_OK) return rc;
+    k_gather_alive<<<e->grid_for(count, 256), 256, 0, e->stream>>>(e->image(image_idx), e->words, first, count, n_rows, e->d_stage);
+    e->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(dst, e->d_stage, count, cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(cudaStreamSynchronize(e->stream));
-    for (uint32_t i = 0; i < count; ++i)
-        if (first + i >= n_rows) dst[i] = 0;
     return BGR_OK;
 }
 
@@ -577,6 +611,21 @@ void detect_bundles(bgr_engine* e) {
     for (uint32_t p = 0; p < e->words; ++p)
         if (!active[p]) e->passive.push_back(uint16_t(p));
     if (e->passive.size() > size_t(kMaxPassive)) { e->passive.clear(); return; }
+    // runs of adjacent passive planes: one cp.async.bulk each
+    e->runs.clear(); e->passive_bytes = 0;
+    for (size_t i = 0; i < e->passive.size();) {
+        size_t j = i;
+        while (j + 1 < e->passive.size() && e->passive[j + 1] == e->passive[j] + 1) ++j;
+        PassiveRun r{uint32_t(e->passive[i]) * kPlaneBytes, uint32_t(j - i + 1) * kPlaneBytes};
+        e->runs.push_back(r);
+        e->passive_bytes += r.bytes;
+        i = j + 1;
+    }
+    if (e->runs.size() > size_t(kMaxRuns)) { e->runs.clear(); e->passive_bytes = 0; }
+    const bool fin_t = e->cols[t].hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32, fin_v = e->cols[v].hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32;
+    const bool ck_t = e->cols[t].hash_kind != BGR_HASH_NONE, ck_v = e->cols[v].hash_kind != BGR_HASH_NONE;
+    if (ck_t && ck_v && fin_t != fin_v) { e->passive.clear(); return; }  // mixed assertions: generic path
+    e->bundle_static_ck = ck_t && ck_v && fin_t && fin_v;
     e->bt = t; e->bv = v; e->bl = l;
     e->bundle_particles = true;
 }
@@ -615,12 +664,12 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
         if (se != cudaSuccess) { delete e; return fail(BGR_ERR_CUDA, cudaGetErrorString(se)); }
         e->own_stream = true;
     }
-    e->tune_vec = env_int("BGR_TUNE_VEC", 4);
-    e->tune_block = env_int("BGR_TUNE_BLOCK", 256);
+    e->tune_vec = env_int("BGR_TUNE_VEC", 2);
+    e->tune_minb = env_int("BGR_TUNE_MINB", 1);
     e->tune_bps = env_int("BGR_TUNE_BPS", 0);
     e->tune_tma = env_int("BGR_TUNE_TMA", 1);
-    if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 4;
-    if (e->tune_block != 128 && e->tune_block != 256) e->tune_block = 256;
+    e->tune_passive_tma = env_int("BGR_TUNE_PASSIVE_TMA", 1);
+    if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 2;
     e->st.confirmed = 0;
     *out = e;
     return BGR_OK;
@@ -636,6 +685,7 @@ BGR_API void bgr_engine_destroy(bgr_engine* e) {
     }
     if (e->arena) cudaFree(e->arena);
     if (e->d_kill) cudaFree(e->d_kill);
+    if (e->d_stage) cudaFree(e->d_stage);
     if (e->d_accum) cudaFree(e->d_accum);
     if (e->d_ticket) cudaFree(e->d_ticket);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
@@ -726,8 +776,12 @@ BGR_API int bgr_build(bgr_engine* e) {
         }
     }
     e->words = plane;
-    e->epad = (e->cfg.max_entities + 255u) & ~255u;
-    e->image_bytes = ((size_t(e->epad) * (size_t(e->words) * 4u + 1u)) + 255u) & ~size_t(255);
+    e->epad = (e->cfg.max_entities + kTileRows - 1) / kTileRows * kTileRows;
+    e->n_tiles_cap = e->epad / kTileRows;
+    e->tile_bytes = tile_bytes_of(e->words);
+    e->image_bytes = size_t(e->n_tiles_cap) * e->tile_bytes;  // multiple of 512
+    if ((e->image_bytes * (size_t(e->cfg.max_depth) + 1u)) >> 8 > 0xffffffffull)
+        return fail(BGR_ERR_CAPACITY, "arena larger than 1 TB");
     size_t total = e->image_bytes * (size_t(e->cfg.max_depth) + 1u);
     CUDA_TRY(cudaMalloc(&e->arena, total));
     CUDA_TRY(cudaMemsetAsync(e->arena, 0, total, e->stream));
@@ -747,13 +801,12 @@ BGR_API int bgr_build(bgr_engine* e) {
     e->st.slot_rows.assign(e->cfg.max_depth, 0);
     e->st.slot_elapsed_ns.assign(e->cfg.max_depth, 0);
     detect_bundles(e);
-    {   // TMA tile: 3 stages of (4*W+1) bytes per row must fit ~200 KB of shared memory
-        size_t per_row = size_t(e->words) * 4u + 1u;
-        size_t rows = (200u * 1024u) / (size_t(kTmaStages) * per_row);
-        rows = std::min<size_t>(rows & ~size_t(255), 2048);
-        e->tma_tile = uint32_t(rows);
-        if (e->tma_tile) {
-            size_t smem = size_t(kTmaStages) * e->tma_tile * per_row;
+    {   // TMA stage: kTmaStages x (stage_tiles tiles) must fit ~200 KB of shared memory, ~64 KB per stage
+        size_t per_stage = (200u * 1024u) / size_t(kTmaStages);
+        uint32_t st = uint32_t(std::min<size_t>(per_stage / e->tile_bytes, 8));
+        e->tma_stage_tiles = st;
+        if (st) {
+            size_t smem = size_t(kTmaStages) * st * e->tile_bytes;
             CUDA_TRY(cudaFuncSetAttribute(k_image_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         }
     }
@@ -769,10 +822,9 @@ BGR_API int bgr_spawn(bgr_engine* e, uint32_t count, uint32_t* first_row_out) {
     if (uint64_t(e->st.n_rows) + count > e->cfg.max_entities) return fail(BGR_ERR_CAPACITY, "spawn exceeds max_entities");
     uint32_t first = e->st.n_rows;
     if (count) {
-        uint8_t* live = e->image(0);
-        for (uint32_t p = 0; p < e->words; ++p)
-            CUDA_TRY(cudaMemsetAsync(live + size_t(p) * e->epad * 4u + size_t(first) * 4u, 0, size_t(count) * 4u, e->stream));
-        CUDA_TRY(cudaMemsetAsync(live + size_t(e->words) * e->epad * 4u + first, 1, count, e->stream));
+        k_spawn_rows<<<e->grid_for(count, 64), 256, 0, e->stream>>>(e->image(0), e->words, first, count);
+        e->launches += 1;
+        CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaStreamSynchronize(e->stream));
     }
     e->st.n_rows += count;
@@ -785,7 +837,9 @@ BGR_API int bgr_despawn(bgr_engine* e, uint32_t row) {
     int rc = drain(e);
     if (rc != BGR_OK) return rc;
     if (row >= e->st.n_rows) return fail(BGR_ERR_INVALID_ARGUMENT, "row out of range");
-    CUDA_TRY(cudaMemsetAsync(e->image(0) + size_t(e->words) * e->epad * 4u + row, 0, 1, e->stream));
+    k_set_alive<<<1, 1, 0, e->stream>>>(e->image(0), e->words, row, 0);
+    e->launches += 1;
+    CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     return BGR_OK;
 }

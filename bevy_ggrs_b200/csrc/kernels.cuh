@@ -1,11 +1,19 @@
 // CUDA kernels of the rollback engine (sm_100a).  HBM-bound integer / f32 streaming work:
-// no tensor cores (there is no dense contraction on this path), the design rules that matter are
-// coalescing (word-planar columns => every warp access is a contiguous 128..512 B run),
-// 16-byte vector loads/stores, enough bytes in flight per SM, and ONE launch per request vector.
+// no tensor cores (there is no dense contraction on this path); what matters is coalescing,
+// vector accesses, TMA bulk copies for bytes nobody computes on, instruction count per byte
+// and ONE launch per request vector.
 //
-// Data layout (DESIGN.md "Data layout in HBM"): an *image* is every registered column split into
-// 4-byte word planes of `epad` rows each, followed by a 1-byte-per-row alive plane:
-//     image = [plane 0 | plane 1 | ... | plane W-1 | alive]      plane p at p*epad*4
+// Data layout (DESIGN.md "Data layout in HBM") — TILE-PLANAR images:
+//   an image is a sequence of tiles of kTileRows = 512 rows; inside a tile every registered
+//   column is split into 4-byte word planes, followed by the 1-byte-per-row alive plane:
+//       tile = [plane 0: 512 words | plane 1 | ... | plane W-1 | alive: 512 bytes]      (512*(4W+1) bytes)
+//       image = tile 0 | tile 1 | ...
+//   * every warp access is a contiguous 128..512 B run (coalesced) whatever the element size,
+//   * all planes of a tile sit within 64 KB, so a thread reaches them with ONE base pointer plus
+//     compile-time immediates (the first profile of the plane-major layout spent ~4 address
+//     instructions per store),
+//   * a whole tile — or any run of adjacent planes — is ONE contiguous chunk for cp.async.bulk (TMA),
+//   * an image is flat: save/load of any schema is a flat copy of n_tiles * tile_bytes.
 // Image 0 is the live world, image s+1 is snapshot slot s of the ring.  A row is one rollback
 // entity; its RollbackOrdered index is order_base + row (rollback.rs:66-83).
 //
@@ -22,23 +30,34 @@
 
 namespace bgr {
 
+constexpr uint32_t kTileRows = 512;
+constexpr uint32_t kPlaneBytes = kTileRows * 4;  // one word plane inside a tile
 constexpr int kMaxOps = 80;       // == BGR_MAX_REQUESTS
 constexpr int kMaxSaves = 40;
-constexpr int kMaxPassive = 64;   // word planes that no compiled system touches
+constexpr int kMaxPassive = 64;   // word planes that no compiled system touches (per-thread fallback)
+constexpr int kMaxRuns = 8;       // runs of adjacent passive planes (TMA path)
 constexpr int kAccStride = 8;     // u64 per save: [0..5] column xors, [6] active rows, [7] flags
+
+__host__ __device__ inline uint32_t tile_bytes_of(uint32_t words) { return kTileRows * (4u * words + 1u); }
+__host__ __device__ inline size_t word_offset(uint32_t words, uint32_t row, uint32_t plane) {
+    return size_t(row / kTileRows) * tile_bytes_of(words) + size_t(plane) * kPlaneBytes + size_t(row % kTileRows) * 4u;
+}
+__host__ __device__ inline size_t alive_offset(uint32_t words, uint32_t row) {
+    return size_t(row / kTileRows) * tile_bytes_of(words) + size_t(words) * kPlaneBytes + size_t(row % kTileRows);
+}
 
 enum OpKind : uint32_t { OP_SAVE = 0, OP_LOAD = 1, OP_ADVANCE = 2 };
 enum OpFlags : uint32_t { OPF_NO_STORE = 1u };  // ring depth 0: checksum only
 
 struct Op {
     uint32_t kind;
-    uint32_t image;       // image index the op reads (LOAD) or writes (SAVE)
-    uint32_t dt_bits;     // ADVANCE: Time<GgrsTime>::delta_secs as f32 bits (time.rs:63-76)
-    uint32_t n_rows;      // rows that exist while this op runs (RollbackOrdered::len())
-    uint32_t save_index;  // SAVE: which accumulator row
+    uint32_t image_off256;  // byte offset of the image the op reads (LOAD) / writes (SAVE), in 256-byte units
+    uint32_t dt_bits;       // ADVANCE: Time<GgrsTime>::delta_secs as f32 bits (time.rs:63-76)
+    uint32_t n_rows;        // rows that exist while this op runs (RollbackOrdered::len())
+    uint32_t save_index;    // SAVE: which accumulator row
     uint32_t flags;
-    uint32_t call_count;  // ADVANCE: value of the un-rolled-back host counter (test system only)
-    uint8_t inputs[4];    // ADVANCE: first 4 player inputs (u8); systems needing more use the stepwise path
+    uint32_t call_count;    // ADVANCE: value of the un-rolled-back host counter (test system only)
+    uint8_t inputs[4];      // ADVANCE: first 4 player inputs (u8)
 };
 static_assert(sizeof(Op) == 32, "Op must stay 32 bytes");
 
@@ -46,21 +65,25 @@ enum ProgFlags : uint32_t {
     PF_READ_LIVE = 1u,           // program does not start with LOAD: initial state comes from image 0
     PF_WRITE_LIVE_ACTIVE = 2u,   // program contains LOAD or ADVANCE: final active planes go to image 0
     PF_WRITE_LIVE_PASSIVE = 4u,  // program contains LOAD: final passive planes go to image 0
-    PF_CK_T = 8u, PF_CK_T_FINITE = 16u, PF_CK_V = 32u, PF_CK_V_FINITE = 64u,
+    PF_PASSIVE_TMA = 8u,         // at most one LOAD and it is ops[0]: passive planes move by TMA bulk copies
+    PF_CK_T = 16u, PF_CK_V = 32u, PF_CK_FIN = 64u,  // which bundle columns are checksummed / assert finite
 };
+
+struct PassiveRun { uint32_t off, bytes; };  // inside a tile; adjacent passive planes form one run
 
 struct ProgramParams {
     uint8_t* arena;
-    unsigned long long image_bytes;
     unsigned long long order_base;
     unsigned long long* accum;  // device [kMaxSaves][kAccStride]
     unsigned long long* out;    // host-mapped [kMaxSaves][kAccStride]
     unsigned int* ticket;
-    uint32_t epad, words, n_ops, n_saves;
-    uint32_t max_rows, live_rows, flags;
-    uint32_t t_plane, v_plane, l_plane;     // first word plane of Transform / Velocity / Ttl
-    uint32_t ck_t_slot, ck_v_slot;           // accumulator column of each checksummed type
-    uint32_t n_passive;
+    uint32_t words, tile_bytes, n_tiles, n_ops, n_saves;
+    uint32_t live_rows, flags;
+    uint32_t t_off, v_off, l_off, alive_off;  // byte offsets inside a tile of Transform / Velocity / Ttl word 0 / alive plane
+    uint32_t ck_t_slot, ck_v_slot;            // accumulator column of each checksummed type
+    uint32_t n_runs, passive_bytes;           // TMA path
+    uint32_t n_passive;                       // per-thread fallback path
+    PassiveRun runs[kMaxRuns];
     uint16_t passive[kMaxPassive];
     Op ops[kMaxOps];
 };
@@ -69,11 +92,6 @@ static_assert(sizeof(ProgramParams) <= 4000, "kernel parameter block must fit 4 
 // ---------------------------------------------------------------------------------------------
 // vector access helpers: VEC consecutive rows of one word plane = one 4*VEC byte access
 // ---------------------------------------------------------------------------------------------
-template <int VEC> struct Vec;
-template <> struct Vec<1> { using T = uint32_t; };
-template <> struct Vec<2> { using T = uint2; };
-template <> struct Vec<4> { using T = uint4; };
-
 template <int VEC> __device__ __forceinline__ void vec_load(const uint8_t* p, uint32_t (&r)[VEC]);
 template <> __device__ __forceinline__ void vec_load<1>(const uint8_t* p, uint32_t (&r)[1]) { r[0] = __ldcs(reinterpret_cast<const uint32_t*>(p)); }
 template <> __device__ __forceinline__ void vec_load<2>(const uint8_t* p, uint32_t (&r)[2]) { uint2 v = __ldcs(reinterpret_cast<const uint2*>(p)); r[0] = v.x; r[1] = v.y; }
@@ -94,7 +112,7 @@ template <> __device__ __forceinline__ void alive_store<1>(uint8_t* p, uint32_t 
 template <> __device__ __forceinline__ void alive_store<2>(uint8_t* p, uint32_t a) { __stcs(reinterpret_cast<unsigned short*>(p), (unsigned short)a); }
 template <> __device__ __forceinline__ void alive_store<4>(uint8_t* p, uint32_t a) { __stcs(reinterpret_cast<uint32_t*>(p), a); }
 
-__device__ __forceinline__ bool f32_bits_nonfinite(uint32_t b) { return (b & 0x7f800000u) == 0x7f800000u; }
+__device__ __forceinline__ uint32_t f32_bits_nonfinite(uint32_t b) { return ((b & 0x7f800000u) == 0x7f800000u) ? 1u : 0u; }
 
 // mask with byte j = 0x01 for every row (row0 + j) < n_rows
 template <int VEC> __device__ __forceinline__ uint32_t rows_mask(uint32_t row0, uint32_t n_rows) {
@@ -103,6 +121,38 @@ template <int VEC> __device__ __forceinline__ uint32_t rows_mask(uint32_t row0, 
     for (int j = 0; j < VEC; ++j) m |= (row0 + j < n_rows) ? (1u << (8 * j)) : 0u;
     return m;
 }
+
+// ---- TMA / mbarrier primitives (cp.async.bulk, SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok = 0;
+    while (!ok) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
 // update_particles (particles.rs:272-280) for one entity: every mul and add individually rounded
@@ -124,173 +174,217 @@ __device__ __forceinline__ void particle_step(uint32_t& tx, uint32_t& ty, uint32
 
 // =============================================================================================
 // THE fused kernel: interprets the whole request vector (Load / Advance / Save ...) for the
-// particles bundle with every entity's state in registers.  One launch per handle_requests.
-//   * LOAD    : read the snapshot image once (S bytes/entity)
-//   * ADVANCE : update_particles + despawn_particles in registers (0 bytes)
-//   * SAVE    : stream the state into the frame's slot (S bytes/entity) and fold the per-entity
-//               seahashes of the checksummed columns: warp REDUX.XOR -> shared atomics -> one
-//               global atomic per block per (save, column) -> last block publishes to host memory
-//   * end     : write the live image once
+// particles bundle.  One launch per handle_requests; one tile (512 rows) per block iteration.
+//   * active words (translation, velocity, ttl, alive) live in registers for the whole program:
+//       LOAD    : read them from the snapshot image once
+//       ADVANCE : update_particles + despawn_particles in registers (0 bytes)
+//       SAVE    : stream them into the frame's slot and fold the per-entity seahashes of the
+//                 checksummed columns: warp REDUX.XOR -> shared atomics -> one global atomic per
+//                 block per (save, column) -> last block publishes to host-mapped memory
+//       end     : write the live image once
+//   * passive planes (rotation, scale, any registered column no compiled system writes) never
+//     touch a register: one cp.async.bulk brings the tile's passive runs into shared memory and
+//     one cp.async.bulk per SAVE (and one for the live image) streams them out again.
 // Frames of one entity are sequentially dependent, so the frame loop is per thread; entities are
 // independent, so the grid dimension is the entity dimension.
+// Dead rows are advanced and hashed like live ones and masked at the fold: their bytes are not
+// observable (a row only comes back to life through LOAD, which restores data and flag together).
 // =============================================================================================
-template <int VEC, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_particles_program(const __grid_constant__ ProgramParams p) {
+template <int VEC, bool STATIC_CK, int MINB>
+__global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(const __grid_constant__ ProgramParams p) {
+    constexpr int BLOCK = kTileRows / VEC;
+    // STATIC_CK: both columns checksummed with the finite assertion (the stress test's registration) —
+    // the flag tests fold away; otherwise they are warp-uniform runtime tests.
+    const bool CKT = STATIC_CK ? true : (p.flags & PF_CK_T) != 0;
+    const bool CKV = STATIC_CK ? true : (p.flags & PF_CK_V) != 0;
+    const bool FIN = STATIC_CK ? true : (p.flags & PF_CK_FIN) != 0;
+    extern __shared__ __align__(128) uint8_t s_passive[];  // 2 x passive_bytes (double buffer)
     __shared__ unsigned long long s_acc[kMaxSaves * kAccStride];
+    __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ unsigned int s_last;
-    for (uint32_t i = threadIdx.x; i < p.n_saves * kAccStride; i += BLOCK) s_acc[i] = 0ULL;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    for (uint32_t i = tid; i < p.n_saves * kAccStride; i += BLOCK) s_acc[i] = 0ULL;
+    const bool use_tma = (p.flags & PF_PASSIVE_TMA) && p.n_runs > 0;
+    if (tid == 0 && use_tma) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        fence_mbar_init();
+    }
     __syncthreads();
 
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t n_groups = (p.max_rows + VEC - 1) / VEC;
-    const size_t plane_bytes = size_t(p.epad) * 4u;
-    const size_t alive_off = size_t(p.words) * plane_bytes;
-    uint8_t* const live = p.arena;
+    const uint32_t i0 = tid * VEC;  // first row of this thread inside the tile
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+        const size_t tile_off = size_t(tile) * p.tile_bytes;
+        const uint32_t row0 = tile * kTileRows + i0;
+        const size_t woff = tile_off + size_t(i0) * 4u;  // + plane offset (+ image offset) = address of this thread's words
+        const size_t aoff = tile_off + p.alive_off + i0;
 
-    for (uint32_t g = blockIdx.x * BLOCK + threadIdx.x; g - lane < n_groups; g += gridDim.x * BLOCK) {
-        const bool valid = g < n_groups;
-        const uint32_t row0 = g * VEC;
-        const size_t woff = size_t(row0) * 4u;
+        // ---- passive planes, TMA path: issue the load of this tile's passive runs now ----
+        const uint32_t buf = it & 1u;
+        if (use_tma && tid == 0) {
+            tma_wait_read<1>();  // the stores issued two tiles ago have finished reading this buffer
+            const uint8_t* src = p.arena + ((p.flags & PF_READ_LIVE) ? size_t(0) : (size_t(p.ops[0].image_off256) << 8)) + tile_off;
+            uint8_t* dst = s_passive + size_t(buf) * p.passive_bytes;
+            mbar_arrive_expect_tx(&s_bar[buf], p.passive_bytes);
+            uint32_t o = 0;
+            for (uint32_t r = 0; r < p.n_runs; ++r) {
+                tma_load_1d(dst + o, src + p.runs[r].off, p.runs[r].bytes, &s_bar[buf]);
+                o += p.runs[r].bytes;
+            }
+        }
 
         // ------------------------------ active words ------------------------------
         uint32_t tr[3][VEC], vl[3][VEC], tl[2][VEC];
         uint32_t alive = 0;
-#pragma unroll
-        for (int k = 0; k < 3; ++k)
-#pragma unroll
-            for (int j = 0; j < VEC; ++j) { tr[k][j] = 0; vl[k][j] = 0; }
-#pragma unroll
-        for (int j = 0; j < VEC; ++j) { tl[0][j] = 0; tl[1][j] = 0; }
 
         auto load_active = [&](const uint8_t* img, uint32_t n_rows) {
-            if (valid) {
+            const uint8_t* pt = img + p.t_off + woff;
+            const uint8_t* pv = img + p.v_off + woff;
+            const uint8_t* pl = img + p.l_off + woff;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) vec_load<VEC>(img + (p.t_plane + k) * plane_bytes + woff, tr[k]);
+            for (int k = 0; k < 3; ++k) vec_load<VEC>(pt + k * kPlaneBytes, tr[k]);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) vec_load<VEC>(img + (p.v_plane + k) * plane_bytes + woff, vl[k]);
+            for (int k = 0; k < 3; ++k) vec_load<VEC>(pv + k * kPlaneBytes, vl[k]);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) vec_load<VEC>(img + (p.l_plane + k) * plane_bytes + woff, tl[k]);
-                alive = alive_load<VEC>(img + alive_off + row0) & rows_mask<VEC>(row0, n_rows);
-            }
+            for (int k = 0; k < 2; ++k) vec_load<VEC>(pl + k * kPlaneBytes, tl[k]);
+            alive = alive_load<VEC>(img + aoff) & rows_mask<VEC>(row0, n_rows);
         };
-        auto store_active = [&](uint8_t* img, uint32_t n_rows) {
-            if (valid) {
+        auto store_active = [&](uint8_t* img) {
+            uint8_t* pt = img + p.t_off + woff;
+            uint8_t* pv = img + p.v_off + woff;
+            uint8_t* pl = img + p.l_off + woff;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) vec_store<VEC>(img + (p.t_plane + k) * plane_bytes + woff, tr[k]);
+            for (int k = 0; k < 3; ++k) vec_store<VEC>(pt + k * kPlaneBytes, tr[k]);
 #pragma unroll
-                for (int k = 0; k < 3; ++k) vec_store<VEC>(img + (p.v_plane + k) * plane_bytes + woff, vl[k]);
+            for (int k = 0; k < 3; ++k) vec_store<VEC>(pv + k * kPlaneBytes, vl[k]);
 #pragma unroll
-                for (int k = 0; k < 2; ++k) vec_store<VEC>(img + (p.l_plane + k) * plane_bytes + woff, tl[k]);
-                alive_store<VEC>(img + alive_off + row0, alive & rows_mask<VEC>(row0, n_rows));
-            }
+            for (int k = 0; k < 2; ++k) vec_store<VEC>(pl + k * kPlaneBytes, tl[k]);
+            alive_store<VEC>(img + aoff, alive);
         };
 
-        if (p.flags & PF_READ_LIVE) load_active(live, p.live_rows);
+        if (p.flags & PF_READ_LIVE) load_active(p.arena, p.live_rows);
+        else load_active(p.arena + (size_t(p.ops[0].image_off256) << 8), p.ops[0].n_rows);  // ops[0] is a LOAD
 
         // lane of the per-entity hash that only depends on the RollbackOrdered index
         uint64_t t0[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) t0[j] = sea_order_lane(p.order_base + row0 + j);
 
-        for (uint32_t i = 0; i < p.n_ops; ++i) {
-            const Op& op = p.ops[i];
-            if (op.kind == OP_ADVANCE) {
-                const float dt = __uint_as_float(op.dt_bits);
+        for (uint32_t i = (p.flags & PF_READ_LIVE) ? 0u : 1u; i < p.n_ops; ++i) {
+            const uint32_t kind = p.ops[i].kind;
+            if (kind == OP_ADVANCE) {
+                const float dt = __uint_as_float(p.ops[i].dt_bits);
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    if ((alive >> (8 * j)) & 1u) {
-                        particle_step(tr[0][j], tr[1][j], tr[2][j], vl[0][j], vl[1][j], vl[2][j], dt);
-                        // despawn_particles (particles.rs:282-289): ttl -= 1 (wrapping usize); despawn at 0
-                        uint32_t lo = tl[0][j], hi = tl[1][j];
-                        hi -= (lo == 0u) ? 1u : 0u;
-                        lo -= 1u;
-                        tl[0][j] = lo; tl[1][j] = hi;
-                        if ((lo | hi) == 0u) alive &= ~(0xFFu << (8 * j));
-                    }
+                    particle_step(tr[0][j], tr[1][j], tr[2][j], vl[0][j], vl[1][j], vl[2][j], dt);
+                    // despawn_particles (particles.rs:282-289): ttl -= 1 (wrapping usize); despawn at 0
+                    uint32_t lo = tl[0][j], hi = tl[1][j];
+                    hi -= (lo == 0u) ? 1u : 0u;
+                    lo -= 1u;
+                    tl[0][j] = lo; tl[1][j] = hi;
+                    alive &= ((lo | hi) == 0u) ? ~(0xFFu << (8 * j)) : 0xFFFFFFFFu;
                 }
-            } else if (op.kind == OP_SAVE) {
-                uint8_t* img = p.arena + size_t(op.image) * p.image_bytes;
-                alive &= rows_mask<VEC>(row0, op.n_rows);
-                if (!(op.flags & OPF_NO_STORE)) store_active(img, op.n_rows);
+            } else if (kind == OP_SAVE) {
+                uint8_t* img = p.arena + (size_t(p.ops[i].image_off256) << 8);
+                if (!(p.ops[i].flags & OPF_NO_STORE)) store_active(img);
                 // ---- checksum partials (component_checksum.rs:81-90) ----
                 uint64_t hx_t = 0, hx_v = 0;
-                uint32_t n_alive = 0, bad = 0;
+                uint32_t bad = 0;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    if ((alive >> (8 * j)) & 1u) {
-                        ++n_alive;
-                        if (p.flags & PF_CK_T) {
-                            if (p.flags & PF_CK_T_FINITE)
-                                bad |= f32_bits_nonfinite(tr[0][j]) | f32_bits_nonfinite(tr[1][j]) | f32_bits_nonfinite(tr[2][j]);
-                            uint64_t c = sea_hash_12(uint64_t(tr[0][j]) | (uint64_t(tr[1][j]) << 32), tr[2][j]);
-                            hx_t ^= sea_hash_entity(t0[j], c);
-                        }
-                        if (p.flags & PF_CK_V) {
-                            if (p.flags & PF_CK_V_FINITE)
-                                bad |= f32_bits_nonfinite(vl[0][j]) | f32_bits_nonfinite(vl[1][j]) | f32_bits_nonfinite(vl[2][j]);
-                            uint64_t c = sea_hash_12(uint64_t(vl[0][j]) | (uint64_t(vl[1][j]) << 32), vl[2][j]);
-                            hx_v ^= sea_hash_entity(t0[j], c);
-                        }
+                    const uint64_t live = ((alive >> (8 * j)) & 1u) ? ~0ULL : 0ULL;
+                    if (CKT) {
+                        if (FIN) bad |= (f32_bits_nonfinite(tr[0][j]) | f32_bits_nonfinite(tr[1][j]) | f32_bits_nonfinite(tr[2][j])) & uint32_t(live);
+                        uint64_t c = sea_hash_12(uint64_t(tr[0][j]) | (uint64_t(tr[1][j]) << 32), tr[2][j]);
+                        hx_t ^= sea_hash_entity(t0[j], c) & live;
+                    }
+                    if (CKV) {
+                        if (FIN) bad |= (f32_bits_nonfinite(vl[0][j]) | f32_bits_nonfinite(vl[1][j]) | f32_bits_nonfinite(vl[2][j])) & uint32_t(live);
+                        uint64_t c = sea_hash_12(uint64_t(vl[0][j]) | (uint64_t(vl[1][j]) << 32), vl[2][j]);
+                        hx_v ^= sea_hash_entity(t0[j], c) & live;
                     }
                 }
+                const uint32_t n_alive = __popc(alive & 0x01010101u);
                 // warp-level fold (REDUX), then one shared-memory atomic per warp
                 const unsigned full = 0xffffffffu;
-                uint32_t tlo = __reduce_xor_sync(full, uint32_t(hx_t)), thi = __reduce_xor_sync(full, uint32_t(hx_t >> 32));
-                uint32_t vlo = __reduce_xor_sync(full, uint32_t(hx_v)), vhi = __reduce_xor_sync(full, uint32_t(hx_v >> 32));
+                unsigned long long* a = &s_acc[p.ops[i].save_index * kAccStride];
+                if (CKT) {
+                    uint32_t lo = __reduce_xor_sync(full, uint32_t(hx_t)), hi = __reduce_xor_sync(full, uint32_t(hx_t >> 32));
+                    if (lane == 0) atomicXor(&a[p.ck_t_slot], (unsigned long long)lo | ((unsigned long long)hi << 32));
+                }
+                if (CKV) {
+                    uint32_t lo = __reduce_xor_sync(full, uint32_t(hx_v)), hi = __reduce_xor_sync(full, uint32_t(hx_v >> 32));
+                    if (lane == 0) atomicXor(&a[p.ck_v_slot], (unsigned long long)lo | ((unsigned long long)hi << 32));
+                }
                 uint32_t cnt = __reduce_add_sync(full, n_alive);
-                uint32_t anybad = __reduce_or_sync(full, bad);
-                if (lane == 0) {
-                    unsigned long long* a = &s_acc[op.save_index * kAccStride];
-                    if (p.flags & PF_CK_T) atomicXor(&a[p.ck_t_slot], (unsigned long long)tlo | ((unsigned long long)thi << 32));
-                    if (p.flags & PF_CK_V) atomicXor(&a[p.ck_v_slot], (unsigned long long)vlo | ((unsigned long long)vhi << 32));
-                    atomicAdd(&a[6], (unsigned long long)cnt);
-                    if (anybad) atomicOr(&a[7], 1ULL);
+                if (lane == 0) atomicAdd(&a[6], (unsigned long long)cnt);
+                if (FIN) {
+                    uint32_t anybad = __reduce_or_sync(full, bad);
+                    if (lane == 0 && anybad) atomicOr(&a[7], 1ULL);
                 }
             } else {  // OP_LOAD
-                const uint8_t* img = p.arena + size_t(op.image) * p.image_bytes;
-                load_active(img, op.n_rows);
+                load_active(p.arena + (size_t(p.ops[i].image_off256) << 8), p.ops[i].n_rows);
             }
         }
-        if (p.flags & PF_WRITE_LIVE_ACTIVE) store_active(live, p.max_rows);
+        if (p.flags & PF_WRITE_LIVE_ACTIVE) store_active(p.arena);
 
         // ------------------------------ passive planes ------------------------------
-        // columns no compiled system writes (rotation, scale, any other registered POD): the
-        // same program, but a value is only ever loaded and stored, never computed on.
-        if (valid) {
+        if (use_tma) {
+            if (tid == 0) {
+                mbar_wait(&s_bar[buf], (it >> 1) & 1u);
+                const uint8_t* src = s_passive + size_t(buf) * p.passive_bytes;
+                for (uint32_t i = 0; i < p.n_ops; ++i) {
+                    if (p.ops[i].kind != OP_SAVE || (p.ops[i].flags & OPF_NO_STORE)) continue;
+                    uint8_t* img = p.arena + (size_t(p.ops[i].image_off256) << 8) + tile_off;
+                    uint32_t o = 0;
+                    for (uint32_t r = 0; r < p.n_runs; ++r) { tma_store_1d(img + p.runs[r].off, src + o, p.runs[r].bytes); o += p.runs[r].bytes; }
+                }
+                if (p.flags & PF_WRITE_LIVE_PASSIVE) {
+                    uint8_t* img = p.arena + tile_off;
+                    uint32_t o = 0;
+                    for (uint32_t r = 0; r < p.n_runs; ++r) { tma_store_1d(img + p.runs[r].off, src + o, p.runs[r].bytes); o += p.runs[r].bytes; }
+                }
+                tma_commit();
+            }
+        } else {
+            // generic fallback (several LOADs in one program): the same program per passive plane,
+            // a value is only ever loaded and stored, never computed on
             for (uint32_t pp = 0; pp < p.n_passive; pp += 4) {
                 uint32_t v[4][VEC];
                 const uint32_t nk = min(4u, p.n_passive - pp);
                 if (p.flags & PF_READ_LIVE) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (k < nk) vec_load<VEC>(live + p.passive[pp + k] * plane_bytes + woff, v[k]);
+                        if (k < nk) vec_load<VEC>(p.arena + size_t(p.passive[pp + k]) * kPlaneBytes + woff, v[k]);
                 }
                 for (uint32_t i = 0; i < p.n_ops; ++i) {
-                    const Op& op = p.ops[i];
-                    if (op.kind == OP_LOAD) {
-                        const uint8_t* img = p.arena + size_t(op.image) * p.image_bytes;
+                    const uint32_t kind = p.ops[i].kind;
+                    uint8_t* img = p.arena + (size_t(p.ops[i].image_off256) << 8);
+                    if (kind == OP_LOAD) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < nk) vec_load<VEC>(img + p.passive[pp + k] * plane_bytes + woff, v[k]);
-                    } else if (op.kind == OP_SAVE && !(op.flags & OPF_NO_STORE)) {
-                        uint8_t* img = p.arena + size_t(op.image) * p.image_bytes;
+                            if (k < nk) vec_load<VEC>(img + size_t(p.passive[pp + k]) * kPlaneBytes + woff, v[k]);
+                    } else if (kind == OP_SAVE && !(p.ops[i].flags & OPF_NO_STORE)) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
-                            if (k < nk) vec_store<VEC>(img + p.passive[pp + k] * plane_bytes + woff, v[k]);
+                            if (k < nk) vec_store<VEC>(img + size_t(p.passive[pp + k]) * kPlaneBytes + woff, v[k]);
                     }
                 }
                 if (p.flags & PF_WRITE_LIVE_PASSIVE) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
-                        if (k < nk) vec_store<VEC>(live + p.passive[pp + k] * plane_bytes + woff, v[k]);
+                        if (k < nk) vec_store<VEC>(p.arena + size_t(p.passive[pp + k]) * kPlaneBytes + woff, v[k]);
                 }
             }
         }
     }
+    if (use_tma && tid == 0) tma_wait_all();  // every bulk store has landed before the results are published
 
     // ---- block partials -> global accumulators -> (last block) host-visible results ----
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < p.n_saves * kAccStride; i += BLOCK) {
+    for (uint32_t i = tid; i < p.n_saves * kAccStride; i += BLOCK) {
         unsigned long long v = s_acc[i];
         uint32_t c = i % kAccStride;
         if (v) {
@@ -301,13 +395,13 @@ __global__ void __launch_bounds__(BLOCK) k_particles_program(const __grid_consta
     }
     __threadfence();
     __syncthreads();
-    if (threadIdx.x == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1u);
+    if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1u);
     __syncthreads();
     if (s_last) {
         __threadfence();
-        for (uint32_t i = threadIdx.x; i < p.n_saves * kAccStride; i += BLOCK)
+        for (uint32_t i = tid; i < p.n_saves * kAccStride; i += BLOCK)
             p.out[i] = atomicExch(&p.accum[i], 0ULL);  // publish and re-arm for the next launch
-        if (threadIdx.x == 0) *p.ticket = 0u;
+        if (tid == 0) *p.ticket = 0u;
     }
 }
 
@@ -315,58 +409,50 @@ __global__ void __launch_bounds__(BLOCK) k_particles_program(const __grid_consta
 // Stepwise (generic) path: one kernel per request, any registered schema / system list.
 // =============================================================================================
 
-// copy rows [0, n_rows) of every word plane + the alive plane from one image to another
-// (ComponentSnapshotPlugin::save / ::load as a pure copy).  Thread = 4 consecutive rows.
+// flat copy of tiles [0, n_tiles) of an image (fallback when the TMA kernel cannot be used);
+// alive bytes of rows >= n_rows_src are forced to 0 (a Load that shrinks the world).
 __global__ void __launch_bounds__(256) k_copy_image(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst,
-                                                    uint32_t epad, uint32_t words, uint32_t n_rows_src,
-                                                    uint32_t n_rows_copy) {
-    const uint32_t n_groups = (n_rows_copy + 3) / 4;
-    const size_t plane_bytes = size_t(epad) * 4u;
-    for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
-        const size_t woff = size_t(g) * 16u;
-        for (uint32_t w = 0; w < words; w += 4) {
-            uint4 v[4];
+                                                    uint32_t words, uint32_t n_tiles, uint32_t n_rows_src) {
+    const uint32_t tb = tile_bytes_of(words);
+    const size_t n_vec = size_t(n_tiles) * tb / 16u;
+    for (size_t v = size_t(blockIdx.x) * blockDim.x + threadIdx.x; v < n_vec; v += size_t(gridDim.x) * blockDim.x) {
+        uint4 x = __ldcs(reinterpret_cast<const uint4*>(src) + v);
+        const size_t byte = v * 16u;
+        const uint32_t tile = uint32_t(byte / tb), in_tile = uint32_t(byte % tb);
+        if (in_tile >= words * kPlaneBytes) {  // alive plane: mask rows the source never contained
+            const uint32_t r0 = tile * kTileRows + (in_tile - words * kPlaneBytes);
+            uint32_t* w = reinterpret_cast<uint32_t*>(&x);
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (w + k < words) v[k] = __ldcs(reinterpret_cast<const uint4*>(src + (w + k) * plane_bytes + woff));
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (w + k < words) __stcs(reinterpret_cast<uint4*>(dst + (w + k) * plane_bytes + woff), v[k]);
+            for (int k = 0; k < 4; ++k) w[k] &= rows_mask<4>(r0 + 4 * k, n_rows_src);
         }
-        uint32_t a = __ldcs(reinterpret_cast<const uint32_t*>(src + size_t(words) * plane_bytes + g * 4u));
-        a &= rows_mask<4>(g * 4u, n_rows_src);
-        __stcs(reinterpret_cast<uint32_t*>(dst + size_t(words) * plane_bytes + g * 4u), a);
+        __stcs(reinterpret_cast<uint4*>(dst) + v, x);
     }
 }
 
 // per-column XOR of per-entity hashes over live rows (component_checksum.rs:67-108), generic
-// byte range [off, off+len) of an element that is stored as `words` planes starting at first_plane.
+// byte range [off, off+len) of an element stored as word planes starting at first_plane.
 // acc[col_slot] ^= ..., acc[6] += live rows (only when count_alive), acc[7] |= nonfinite.
-__global__ void __launch_bounds__(256) k_checksum_column(const uint8_t* __restrict__ img, uint32_t epad,
-                                                         uint32_t total_words, uint32_t first_plane,
-                                                         uint32_t off, uint32_t len, uint32_t finite_flag,
-                                                         uint32_t n_rows, unsigned long long order_base,
-                                                         unsigned long long* acc, uint32_t col_slot,
-                                                         uint32_t count_alive, uint32_t hash_column) {
-    const size_t plane_bytes = size_t(epad) * 4u;
-    const uint8_t* alive = img + size_t(total_words) * plane_bytes;
+__global__ void __launch_bounds__(256) k_checksum_column(const uint8_t* __restrict__ img, uint32_t words,
+                                                         uint32_t first_plane, uint32_t off, uint32_t len,
+                                                         uint32_t finite_flag, uint32_t n_rows,
+                                                         unsigned long long order_base, unsigned long long* acc,
+                                                         uint32_t col_slot, uint32_t count_alive, uint32_t hash_column) {
     const uint32_t lane = threadIdx.x & 31u;
     uint64_t hx = 0;
     uint32_t cnt = 0, bad = 0;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r - lane < n_rows; r += gridDim.x * blockDim.x) {
-        if (r < n_rows && alive[r]) {
+        if (r < n_rows && img[alive_offset(words, r)]) {
             ++cnt;
             if (hash_column) {
+                const uint8_t* base = img + word_offset(words, r, first_plane);
                 auto byte_at = [&](uint32_t i) -> uint8_t {
                     uint32_t b = off + i;
-                    uint32_t w = *reinterpret_cast<const uint32_t*>(img + (first_plane + (b >> 2)) * plane_bytes + size_t(r) * 4u);
+                    uint32_t w = *reinterpret_cast<const uint32_t*>(base + size_t(b >> 2) * kPlaneBytes);
                     return uint8_t(w >> (8 * (b & 3u)));
                 };
                 if (finite_flag)
-                    for (uint32_t i = 0; i + 4 <= len; i += 4) {
-                        uint32_t w = uint32_t(byte_at(i)) | (uint32_t(byte_at(i + 1)) << 8) | (uint32_t(byte_at(i + 2)) << 16) | (uint32_t(byte_at(i + 3)) << 24);
-                        bad |= f32_bits_nonfinite(w);
-                    }
+                    for (uint32_t i = 0; i + 4 <= len; i += 4)
+                        bad |= f32_bits_nonfinite(*reinterpret_cast<const uint32_t*>(base + size_t((off + i) >> 2) * kPlaneBytes));
                 uint64_t custom = sea_hash_stream(len, byte_at);
                 hx ^= sea_hash_2xu64(order_base + r, custom);
             }
@@ -388,60 +474,90 @@ __global__ void k_publish(unsigned long long* accum, unsigned long long* out, ui
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = atomicExch(&accum[i], 0ULL);
 }
 
+// ---- ECS column (array of T, `stride` bytes apart) <-> tile-planar image -----------------------
+// one thread per (row, word); tail words of an element whose size is not a multiple of 4 are zero-padded
+__global__ void __launch_bounds__(256) k_scatter_column(uint8_t* img, uint32_t words, uint32_t first_plane,
+                                                        uint32_t col_words, uint32_t elem_bytes, uint32_t first_row,
+                                                        uint32_t count, const uint8_t* __restrict__ stage, uint32_t stride) {
+    const size_t n = size_t(count) * col_words;
+    for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += size_t(gridDim.x) * blockDim.x) {
+        const uint32_t i = uint32_t(t / col_words), w = uint32_t(t % col_words);
+        const uint8_t* s = stage + size_t(i) * stride + 4u * w;
+        uint32_t v = 0;
+        const uint32_t nb = min(4u, elem_bytes - 4u * w);
+        for (uint32_t b = 0; b < nb; ++b) v |= uint32_t(s[b]) << (8 * b);
+        *reinterpret_cast<uint32_t*>(img + word_offset(words, first_row + i, first_plane + w)) = v;
+    }
+}
+__global__ void __launch_bounds__(256) k_gather_column(const uint8_t* __restrict__ img, uint32_t words, uint32_t first_plane,
+                                                       uint32_t col_words, uint32_t elem_bytes, uint32_t first_row,
+                                                       uint32_t count, uint8_t* stage, uint32_t stride) {
+    const size_t n = size_t(count) * col_words;
+    for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += size_t(gridDim.x) * blockDim.x) {
+        const uint32_t i = uint32_t(t / col_words), w = uint32_t(t % col_words);
+        uint32_t v = *reinterpret_cast<const uint32_t*>(img + word_offset(words, first_row + i, first_plane + w));
+        uint8_t* d = stage + size_t(i) * stride + 4u * w;
+        const uint32_t nb = min(4u, elem_bytes - 4u * w);
+        for (uint32_t b = 0; b < nb; ++b) d[b] = uint8_t(v >> (8 * b));
+    }
+}
+// alive bytes of rows [first, first+count): gather to a dense array / set to a value
+__global__ void __launch_bounds__(256) k_gather_alive(const uint8_t* __restrict__ img, uint32_t words, uint32_t first_row,
+                                                      uint32_t count, uint32_t n_rows, uint8_t* out) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
+        out[i] = (first_row + i < n_rows) ? img[alive_offset(words, first_row + i)] : uint8_t(0);
+}
+// `commands.spawn((..., Rollback))`: zeroed components, alive = 1
+__global__ void __launch_bounds__(256) k_spawn_rows(uint8_t* img, uint32_t words, uint32_t first_row, uint32_t count) {
+    const size_t n = size_t(count) * (words + 1);
+    for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += size_t(gridDim.x) * blockDim.x) {
+        const uint32_t i = uint32_t(t / (words + 1)), w = uint32_t(t % (words + 1));
+        if (w < words) *reinterpret_cast<uint32_t*>(img + word_offset(words, first_row + i, w)) = 0u;
+        else img[alive_offset(words, first_row + i)] = 1;
+    }
+}
+__global__ void k_set_alive(uint8_t* img, uint32_t words, uint32_t row, uint8_t value) { img[alive_offset(words, row)] = value; }
+
 // ---- GgrsSchedule systems on the live image (stepwise path) ----
-__global__ void __launch_bounds__(256) k_sys_particles_update(uint8_t* img, uint32_t epad, uint32_t words,
-                                                              uint32_t t_plane, uint32_t v_plane, uint32_t n_rows,
-                                                              uint32_t dt_bits) {
-    const size_t pb = size_t(epad) * 4u;
-    const uint8_t* alive = img + size_t(words) * pb;
+__global__ void __launch_bounds__(256) k_sys_particles_update(uint8_t* img, uint32_t words, uint32_t t_plane,
+                                                              uint32_t v_plane, uint32_t n_rows, uint32_t dt_bits) {
     const float dt = __uint_as_float(dt_bits);
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
-        if (!alive[r]) continue;
-        uint32_t* t[3]; uint32_t* v[3];
-        for (int k = 0; k < 3; ++k) {
-            t[k] = reinterpret_cast<uint32_t*>(img + (t_plane + k) * pb) + r;
-            v[k] = reinterpret_cast<uint32_t*>(img + (v_plane + k) * pb) + r;
-        }
-        uint32_t tx = *t[0], ty = *t[1], tz = *t[2], vx = *v[0], vy = *v[1], vz = *v[2];
+        if (!img[alive_offset(words, r)]) continue;
+        uint32_t* t = reinterpret_cast<uint32_t*>(img + word_offset(words, r, t_plane));
+        uint32_t* v = reinterpret_cast<uint32_t*>(img + word_offset(words, r, v_plane));
+        uint32_t tx = t[0], ty = t[kTileRows], tz = t[2 * kTileRows], vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
         particle_step(tx, ty, tz, vx, vy, vz, dt);
-        *t[0] = tx; *t[1] = ty; *t[2] = tz; *v[0] = vx; *v[1] = vy; *v[2] = vz;
+        t[0] = tx; t[kTileRows] = ty; t[2 * kTileRows] = tz; v[0] = vx; v[kTileRows] = vy; v[2 * kTileRows] = vz;
     }
 }
 
-// `alive_next` receives the despawns; it is applied after every system of the schedule has run
+// `kill` receives the despawns; they are applied after every system of the schedule has run
 // (Commands are deferred to the end of GgrsSchedule).
-__global__ void __launch_bounds__(256) k_sys_particles_despawn(uint8_t* img, uint32_t epad, uint32_t words,
-                                                               uint32_t l_plane, uint32_t n_rows, uint8_t* kill) {
-    const size_t pb = size_t(epad) * 4u;
-    const uint8_t* alive = img + size_t(words) * pb;
+__global__ void __launch_bounds__(256) k_sys_particles_despawn(uint8_t* img, uint32_t words, uint32_t l_plane,
+                                                               uint32_t n_rows, uint8_t* kill) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
-        if (!alive[r]) continue;
-        uint32_t* lo = reinterpret_cast<uint32_t*>(img + l_plane * pb) + r;
-        uint32_t* hi = reinterpret_cast<uint32_t*>(img + (l_plane + 1) * pb) + r;
-        uint64_t ttl = (uint64_t(*hi) << 32) | *lo;
+        if (!img[alive_offset(words, r)]) continue;
+        uint32_t* l = reinterpret_cast<uint32_t*>(img + word_offset(words, r, l_plane));
+        uint64_t ttl = (uint64_t(l[kTileRows]) << 32) | l[0];
         ttl -= 1;
-        *lo = uint32_t(ttl); *hi = uint32_t(ttl >> 32);
+        l[0] = uint32_t(ttl); l[kTileRows] = uint32_t(ttl >> 32);
         if (ttl == 0) kill[r] = 1;
     }
 }
 
 // x.0 += k   (tests/component_rollback.rs:25-29)
-__global__ void __launch_bounds__(256) k_sys_u32_add(uint8_t* img, uint32_t epad, uint32_t words, uint32_t plane,
-                                                     uint32_t n_rows, uint32_t k) {
-    const size_t pb = size_t(epad) * 4u;
-    const uint8_t* alive = img + size_t(words) * pb;
+__global__ void __launch_bounds__(256) k_sys_u32_add(uint8_t* img, uint32_t words, uint32_t plane, uint32_t n_rows, uint32_t k) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
-        if (alive[r]) reinterpret_cast<uint32_t*>(img + plane * pb)[r] += k;
+        if (img[alive_offset(words, r)]) *reinterpret_cast<uint32_t*>(img + word_offset(words, r, plane)) += k;
 }
 
 // h = h.saturating_sub(k); despawn at 0   (tests/synctest.rs:38-45)
-__global__ void __launch_bounds__(256) k_sys_u32_satsub_despawn(uint8_t* img, uint32_t epad, uint32_t words,
-                                                                uint32_t plane, uint32_t n_rows, uint32_t k, uint8_t* kill) {
-    const size_t pb = size_t(epad) * 4u;
-    const uint8_t* alive = img + size_t(words) * pb;
+__global__ void __launch_bounds__(256) k_sys_u32_satsub_despawn(uint8_t* img, uint32_t words, uint32_t plane,
+                                                                uint32_t n_rows, uint32_t k, uint8_t* kill) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
-        if (!alive[r]) continue;
-        uint32_t* x = reinterpret_cast<uint32_t*>(img + plane * pb) + r;
+        if (!img[alive_offset(words, r)]) continue;
+        uint32_t* x = reinterpret_cast<uint32_t*>(img + word_offset(words, r, plane));
         uint32_t v = *x;
         v = v > k ? v - k : 0u;
         *x = v;
@@ -450,20 +566,15 @@ __global__ void __launch_bounds__(256) k_sys_u32_satsub_despawn(uint8_t* img, ui
 }
 
 // c.0 = count  (the deliberately non-deterministic system of tests/synctest.rs:92-97)
-__global__ void __launch_bounds__(256) k_sys_u32_store(uint8_t* img, uint32_t epad, uint32_t words, uint32_t plane,
-                                                       uint32_t n_rows, uint32_t value) {
-    const size_t pb = size_t(epad) * 4u;
-    const uint8_t* alive = img + size_t(words) * pb;
+__global__ void __launch_bounds__(256) k_sys_u32_store(uint8_t* img, uint32_t words, uint32_t plane, uint32_t n_rows, uint32_t value) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
-        if (alive[r]) reinterpret_cast<uint32_t*>(img + plane * pb)[r] = value;
+        if (img[alive_offset(words, r)]) *reinterpret_cast<uint32_t*>(img + word_offset(words, r, plane)) = value;
 }
 
 // apply deferred despawn commands: alive &= !kill ; kill = 0
-__global__ void __launch_bounds__(256) k_apply_despawns(uint8_t* img, uint32_t epad, uint32_t words, uint32_t n_rows,
-                                                        uint8_t* kill) {
-    uint8_t* alive = img + size_t(words) * size_t(epad) * 4u;
+__global__ void __launch_bounds__(256) k_apply_despawns(uint8_t* img, uint32_t words, uint32_t n_rows, uint8_t* kill) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
-        if (kill[r]) { alive[r] = 0; kill[r] = 0; }
+        if (kill[r]) { img[alive_offset(words, r)] = 0; kill[r] = 0; }
 }
 
 }  // namespace bgr
