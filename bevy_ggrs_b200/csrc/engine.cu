@@ -295,8 +295,8 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
     const bool simple = n_loads == 0 || (n_loads == 1 && pg.first_is_load);
     if (simple && e->tune_passive_tma && !e->runs.empty() && 2u * e->passive_bytes <= 96u * 1024u) pp.flags |= PF_PASSIVE_TMA;
     const Column& ct = e->cols[e->bt]; const Column& cv = e->cols[e->bv];
-    if (ct.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_T; if (ct.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_CK_FIN; pp.ck_t_slot = uint32_t(ct.ck_slot); }
-    if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_CK_FIN; pp.ck_v_slot = uint32_t(cv.ck_slot); }
+    if (ct.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_T; if (ct.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_T; pp.ck_t_slot = uint32_t(ct.ck_slot); }
+    if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_V; pp.ck_v_slot = uint32_t(cv.ck_slot); }
     pp.t_off = ct.first_plane * kPlaneBytes; pp.v_off = cv.first_plane * kPlaneBytes;
     pp.l_off = e->cols[e->bl].first_plane * kPlaneBytes; pp.alive_off = e->words * kPlaneBytes;
     pp.n_runs = uint32_t(e->runs.size()); pp.passive_bytes = e->passive_bytes;
@@ -624,7 +624,6 @@ void detect_bundles(bgr_engine* e) {
     if (e->runs.size() > size_t(kMaxRuns)) { e->runs.clear(); e->passive_bytes = 0; }
     const bool fin_t = e->cols[t].hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32, fin_v = e->cols[v].hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32;
     const bool ck_t = e->cols[t].hash_kind != BGR_HASH_NONE, ck_v = e->cols[v].hash_kind != BGR_HASH_NONE;
-    if (ck_t && ck_v && fin_t != fin_v) { e->passive.clear(); return; }  // mixed assertions: generic path
     e->bundle_static_ck = ck_t && ck_v && fin_t && fin_v;
     e->bt = t; e->bv = v; e->bl = l;
     e->bundle_particles = true;

@@ -66,7 +66,7 @@ enum ProgFlags : uint32_t {
     PF_WRITE_LIVE_ACTIVE = 2u,   // program contains LOAD or ADVANCE: final active planes go to image 0
     PF_WRITE_LIVE_PASSIVE = 4u,  // program contains LOAD: final passive planes go to image 0
     PF_PASSIVE_TMA = 8u,         // at most one LOAD and it is ops[0]: passive planes move by TMA bulk copies
-    PF_CK_T = 16u, PF_CK_V = 32u, PF_CK_FIN = 64u,  // which bundle columns are checksummed / assert finite
+    PF_CK_T = 16u, PF_CK_V = 32u, PF_FIN_T = 64u, PF_FIN_V = 128u,  // which bundle columns are checksummed / assert finite
 };
 
 struct PassiveRun { uint32_t off, bytes; };  // inside a tile; adjacent passive planes form one run
@@ -197,7 +197,8 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     // the flag tests fold away; otherwise they are warp-uniform runtime tests.
     const bool CKT = STATIC_CK ? true : (p.flags & PF_CK_T) != 0;
     const bool CKV = STATIC_CK ? true : (p.flags & PF_CK_V) != 0;
-    const bool FIN = STATIC_CK ? true : (p.flags & PF_CK_FIN) != 0;
+    const bool FINT = STATIC_CK ? true : (p.flags & PF_FIN_T) != 0;
+    const bool FINV = STATIC_CK ? true : (p.flags & PF_FIN_V) != 0;
     extern __shared__ __align__(128) uint8_t s_passive[];  // 2 x passive_bytes (double buffer)
     __shared__ unsigned long long s_acc[kMaxSaves * kAccStride];
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -296,12 +297,12 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                 for (int j = 0; j < VEC; ++j) {
                     const uint64_t live = ((alive >> (8 * j)) & 1u) ? ~0ULL : 0ULL;
                     if (CKT) {
-                        if (FIN) bad |= (f32_bits_nonfinite(tr[0][j]) | f32_bits_nonfinite(tr[1][j]) | f32_bits_nonfinite(tr[2][j])) & uint32_t(live);
+                        if (FINT) bad |= (f32_bits_nonfinite(tr[0][j]) | f32_bits_nonfinite(tr[1][j]) | f32_bits_nonfinite(tr[2][j])) & uint32_t(live);
                         uint64_t c = sea_hash_12(uint64_t(tr[0][j]) | (uint64_t(tr[1][j]) << 32), tr[2][j]);
                         hx_t ^= sea_hash_entity(t0[j], c) & live;
                     }
                     if (CKV) {
-                        if (FIN) bad |= (f32_bits_nonfinite(vl[0][j]) | f32_bits_nonfinite(vl[1][j]) | f32_bits_nonfinite(vl[2][j])) & uint32_t(live);
+                        if (FINV) bad |= (f32_bits_nonfinite(vl[0][j]) | f32_bits_nonfinite(vl[1][j]) | f32_bits_nonfinite(vl[2][j])) & uint32_t(live);
                         uint64_t c = sea_hash_12(uint64_t(vl[0][j]) | (uint64_t(vl[1][j]) << 32), vl[2][j]);
                         hx_v ^= sea_hash_entity(t0[j], c) & live;
                     }
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                 }
                 uint32_t cnt = __reduce_add_sync(full, n_alive);
                 if (lane == 0) atomicAdd(&a[6], (unsigned long long)cnt);
-                if (FIN) {
+                if (FINT || FINV) {
                     uint32_t anybad = __reduce_or_sync(full, bad);
                     if (lane == 0 && anybad) atomicOr(&a[7], 1ULL);
                 }

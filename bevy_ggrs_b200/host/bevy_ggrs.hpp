@@ -1,0 +1,227 @@
+// C++ host-side mirror of the bevy_ggrs plugin surface for the rollback hot path, above the C ABI
+// (include/bevy_ggrs_b200.h).  Same names, argument meaning and error behaviour as the reference:
+//
+//   App app(max_entities, max_depth);
+//   app.add_plugins(GgrsPlugin<GgrsConfig<uint8_t>>{})                 // lib.rs:198-258
+//      .insert_resource(RollbackFrameRate{60})                         // time.rs:19-26
+//      .add_systems(ReadInputs{}, read_local_inputs)                   // lib.rs:148-149
+//      .rollback_component_with_clone<Transform>()                     // rollback_app.rs:178-183
+//      .rollback_component_with_copy<Velocity>()                       // rollback_app.rs:157-162
+//      .checksum_component<Transform>(hash_bytes(0, 12, true))         // rollback_app.rs:227-232
+//      .add_systems(GgrsSchedule{}, System{BGR_SYS_PARTICLES_UPDATE, {col<Transform>, col<Velocity>}})
+//      .insert_resource(Session::SyncTest(ggrs::SyncTestSession(2, 8, 9, 2)))
+//      .add_observer([](const SyncTestMismatch& m) { ... });
+//   app.update();                                                      // run_ggrs_schedules, schedule_systems.rs:19-83
+//
+// A Rust panic becomes a C++ exception carrying the same text (`Panic`).  The "World" is the engine:
+// columns and the snapshot ring live in HBM, this layer holds no component data.
+#pragma once
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <optional>
+#include <stdexcept>
+#include <string>
+#include <typeindex>
+#include <typeinfo>
+#include <vector>
+
+#include "../../include/bevy_ggrs_b200.h"
+#include "ggrs_standin.hpp"
+
+namespace bevy_ggrs {
+
+struct Panic : std::runtime_error {
+    int status;
+    Panic(int s, const std::string& text) : std::runtime_error(text), status(s) {}
+};
+inline void check(int status) {
+    if (status != BGR_OK) throw Panic(status, bgr_last_error());
+}
+
+// ---- schedule labels / resources / events (lib.rs:73-149, snapshot/mod.rs:66-77) ----
+struct GgrsSchedule {};
+struct ReadInputs {};
+struct Startup {};
+struct RollbackFrameRate { size_t fps = 60; };
+struct LocalPlayers { std::vector<ggrs::PlayerHandle> handles; };
+struct LocalInputs { std::map<ggrs::PlayerHandle, uint8_t> inputs; };
+struct SyncTestMismatch { ggrs::Frame current_frame; std::vector<ggrs::Frame> mismatched_frames; };
+template <class Input = uint8_t> struct GgrsConfig { using input_type = Input; };
+template <class Config> struct GgrsPlugin {};
+
+struct Session {  // lib.rs:79-86 (SyncTest is the variant the tests and the bench drive)
+    enum Kind { SyncTestKind } kind = SyncTestKind;
+    std::shared_ptr<ggrs::SyncTestSession> synctest;
+    static Session SyncTest(ggrs::SyncTestSession s) { return Session{SyncTestKind, std::make_shared<ggrs::SyncTestSession>(std::move(s))}; }
+};
+
+// a compiled-in GgrsSchedule system: id + bound columns + scalar parameters
+struct System {
+    uint32_t id;
+    std::vector<uint32_t> columns;
+    std::vector<uint32_t> params;
+};
+
+// what a `fn(&T) -> u64` hasher becomes across the C ABI: seahash of a byte range of the element
+struct ByteRangeHasher { uint32_t offset, len; bool assert_finite; };
+inline ByteRangeHasher hash_bytes(uint32_t offset, uint32_t len, bool assert_finite = false) { return {offset, len, assert_finite}; }
+
+class App {
+public:
+    App(uint32_t max_entities, uint32_t max_depth, int device = 0, uint32_t flags = 0) {
+        bgr_config cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.abi_version = BGR_ABI_VERSION; cfg.device = device; cfg.max_entities = max_entities;
+        cfg.max_depth = max_depth; cfg.fps = 60; cfg.flags = flags;
+        cfg_ = cfg;
+    }
+    ~App() { if (engine_) bgr_engine_destroy(engine_); }
+    App(const App&) = delete;
+
+    template <class C> App& add_plugins(GgrsPlugin<C>) { return *this; }
+    App& insert_resource(RollbackFrameRate r) { cfg_.fps = uint32_t(r.fps); return *this; }
+    App& insert_resource(Session s) { session_ = std::move(s); return *this; }
+    App& insert_resource(LocalInputs li) { local_inputs_ = std::move(li); return *this; }
+    App& add_systems(ReadInputs, std::function<void(App&)> f) { read_inputs_.push_back(std::move(f)); return *this; }
+    App& add_systems(Startup, std::function<void(App&)> f) { startup_.push_back(std::move(f)); return *this; }
+    App& add_systems(GgrsSchedule, System s) { systems_.push_back(std::move(s)); return *this; }
+    App& add_observer(std::function<void(const SyncTestMismatch&)> f) { observers_.push_back(std::move(f)); return *this; }
+
+    // ---- RollbackApp (rollback_app.rs:31-248) ----
+    template <class T> App& rollback_component_with_copy() { return register_component<T>(BGR_STRATEGY_COPY); }
+    template <class T> App& rollback_component_with_clone() { return register_component<T>(BGR_STRATEGY_CLONE); }
+    template <class T> App& checksum_component(ByteRangeHasher h) { checksums_.push_back({col<T>(), h}); return *this; }
+    template <class T> App& checksum_component_with_hash() { return checksum_component<T>(hash_bytes(0, uint32_t(sizeof(T)))); }
+
+    template <class T> uint32_t col() const {
+        auto it = columns_.find(std::type_index(typeid(T)));
+        if (it == columns_.end()) throw Panic(BGR_ERR_INVALID_ARGUMENT, std::string("component not registered for rollback: ") + typeid(T).name());
+        return it->second;
+    }
+
+    // ---- World access ----
+    const LocalPlayers& local_players() const { return local_players_; }
+    uint32_t spawn(uint32_t count) { finish(); uint32_t first = 0; check(bgr_spawn(engine_, count, &first)); return first; }
+    template <class T> void write(uint32_t first_row, const std::vector<T>& v) {
+        finish();
+        check(bgr_write_component(engine_, col<T>(), first_row, uint32_t(v.size()), v.data(), uint32_t(sizeof(T))));
+    }
+    template <class T> std::vector<T> read(uint32_t first_row, uint32_t count) {
+        std::vector<T> v(count);
+        check(bgr_read_component(engine_, col<T>(), first_row, count, v.data(), uint32_t(sizeof(T))));
+        return v;
+    }
+    // GgrsComponentSnapshots<T>::peek(frame) (mod.rs:233-240)
+    template <class T> std::optional<std::vector<T>> peek(ggrs::Frame frame, uint32_t first_row, uint32_t count) {
+        std::vector<T> v(count);
+        int32_t found = 0;
+        check(bgr_peek(engine_, frame, col<T>(), first_row, count, v.data(), uint32_t(sizeof(T)), nullptr, &found));
+        if (!found) return std::nullopt;
+        return v;
+    }
+    uint64_t active_count() { uint64_t n = 0; check(bgr_active_count(engine_, &n)); return n; }
+    int32_t rollback_frame_count() { int32_t f = 0; check(bgr_rollback_frame_count(engine_, &f)); return f; }
+    int32_t confirmed_frame_count() { int32_t f = 0; check(bgr_confirmed_frame_count(engine_, &f)); return f; }
+    uint64_t launch_count() { uint64_t n = 0; check(bgr_launch_count(engine_, &n)); return n; }
+    bgr_engine* engine() { finish(); return engine_; }
+    const std::vector<bgr_checksum>& last_checksums() const { return last_checksums_; }
+
+    // ---- one Bevy frame: run_ggrs_schedules (schedule_systems.rs:19-83) ----
+    void update() {
+        finish();
+        // bevy Time<Real>: zero delta on the first update, then TimeUpdateStrategy::ManualDuration(1/60 s)
+        const uint64_t delta = first_update_ ? 0 : 16666667ull;
+        first_update_ = false;
+        const uint64_t fps_delta = run_slow_ ? 1000000000ull * 11 / (uint64_t(cfg_.fps) * 10) : 1000000000ull / cfg_.fps;
+        accumulator_ns_ += delta;
+        while (accumulator_ns_ >= fps_delta) {
+            accumulator_ns_ -= fps_delta;
+            if (!session_) { accumulator_ns_ = 0; run_slow_ = false; return; }
+            run_synctest(*session_->synctest);
+        }
+    }
+    // exactly one GGRS tick (benches)
+    void step() { finish(); run_synctest(*session_->synctest); }
+
+private:
+    template <class T> App& register_component(uint32_t strategy) {
+        static_assert(std::is_trivially_copyable<T>::value, "only POD components cross the C ABI");
+        pending_cols_.push_back({std::type_index(typeid(T)), typeid(T).name(), uint32_t(sizeof(T)), strategy});
+        columns_[std::type_index(typeid(T))] = uint32_t(pending_cols_.size() - 1);
+        return *this;
+    }
+    void finish() {  // end of App::build
+        if (engine_) return;
+        check(bgr_engine_create(&cfg_, &engine_));
+        for (auto& c : pending_cols_) { uint32_t id = 0; check(bgr_rollback_component(engine_, c.name.c_str(), c.bytes, c.strategy, &id)); }
+        for (auto& ck : checksums_)
+            check(bgr_checksum_component(engine_, ck.first, BGR_HASH_BYTES, ck.second.offset, ck.second.len,
+                                         ck.second.assert_finite ? BGR_HASH_FLAG_ASSERT_FINITE_F32 : 0u));
+        for (auto& s : systems_)
+            check(bgr_add_system(engine_, s.id, s.columns.data(), uint32_t(s.columns.size()), s.params.data(), uint32_t(s.params.size())));
+        check(bgr_build(engine_));
+        for (auto& f : startup_) f(*this);
+    }
+
+    // run_synctest (schedule_systems.rs:85-118)
+    void run_synctest(ggrs::SyncTestSession& sess) {
+        local_players_.handles.clear();
+        for (size_t i = 0; i < sess.num_players(); ++i) local_players_.handles.push_back(i);
+        local_inputs_.reset();
+        for (auto& f : read_inputs_) f(*this);  // world.run_schedule(ReadInputs)
+        if (!local_inputs_)
+            throw Panic(BGR_ERR_MISSING_RESOURCE, "No local player inputs found. Did you insert systems into the ReadInputs schedule?");
+        for (auto& kv : local_inputs_->inputs) sess.add_local_input(kv.first, kv.second);
+        std::vector<ggrs::GgrsRequest> requests;
+        ggrs::MismatchedChecksum err;
+        if (sess.advance_frame(requests, err)) handle_requests(requests, sess);
+        else {  // :104-115
+            SyncTestMismatch ev{err.current_frame, err.mismatched_frames};
+            for (auto& o : observers_) o(ev);
+        }
+    }
+
+    // handle_requests (schedule_systems.rs:170-289): ONE C-ABI call for the whole vector
+    void handle_requests(const std::vector<ggrs::GgrsRequest>& requests, ggrs::SyncTestSession& sess) {
+        bgr_session_info info{BGR_SESSION_SYNCTEST, uint32_t(sess.max_prediction()), uint32_t(sess.check_distance()), 0};
+        std::vector<bgr_request> reqs(requests.size());
+        for (size_t i = 0; i < requests.size(); ++i) {
+            bgr_request& q = reqs[i];
+            std::memset(&q, 0, sizeof q);
+            q.kind = uint32_t(requests[i].kind);
+            q.frame = requests[i].frame;
+            q.n_players = uint32_t(requests[i].inputs.size());
+            for (size_t p = 0; p < requests[i].inputs.size() && p < BGR_MAX_PLAYERS; ++p) {
+                q.inputs[p] = requests[i].inputs[p].first;
+                q.status[p] = uint8_t(requests[i].inputs[p].second);
+            }
+        }
+        last_checksums_.assign(BGR_MAX_REQUESTS, bgr_checksum{});
+        uint32_t n = 0;
+        check(bgr_handle_requests(engine_, &info, reqs.data(), uint32_t(reqs.size()), last_checksums_.data(), BGR_MAX_REQUESTS, &n));
+        last_checksums_.resize(n);
+        for (auto& cs : last_checksums_)  // cell.save(frame, None, checksum) (:231-236)
+            sess.save_cell(cs.frame, (static_cast<unsigned __int128>(cs.hi) << 64) | cs.lo);
+    }
+
+    struct PendingCol { std::type_index type; std::string name; uint32_t bytes, strategy; };
+    bgr_config cfg_{};
+    bgr_engine* engine_ = nullptr;
+    std::vector<PendingCol> pending_cols_;
+    std::map<std::type_index, uint32_t> columns_;
+    std::vector<std::pair<uint32_t, ByteRangeHasher>> checksums_;
+    std::vector<System> systems_;
+    std::vector<std::function<void(App&)>> read_inputs_, startup_;
+    std::vector<std::function<void(const SyncTestMismatch&)>> observers_;
+    std::optional<Session> session_;
+    std::optional<LocalInputs> local_inputs_;
+    LocalPlayers local_players_;
+    std::vector<bgr_checksum> last_checksums_;
+    uint64_t accumulator_ns_ = 0;
+    bool run_slow_ = false, first_update_ = true;
+};
+
+}  // namespace bevy_ggrs

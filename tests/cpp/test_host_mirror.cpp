@@ -1,0 +1,185 @@
+// The reference's SyncTest integration tests (tests/synctest.rs, tests/component_rollback.rs,
+// tests/common/mod.rs) and the particles stress test, written against the C++ host mirror
+// (bevy_ggrs_b200/host/bevy_ggrs.hpp) and therefore through the C ABI onto the GPU.
+// Exit code 0 = all passed.  Needs a B200 (run by tests/test_gpu_cpp_host_mirror.py, -m gpu);
+// `--no-gpu` only checks that the engine refuses to start without a device.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../bevy_ggrs_b200/host/bevy_ggrs.hpp"
+
+using namespace bevy_ggrs;
+
+static int g_failed = 0;
+#define EXPECT(cond)                                                                  \
+    do {                                                                              \
+        if (!(cond)) { std::printf("  FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); ++g_failed; } \
+    } while (0)
+
+// ---- components of the reference tests / examples ----
+struct Score { uint32_t v; };                                    // component_rollback.rs:22-23
+struct Health { uint32_t v; };                                   // synctest.rs:24-31
+struct Counter { uint32_t v; };                                  // synctest.rs:87-88
+struct FrameCounter { uint32_t v; };
+struct Transform { float translation[3]; float rotation[4]; float scale[3]; };  // 40 B payload
+struct Velocity { float v[3]; };                                 // particles.rs:104-105
+struct Ttl { uint64_t frames; };                                 // particles.rs:122-123
+
+// tests/common/mod.rs:16-22
+static void input_system(App& app) {
+    LocalInputs li;
+    for (auto h : app.local_players().handles) li.inputs[h] = 0;
+    app.insert_resource(li);
+}
+// tests/common/mod.rs:44-54
+static void base_synctest_app(App& app, size_t check_distance) {
+    app.insert_resource(Session::SyncTest(ggrs::SyncTestSession(1, check_distance)))
+        .add_plugins(GgrsPlugin<GgrsConfig<uint8_t>>{})
+        .add_systems(ReadInputs{}, input_system);
+}
+
+static void copy_strategy_rolls_back_component_data() {  // component_rollback.rs:33-64
+    std::printf("copy_strategy_rolls_back_component_data\n");
+    App app(16, 8);
+    base_synctest_app(app, 2);
+    app.rollback_component_with_copy<Score>().checksum_component_with_hash<Score>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_U32_ADD, {0}, {0, 1}});
+    app.add_systems(Startup{}, [](App& a) { a.write<Score>(a.spawn(1), {Score{0}}); });
+    bool mismatch = false;
+    app.add_observer([&](const SyncTestMismatch&) { mismatch = true; });
+    for (int i = 0; i < 20; ++i) app.update();
+    EXPECT(!mismatch);
+    EXPECT(app.rollback_frame_count() == 19);
+    EXPECT(app.read<Score>(0, 1)[0].v == uint32_t(app.rollback_frame_count()));
+}
+
+static void despawn_and_rollback_does_not_panic() {  // synctest.rs:59-75
+    std::printf("despawn_and_rollback_does_not_panic\n");
+    App app(16, 8);
+    base_synctest_app(app, 5);
+    app.rollback_component_with_copy<Health>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_U32_SATSUB_DESPAWN, {0}, {0, 1}});
+    app.add_systems(Startup{}, [](App& a) { a.write<Health>(a.spawn(1), {Health{10}}); });
+    for (int i = 0; i < 60; ++i) app.update();
+    EXPECT(app.active_count() == 0);
+}
+
+static void synctest_mismatch_fires_on_non_determinism() {  // synctest.rs:83-125
+    std::printf("synctest_mismatch_fires_on_non_determinism\n");
+    App app(16, 8);
+    base_synctest_app(app, 2);
+    app.rollback_component_with_copy<Counter>().checksum_component_with_hash<Counter>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_U32_STORE_CALL_COUNT, {0}, {0}});
+    app.add_systems(Startup{}, [](App& a) { a.spawn(1); });
+    bool detected = false;
+    app.add_observer([&](const SyncTestMismatch& m) { detected = true; EXPECT(!m.mismatched_frames.empty()); });
+    for (int i = 0; i < 10; ++i) app.update();
+    EXPECT(detected);
+}
+
+static void synctest_prunes_confirmed_snapshots() {  // synctest.rs:129-153
+    std::printf("synctest_prunes_confirmed_snapshots\n");
+    App app(16, 8);
+    base_synctest_app(app, 5);
+    app.rollback_component_with_clone<FrameCounter>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_U32_ADD, {0}, {0, 1}});
+    app.add_systems(Startup{}, [](App& a) { a.spawn(1); });
+    for (int i = 0; i < 20; ++i) app.update();
+    EXPECT(app.confirmed_frame_count() > 0);
+    EXPECT(!app.peek<FrameCounter>(0, 0, 1).has_value());
+    auto newest = app.peek<FrameCounter>(app.rollback_frame_count() - 1, 0, 1);
+    EXPECT(newest.has_value() && (*newest)[0].v == uint32_t(app.rollback_frame_count() - 1));
+}
+
+static void rollback_missing_frame_panics() {  // mod.rs:467-473 through the engine
+    std::printf("rollback_missing_frame_panics\n");
+    App app(16, 8);
+    app.rollback_component_with_copy<Score>();
+    app.spawn(1);
+    bgr_checksum cs;
+    check(bgr_save_world(app.engine(), &cs));
+    check(bgr_set_rollback_frame_count(app.engine(), 99));
+    bool panicked = false;
+    try { check(bgr_load_world(app.engine())); }
+    catch (const Panic& p) { panicked = std::string(p.what()).find("Could not rollback to 99") != std::string::npos && p.status == BGR_ERR_NO_SNAPSHOT; }
+    EXPECT(panicked);
+}
+
+static void particles_stress_synctest() {  // examples/stress_tests/particles.rs as a SyncTest (BASELINE C2 shape, small)
+    std::printf("particles_stress_synctest\n");
+    const uint32_t n = 20000;
+    App app(n, 9);
+    app.insert_resource(Session::SyncTest(ggrs::SyncTestSession(2, 8, 9, 2)))
+        .add_plugins(GgrsPlugin<GgrsConfig<uint8_t>>{})
+        .insert_resource(RollbackFrameRate{60})
+        .add_systems(ReadInputs{}, input_system)
+        .rollback_component_with_clone<Transform>()
+        .rollback_component_with_copy<Velocity>()
+        .rollback_component_with_copy<Ttl>()
+        .checksum_component<Velocity>(hash_bytes(0, 12, true))   // impl Hash for Velocity asserts is_finite (particles.rs:107-120)
+        .checksum_component<Transform>(hash_bytes(0, 12, true));
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_PARTICLES_UPDATE, {0, 1}, {}});
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_PARTICLES_DESPAWN, {2}, {}});
+    std::vector<Transform> t(n); std::vector<Velocity> v(n); std::vector<Ttl> l(n);
+    uint64_t s = 0x9E3779B97F4A7C15ull;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return float(double(s >> 11) / double(1ull << 53)); };
+    for (uint32_t i = 0; i < n; ++i) {
+        t[i] = Transform{{rnd() * 720.f - 360.f, rnd() * 720.f - 360.f, 0.f}, {0, 0, 0, 1}, {1, 1, 1}};
+        v[i] = Velocity{{rnd() * 400.f - 200.f, rnd() * 400.f - 200.f, 0.f}};
+        l[i] = Ttl{uint64_t(5 + (i % 40))};
+    }
+    uint32_t first = app.spawn(n);
+    app.write<Transform>(first, t); app.write<Velocity>(first, v); app.write<Ttl>(first, l);
+    bool mismatch = false;
+    app.add_observer([&](const SyncTestMismatch&) { mismatch = true; });
+    uint64_t l0 = app.launch_count();
+    const int ticks = 30;
+    for (int i = 0; i < ticks; ++i) app.step();
+    EXPECT(!mismatch);
+    EXPECT(app.rollback_frame_count() == ticks);
+    EXPECT(app.launch_count() - l0 == uint64_t(ticks));  // one fused launch per handle_requests
+    EXPECT(app.active_count() == uint64_t(std::count_if(l.begin(), l.end(), [&](const Ttl& x) { return x.frames > uint64_t(ticks); })));
+    // rotation / scale are passive: bit-identical after 30 frames of save/load/advance
+    auto t2 = app.read<Transform>(0, n);
+    bool passive_ok = true;
+    for (uint32_t i = 0; i < n; ++i)
+        passive_ok = passive_ok && std::memcmp(t2[i].rotation, t[i].rotation, 28) == 0;
+    EXPECT(passive_ok);
+    // a survivor moved under gravity exactly 30 steps: y velocity decreased by ~ 200*0.5
+    uint32_t k = n - 1;  // ttl 5 + (n-1)%40
+    while (l[k].frames <= uint64_t(ticks)) --k;
+    auto v2 = app.read<Velocity>(k, 1);
+    EXPECT(std::fabs((v[k].v[1] - v2[0].v[1]) - 100.0f) < 0.01f);
+}
+
+int main(int argc, char** argv) {
+    if (argc > 1 && std::string(argv[1]) == "--no-gpu") {
+        // the library must refuse loudly (no CPU fallback) when no device is usable
+        try {
+            App app(16, 8);
+            app.rollback_component_with_copy<Score>();
+            app.spawn(1);
+            std::printf("engine started: a GPU is present\n");
+            return 0;
+        } catch (const Panic& p) {
+            std::printf("refused: %s\n", p.what());
+            return (p.status == BGR_ERR_CUDA) ? 0 : 1;
+        }
+    }
+    try {
+        copy_strategy_rolls_back_component_data();
+        despawn_and_rollback_does_not_panic();
+        synctest_mismatch_fires_on_non_determinism();
+        synctest_prunes_confirmed_snapshots();
+        rollback_missing_frame_panics();
+        particles_stress_synctest();
+    } catch (const std::exception& e) {
+        std::printf("unexpected exception: %s\n", e.what());
+        return 2;
+    }
+    std::printf(g_failed ? "%d check(s) FAILED\n" : "all host-mirror tests passed\n", g_failed);
+    return g_failed ? 1 : 0;
+}

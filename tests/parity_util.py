@@ -67,18 +67,21 @@ def run_particles_synctest_pair(n_entities, check_distance, ticks, seed, max_pre
     app_o, cols_o, mism_o = make_particles_app(orc, n_entities, seed, Session.SyncTest(
         SyncTestSession(2, check_distance, maxp, input_delay=2)), ttl_lo, ttl_hi, noop_inputs=True)
     all_e, all_o = [], []
+    launches0 = eng.launch_count()
     for _ in range(ticks):
         app_e.step()
         app_o.step()
         all_e += app_e.last_checksums
         all_o += app_o.last_checksums
+    tick_launches = eng.launch_count() - launches0
+    fused = eng.last_path_fused()
     res = {
         "checksums_equal": all_e == all_o and len(all_e) > 0,
         "n_checksums": len(all_e),
         "state_equal": compare_state(eng, orc, cols_e, n_entities),
         "mismatch_events": (len(mism_e), len(mism_o)),
-        "fused": eng.last_path_fused(),
-        "launches": eng.launch_count(),
+        "fused": fused,
+        "launches": tick_launches,
         "frames": (eng.rollback_frame_count(), orc.rollback_frame_count()),
         "active": (eng.active_count(), orc.active_count()),
         "ring": (eng.snapshot_frames(), orc.snapshot_frames()),
