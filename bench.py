@@ -39,11 +39,12 @@ CHECK_DISTANCE = 8
 MAX_PREDICTION = 9       # ggrs requires check_distance < max_prediction
 SEED = 0xB200
 WORKLOADS = {
-    # name: (entities, check_distance, max_prediction)
-    "stress_1m_d8": (1_000_000, 8, 9),
-    "stress_100k_d8": (100_000, 8, 9),
-    "stress_1m_d16": (1_000_000, 16, 17),
-    "stress_10m_d32": (10_000_000, 32, 33),
+    # name: (entities, check_distance, max_prediction)   BASELINE.md configs
+    "stress_1m_d8": (1_000_000, 8, 9),        # the headline metric: 1M entities x 8-frame rollback
+    "stress_100k_d8": (100_000, 8, 9),        # C2
+    "stress_1m_d16": (1_000_000, 16, 17),     # C3
+    "p2p_1m_maxpred8": (1_000_000, 0, 8),     # C4: synthetic 2-peer P2P trace, input_delay 2, seed 0xB200
+    "stress_10m_d32": (10_000_000, 32, 33),   # C5
 }
 
 
@@ -112,10 +113,10 @@ def build_world(world, n, d, seed):
 
 def pregenerate_ticks(n_ticks, d, maxp, players=2):
     """Request vectors of a SyncTest session (they do not depend on checksum values unless a
-    mismatch occurs, which is checked afterwards)."""
+    mismatch occurs, which is checked afterwards); d == 0 selects the synthetic P2P trace (C4)."""
     from bevy_ggrs_b200 import capi
-    from bevy_ggrs_b200.session import SAVE, SyncTestSession, count_advances
-    sess = SyncTestSession(players, d, maxp, input_delay=2)
+    from bevy_ggrs_b200.session import SAVE, P2PTraceSession, SyncTestSession, count_advances
+    sess = SyncTestSession(players, d, maxp, input_delay=2) if d > 0 else P2PTraceSession(players, maxp, 2, seed=SEED)
     ticks = []
     for t in range(n_ticks):
         for h in range(players):
@@ -166,7 +167,7 @@ def run_ours(args):
     build_world(eng, n, d, SEED + rank)
     slot_bytes = eng.slot_bytes()
 
-    fill = d + 2                      # ticks until the request vector has its steady-state shape
+    fill = max(d, maxp) + 2           # ticks until the request vector has its steady-state shape
     ticks = pregenerate_ticks(fill + W + K + K, d, maxp)
     history = []
 
@@ -205,7 +206,8 @@ def run_ours(args):
         barrier()
         # ---------------- value: device-timed, K ticks back to back ----------------
         timed = ticks[fill + W: fill + W + K]
-        adv_per_tick = timed[0][2]
+        adv_total = sum(t[2] for t in timed)
+        adv_per_tick = adv_total / K
         sampler = ClockSampler(local_rank)
         if rank == 0:
             sampler.start()
@@ -243,15 +245,16 @@ def run_ours(args):
             t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
-        h2d = C.sizeof(capi.bgr_request) * e2e_ticks[0][1] + C.sizeof(capi.bgr_session_info)
-        d2h = 64 * len(e2e_ticks[0][4])  # one 8 x u64 result row per SaveGameState, written to pinned host memory
+        h2d = sum(C.sizeof(capi.bgr_request) * t[1] + C.sizeof(capi.bgr_session_info) for t in e2e_ticks) / K
+        d2h = sum(64 * len(t[4]) + 8 for t in e2e_ticks) / K  # one 8 x u64 result row per SaveGameState + the completion word, pinned host memory
 
     consistent = check_synctest_consistency(history)
     fused = eng.last_path_fused()
 
     # ---------------- roofline of the dominant (only) kernel ----------------
     ms_per_step = ms / K
-    alg_bytes = (d + 2) * slot_bytes          # read 1 slot + write d slots + write live
+    # per tick: read 1 image (slot or live) + write one slot per Save + write the live image
+    alg_bytes = sum(len(t[4]) + 2 for t in timed) / K * slot_bytes
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
     traffic = None
@@ -267,12 +270,12 @@ def run_ours(args):
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         cpu = run_cpu_sample(n, d, maxp, rollback_ticks=3)
     snap = None
-    if rank == 0 and world_size == 1:
+    if rank == 0 and world_size == 1 and not args.no_snapshot_bench:
         eng.close()
         snap = snapshot_bench(n, maxp, local_rank)
 
     if rank == 0:
-        value = world_size * adv_per_tick * K / (ms * 1e-3)
+        value = world_size * adv_total / (ms * 1e-3)
         line = {
             "metric": "rollback frames/sec at 1M entities x 8-frame window (SyncTest: 1 Load + 8 Save+checksum + 9 Advance per tick)",
             "value": value, "unit": "rollback frames/s", "n_gpus": world_size, "steps": K, "warmup": W,
@@ -285,7 +288,7 @@ def run_ours(args):
                        "sharding": f"entity-range x{world_size}, all_gather of checksum partials" if sharded else "none"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "e2e": {"value": world_size * adv_per_tick * K / e2e_s, "unit": "rollback frames/s",
+            "e2e": {"value": world_size * sum(t[2] for t in e2e_ticks) / e2e_s, "unit": "rollback frames/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "note": "bgr_handle_requests per tick: request vector from host memory, checksums to host memory; "
                             "component columns live in HBM by design and never cross"},
@@ -426,6 +429,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="stress_1m_d8", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-snapshot-bench", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -125,7 +125,8 @@ _LIB: Optional[C.CDLL] = None
 
 
 def library_path() -> str:
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbevy_ggrs_b200.so")
+    # BGR_LIBRARY: an alternative build of the same library (tuning experiments only)
+    return os.environ.get("BGR_LIBRARY") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libbevy_ggrs_b200.so")
 
 
 def load_library() -> C.CDLL:

@@ -30,13 +30,17 @@
 
 namespace bgr {
 
-constexpr uint32_t kTileRows = 512;
+#ifndef BGR_TILE_ROWS
+#define BGR_TILE_ROWS 512
+#endif
+constexpr uint32_t kTileRows = BGR_TILE_ROWS;
 constexpr uint32_t kPlaneBytes = kTileRows * 4;  // one word plane inside a tile
 constexpr int kMaxOps = 80;       // == BGR_MAX_REQUESTS
 constexpr int kMaxSaves = 40;
 constexpr int kMaxPassive = 64;   // word planes that no compiled system touches (per-thread fallback)
 constexpr int kMaxRuns = 8;       // runs of adjacent passive planes (TMA path)
 constexpr int kAccStride = 8;     // u64 per save: [0..5] column xors, [6] active rows, [7] flags
+constexpr int kSeqIndex = kMaxSaves * kAccStride;  // result block word that receives the launch sequence number last
 
 __host__ __device__ inline uint32_t tile_bytes_of(uint32_t words) { return kTileRows * (4u * words + 1u); }
 __host__ __device__ inline size_t word_offset(uint32_t words, uint32_t row, uint32_t plane) {
@@ -67,6 +71,7 @@ enum ProgFlags : uint32_t {
     PF_WRITE_LIVE_PASSIVE = 4u,  // program contains LOAD: final passive planes go to image 0
     PF_PASSIVE_TMA = 8u,         // at most one LOAD and it is ops[0]: passive planes move by TMA bulk copies
     PF_CK_T = 16u, PF_CK_V = 32u, PF_FIN_T = 64u, PF_FIN_V = 128u,  // which bundle columns are checksummed / assert finite
+    PF_DYNAMIC_TILES = 256u,     // tiles handed out by an atomic counter instead of a static stride
 };
 
 struct PassiveRun { uint32_t off, bytes; };  // inside a tile; adjacent passive planes form one run
@@ -76,7 +81,8 @@ struct ProgramParams {
     unsigned long long order_base;
     unsigned long long* accum;  // device [kMaxSaves][kAccStride]
     unsigned long long* out;    // host-mapped [kMaxSaves][kAccStride]
-    unsigned int* ticket;
+    unsigned int* ticket;       // [0] block-completion ticket, [1] dynamic tile counter
+    unsigned long long seq;     // written to out[kSeqIndex] after the results (completion flag the host polls)
     uint32_t words, tile_bytes, n_tiles, n_ops, n_saves;
     uint32_t live_rows, flags;
     uint32_t t_off, v_off, l_off, alive_off;  // byte offsets inside a tile of Transform / Velocity / Ttl word 0 / alive plane
@@ -215,8 +221,21 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     __syncthreads();
 
     const uint32_t i0 = tid * VEC;  // first row of this thread inside the tile
+    __shared__ uint32_t s_tile;
+    const bool dynamic = (p.flags & PF_DYNAMIC_TILES) != 0;
     uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t tile = blockIdx.x;; ++it) {
+        if (dynamic) {
+            if (it > 0) {
+                __syncthreads();
+                if (tid == 0) s_tile = gridDim.x + atomicAdd(&p.ticket[1], 1u);
+                __syncthreads();
+                tile = s_tile;
+            }
+        } else if (it > 0) {
+            tile += gridDim.x;
+        }
+        if (tile >= p.n_tiles) break;
         const size_t tile_off = size_t(tile) * p.tile_bytes;
         const uint32_t row0 = tile * kTileRows + i0;
         const size_t woff = tile_off + size_t(i0) * 4u;  // + plane offset (+ image offset) = address of this thread's words
@@ -273,6 +292,20 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
 #pragma unroll
         for (int j = 0; j < VEC; ++j) t0[j] = sea_order_lane(p.order_base + row0 + j);
 
+        uint32_t pend[6] = {0, 0, 0, 0, 0, 0};
+        uint32_t pend_row = 0;
+        bool pend_valid = false;
+        auto flush_pending = [&]() {
+            if (pend_valid && lane == 0) {
+                unsigned long long* a = &s_acc[pend_row];
+                if (CKT) atomicXor(&a[p.ck_t_slot], (unsigned long long)pend[0] | ((unsigned long long)pend[1] << 32));
+                if (CKV) atomicXor(&a[p.ck_v_slot], (unsigned long long)pend[2] | ((unsigned long long)pend[3] << 32));
+                atomicAdd(&a[6], (unsigned long long)pend[4]);
+                if (pend[5]) atomicOr(&a[7], 1ULL);
+            }
+            pend_valid = false;
+        };
+
         for (uint32_t i = (p.flags & PF_READ_LIVE) ? 0u : 1u; i < p.n_ops; ++i) {
             const uint32_t kind = p.ops[i].kind;
             if (kind == OP_ADVANCE) {
@@ -308,27 +341,21 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                     }
                 }
                 const uint32_t n_alive = __popc(alive & 0x01010101u);
-                // warp-level fold (REDUX), then one shared-memory atomic per warp
+                // warp-level fold (REDUX) now, shared-memory atomics at the NEXT save (or after the op
+                // loop): the REDUX latency is covered by the following ADVANCE instead of stalling lane 0
+                flush_pending();
                 const unsigned full = 0xffffffffu;
-                unsigned long long* a = &s_acc[p.ops[i].save_index * kAccStride];
-                if (CKT) {
-                    uint32_t lo = __reduce_xor_sync(full, uint32_t(hx_t)), hi = __reduce_xor_sync(full, uint32_t(hx_t >> 32));
-                    if (lane == 0) atomicXor(&a[p.ck_t_slot], (unsigned long long)lo | ((unsigned long long)hi << 32));
-                }
-                if (CKV) {
-                    uint32_t lo = __reduce_xor_sync(full, uint32_t(hx_v)), hi = __reduce_xor_sync(full, uint32_t(hx_v >> 32));
-                    if (lane == 0) atomicXor(&a[p.ck_v_slot], (unsigned long long)lo | ((unsigned long long)hi << 32));
-                }
-                uint32_t cnt = __reduce_add_sync(full, n_alive);
-                if (lane == 0) atomicAdd(&a[6], (unsigned long long)cnt);
-                if (FINT || FINV) {
-                    uint32_t anybad = __reduce_or_sync(full, bad);
-                    if (lane == 0 && anybad) atomicOr(&a[7], 1ULL);
-                }
+                if (CKT) { pend[0] = __reduce_xor_sync(full, uint32_t(hx_t)); pend[1] = __reduce_xor_sync(full, uint32_t(hx_t >> 32)); }
+                if (CKV) { pend[2] = __reduce_xor_sync(full, uint32_t(hx_v)); pend[3] = __reduce_xor_sync(full, uint32_t(hx_v >> 32)); }
+                pend[4] = __reduce_add_sync(full, n_alive);
+                pend[5] = (FINT || FINV) ? __reduce_or_sync(full, bad) : 0u;
+                pend_row = p.ops[i].save_index * kAccStride;
+                pend_valid = true;
             } else {  // OP_LOAD
                 load_active(p.arena + (size_t(p.ops[i].image_off256) << 8), p.ops[i].n_rows);
             }
         }
+        flush_pending();
         if (p.flags & PF_WRITE_LIVE_ACTIVE) store_active(p.arena);
 
         // ------------------------------ passive planes ------------------------------
@@ -402,7 +429,13 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         __threadfence();
         for (uint32_t i = tid; i < p.n_saves * kAccStride; i += BLOCK)
             p.out[i] = atomicExch(&p.accum[i], 0ULL);  // publish and re-arm for the next launch
-        if (tid == 0) *p.ticket = 0u;
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            p.ticket[0] = 0u;
+            p.ticket[1] = 0u;
+            *reinterpret_cast<volatile unsigned long long*>(&p.out[kSeqIndex]) = p.seq;  // host polls this word
+        }
     }
 }
 
@@ -471,8 +504,11 @@ __global__ void __launch_bounds__(256) k_checksum_column(const uint8_t* __restri
 }
 
 // copy the accumulators of n_saves saves to the host-mapped result block and re-arm them
-__global__ void k_publish(unsigned long long* accum, unsigned long long* out, uint32_t n) {
+__global__ void k_publish(unsigned long long* accum, unsigned long long* out, uint32_t n, unsigned long long seq) {
     for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = atomicExch(&accum[i], 0ULL);
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(&out[kSeqIndex]) = seq;
 }
 
 // ---- ECS column (array of T, `stride` bytes apart) <-> tile-planar image -----------------------
