@@ -313,16 +313,17 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
     const int v = e->tune_vec;
     const bool st = e->bundle_static_ck;
     const bool hi = e->tune_minb > 1;
-#define BGR_LAUNCH(VEC, VI, MINB_HI)                                                                       \
+#define BGR_LAUNCH(VEC, VI)                                                                                \
     if (v == VEC) {                                                                                        \
-        if (st && hi) return launch_particles<VEC, true, MINB_HI>(e, pp, VI, 1, 1);                        \
+        constexpr int kHi = (1024 / int(kTileRows / VEC)) > 32 ? 32 : (1024 / int(kTileRows / VEC));        \
+        if (st && hi) return launch_particles<VEC, true, kHi>(e, pp, VI, 1, 1);                            \
         if (st) return launch_particles<VEC, true, 1>(e, pp, VI, 1, 0);                                    \
-        if (hi) return launch_particles<VEC, false, MINB_HI>(e, pp, VI, 0, 1);                             \
+        if (hi) return launch_particles<VEC, false, kHi>(e, pp, VI, 0, 1);                                 \
         return launch_particles<VEC, false, 1>(e, pp, VI, 0, 0);                                           \
     }
-    BGR_LAUNCH(1, 0, 2)
-    BGR_LAUNCH(4, 2, 6)
-    BGR_LAUNCH(2, 1, 4)
+    BGR_LAUNCH(1, 0)
+    BGR_LAUNCH(4, 2)
+    BGR_LAUNCH(2, 1)
 #undef BGR_LAUNCH
     return fail(BGR_ERR_STATE, "bad BGR_TUNE_VEC");
 }
@@ -797,7 +798,7 @@ BGR_API int bgr_build(bgr_engine* e) {
     e->epad = (e->cfg.max_entities + kTileRows - 1) / kTileRows * kTileRows;
     e->n_tiles_cap = e->epad / kTileRows;
     e->tile_bytes = tile_bytes_of(e->words);
-    e->image_bytes = size_t(e->n_tiles_cap) * e->tile_bytes;  // multiple of 512
+    e->image_bytes = (size_t(e->n_tiles_cap) * e->tile_bytes + 255u) & ~size_t(255);  // ops address images in 256-byte units
     if ((e->image_bytes * (size_t(e->cfg.max_depth) + 1u)) >> 8 > 0xffffffffull)
         return fail(BGR_ERR_CAPACITY, "arena larger than 1 TB");
     size_t total = e->image_bytes * (size_t(e->cfg.max_depth) + 1u);

@@ -206,12 +206,12 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     const bool FINT = STATIC_CK ? true : (p.flags & PF_FIN_T) != 0;
     const bool FINV = STATIC_CK ? true : (p.flags & PF_FIN_V) != 0;
     extern __shared__ __align__(128) uint8_t s_passive[];  // 2 x passive_bytes (double buffer)
-    __shared__ unsigned long long s_acc[kMaxSaves * kAccStride];
+    __shared__ unsigned int s_acc[kMaxSaves * kAccStride * 2];  // 32-bit halves: native shared atomics, no CAS loop
     __shared__ __align__(8) uint64_t s_bar[2];
     __shared__ unsigned int s_last;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    for (uint32_t i = tid; i < p.n_saves * kAccStride; i += BLOCK) s_acc[i] = 0ULL;
+    for (uint32_t i = tid; i < p.n_saves * kAccStride * 2; i += BLOCK) s_acc[i] = 0u;
     const bool use_tma = (p.flags & PF_PASSIVE_TMA) && p.n_runs > 0;
     if (tid == 0 && use_tma) {
         mbar_init(&s_bar[0], 1);
@@ -221,21 +221,14 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     __syncthreads();
 
     const uint32_t i0 = tid * VEC;  // first row of this thread inside the tile
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile[2];
     const bool dynamic = (p.flags & PF_DYNAMIC_TILES) != 0;
     uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x;; ++it) {
-        if (dynamic) {
-            if (it > 0) {
-                __syncthreads();
-                if (tid == 0) s_tile = gridDim.x + atomicAdd(&p.ticket[1], 1u);
-                __syncthreads();
-                tile = s_tile;
-            }
-        } else if (it > 0) {
-            tile += gridDim.x;
-        }
-        if (tile >= p.n_tiles) break;
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; ++it) {
+        // dynamic scheduling: thread 0 claims the NEXT tile now (the atomic's round trip hides behind
+        // this tile's work) and publishes it at the bottom of the iteration
+        uint32_t next_tile = tile + gridDim.x;
+        if (dynamic && tid == 0) next_tile = gridDim.x + atomicAdd(&p.ticket[1], 1u);
         const size_t tile_off = size_t(tile) * p.tile_bytes;
         const uint32_t row0 = tile * kTileRows + i0;
         const size_t woff = tile_off + size_t(i0) * 4u;  // + plane offset (+ image offset) = address of this thread's words
@@ -297,11 +290,11 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         bool pend_valid = false;
         auto flush_pending = [&]() {
             if (pend_valid && lane == 0) {
-                unsigned long long* a = &s_acc[pend_row];
-                if (CKT) atomicXor(&a[p.ck_t_slot], (unsigned long long)pend[0] | ((unsigned long long)pend[1] << 32));
-                if (CKV) atomicXor(&a[p.ck_v_slot], (unsigned long long)pend[2] | ((unsigned long long)pend[3] << 32));
-                atomicAdd(&a[6], (unsigned long long)pend[4]);
-                if (pend[5]) atomicOr(&a[7], 1ULL);
+                unsigned int* a = &s_acc[pend_row * 2];
+                if (CKT) { atomicXor(&a[2 * p.ck_t_slot], pend[0]); atomicXor(&a[2 * p.ck_t_slot + 1], pend[1]); }
+                if (CKV) { atomicXor(&a[2 * p.ck_v_slot], pend[2]); atomicXor(&a[2 * p.ck_v_slot + 1], pend[3]); }
+                atomicAdd(&a[12], pend[4]);
+                if (pend[5]) atomicOr(&a[14], 1u);
             }
             pend_valid = false;
         };
@@ -407,13 +400,20 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                 }
             }
         }
+        if (dynamic) {
+            if (tid == 0) s_tile[it & 1u] = next_tile;
+            __syncthreads();
+            tile = s_tile[it & 1u];
+        } else {
+            tile = next_tile;
+        }
     }
     if (use_tma && tid == 0) tma_wait_all();  // every bulk store has landed before the results are published
 
     // ---- block partials -> global accumulators -> (last block) host-visible results ----
     __syncthreads();
     for (uint32_t i = tid; i < p.n_saves * kAccStride; i += BLOCK) {
-        unsigned long long v = s_acc[i];
+        unsigned long long v = (unsigned long long)s_acc[2 * i] | ((unsigned long long)s_acc[2 * i + 1] << 32);
         uint32_t c = i % kAccStride;
         if (v) {
             if (c == 6) atomicAdd(&p.accum[i], v);
