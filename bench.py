@@ -176,10 +176,21 @@ def run_ours(args):
         from bevy_ggrs_b200.sharded import all_fold
         return all_fold(partials_list, device=dev)
 
+    pending_partials = []
+
+    def flush_partials():
+        if pending_partials:
+            history.extend(fold_all(list(pending_partials)))
+            pending_partials.clear()
+
     def collect_one():
         cs = eng.collect()
         if sharded:
-            history.extend(fold_all(eng.last_partials()))
+            # the cross-shard exchange is batched: desync checksums are only consumed every few frames
+            # (the stress example exchanges them every 10, particles.rs:48-50)
+            pending_partials.extend(eng.last_partials())
+            if len(pending_partials) >= 16 * max(1, d):
+                flush_partials()
         else:
             history.extend(cs)
 
@@ -194,6 +205,8 @@ def run_ours(args):
         while inflight:
             collect_one()
             inflight -= 1
+        if sharded:
+            flush_partials()
 
     def barrier():
         torch.cuda.synchronize()
