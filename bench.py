@@ -176,23 +176,24 @@ def run_ours(args):
         from bevy_ggrs_b200.sharded import all_fold
         return all_fold(partials_list, device=dev)
 
-    pending_partials = []
+    pbuf = None
+    if sharded:
+        from bevy_ggrs_b200.sharded import PartialBuffer, all_fold_array
+        pbuf = PartialBuffer(64 * (maxp + 2))
 
     def flush_partials():
-        if pending_partials:
-            history.extend(fold_all(list(pending_partials)))
-            pending_partials.clear()
+        if pbuf.n:
+            history.extend(all_fold_array(pbuf.take(), device=dev))
 
     def collect_one():
-        cs = eng.collect()
         if sharded:
-            # the cross-shard exchange is batched: desync checksums are only consumed every few frames
-            # (the stress example exchanges them every 10, particles.rs:48-50)
-            pending_partials.extend(eng.last_partials())
-            if len(pending_partials) >= 16 * max(1, d):
+            # the cross-shard exchange is batched (one all_gather per ~32 ticks): desync checksums are only
+            # consumed every few frames (the stress example exchanges them every 10, particles.rs:48-50)
+            pbuf.collect_from(eng)
+            if pbuf.n >= 32 * max(1, d):
                 flush_partials()
         else:
-            history.extend(cs)
+            history.extend(eng.collect())
 
     def run_pipelined(tick_list):
         inflight = 0

@@ -1009,6 +1009,21 @@ BGR_API int bgr_fold_partials(const bgr_partial* combined, bgr_checksum* out) {
     return BGR_OK;
 }
 
+BGR_API int bgr_collect_partials(bgr_engine* e, bgr_partial* partials_out, uint32_t cap, uint32_t* n_out) {
+    uint32_t n = 0;
+    int rc = collect(e, nullptr, 0, &n);
+    if (rc != BGR_OK) return rc;
+    for (uint32_t i = 0; i < n && i < cap && partials_out; ++i) partials_out[i] = e->last_partials[i];
+    if (n_out) *n_out = n;
+    return BGR_OK;
+}
+
+BGR_API int bgr_fold_partials_n(const bgr_partial* combined, uint32_t n, bgr_checksum* out) {
+    if ((!combined || !out) && n) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    for (uint32_t i = 0; i < n; ++i) fold(combined[i], &out[i]);
+    return BGR_OK;
+}
+
 BGR_API uint32_t bgr_ggrs_time_delta_bits(uint32_t fps, int32_t frame) {
     if (fps == 0) return 0;
     uint64_t f = uint64_t(int64_t(frame));

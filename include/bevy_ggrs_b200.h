@@ -221,6 +221,10 @@ BGR_API int bgr_collect(bgr_engine* e, bgr_checksum* checksums_out, uint32_t che
  * (component_checksum.rs:93-95, entity_checksum.rs:35-43, checksum.rs:88-99). */
 BGR_API int bgr_last_partials(bgr_engine* e, bgr_partial* out, uint32_t cap, uint32_t* n_out);
 BGR_API int bgr_fold_partials(const bgr_partial* combined, bgr_checksum* out);
+/* bgr_collect that writes the raw partials of the collected call straight into caller memory (sharded hot loop:
+ * no per-tick allocation), and the fold over an array of already combined partials. */
+BGR_API int bgr_collect_partials(bgr_engine* e, bgr_partial* partials_out, uint32_t cap, uint32_t* n_out);
+BGR_API int bgr_fold_partials_n(const bgr_partial* combined, uint32_t n, bgr_checksum* out);
 
 /* ---- GgrsTime (src/time.rs:63-76): delta_secs of the step that ends at `frame` ---------- */
 BGR_API uint32_t bgr_ggrs_time_delta_bits(uint32_t fps, int32_t frame);

@@ -25,7 +25,8 @@ def _worker(rank, world, port, n_total, seed, ticks, d, q):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import torch.distributed as dist
     from bevy_ggrs_b200.session import SAVE, SyncTestSession
-    from bevy_ggrs_b200.sharded import all_fold, shard_range
+    import numpy as np
+    from bevy_ggrs_b200.sharded import PARTIAL_DTYPE, all_fold, all_fold_array, shard_range
     from bevy_ggrs_b200.stress import populate, register_particles, synth_particles
     from oracle_backend import OracleWorld
 
@@ -37,6 +38,7 @@ def _worker(rank, world, port, n_total, seed, ticks, d, q):
     populate(w, cols, tf[first:first + count], vel[first:first + count], ttl[first:first + count])
     sess = SyncTestSession(1, d, 8)
     got = []
+    raw = []
     for t in range(ticks):
         sess.add_local_input(0, 0)
         reqs = sess.advance_frame()
@@ -44,10 +46,15 @@ def _worker(rank, world, port, n_total, seed, ticks, d, q):
         for r in reqs:
             w.handle_requests(sess.info(), [r])
             if r.kind == SAVE:
-                folded = all_fold([w.last_partial()])
+                part = w.last_partial()
+                raw.append((part.frame, part.n_columns, part.active, part.total, tuple(part.xor_[c] for c in range(6))))
+                folded = all_fold([part])
                 frame, cs = folded[0]
                 sess.save_cell(r.frame, cs)
                 got.append((r.frame, cs))
+    # the batched, vectorised fold used by bench.py must agree with the per-save fold
+    arr = np.array(raw, dtype=PARTIAL_DTYPE)
+    assert all_fold_array(arr) == got
     if rank == 0:
         q.put(got)
     dist.barrier()
