@@ -31,6 +31,8 @@ BGR_SYS_BOX_MOVE = 3
 BGR_SYS_U32_ADD = 4
 BGR_SYS_U32_SATSUB_DESPAWN = 5
 BGR_SYS_U32_STORE_CALL_COUNT = 6
+BGR_SYS_PARTICLES_SPAWN = 7
+BGR_INPUT_SPAWN = 0x10
 # bgr_request_kind
 BGR_REQ_SAVE, BGR_REQ_LOAD, BGR_REQ_ADVANCE = 0, 1, 2
 # bgr_session_kind
@@ -80,6 +82,7 @@ PROTOTYPES = {
     "bgr_checksum_component": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
     "bgr_add_system": (C.c_int, [C.c_void_p, C.c_uint32, u32p, C.c_uint32, u32p, C.c_uint32]),
     "bgr_build": (C.c_int, [C.c_void_p]),
+    "bgr_run_startup_system": (C.c_int, [C.c_void_p, C.c_uint32]),
     "bgr_spawn": (C.c_int, [C.c_void_p, C.c_uint32, u32p]),
     "bgr_despawn": (C.c_int, [C.c_void_p, C.c_uint32]),
     "bgr_row_count": (C.c_int, [C.c_void_p, u32p]),

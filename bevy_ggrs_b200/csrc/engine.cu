@@ -50,6 +50,46 @@ struct SystemReg {
 
 constexpr uint32_t kReqAdvanceNoBump = 100;  // bgr_advance_world: caller already bumped RollbackFrameCount
 
+// ParticleRng = rand_xoshiro::Xoshiro256PlusPlus (particles.rs:125-128), kept host-side and rolled back with
+// every snapshot like the reference's rollback_resource_with_clone::<ParticleRng>() (:200).  Third-party
+// arithmetic restated from the published algorithms (rand_xoshiro 0.7 / rand 0.9): SplitMix64 seeding,
+// xoshiro256++ step, next_u32 = upper half, f32 range sample = ((u32 >> 9 | 0x3f800000) as f32 - 1) * scale + low.
+struct ParticleRng {
+    uint64_t s[4] = {0, 0, 0, 0};
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    void seed_from_u64(uint64_t seed) {
+        uint64_t x = seed;
+        for (int i = 0; i < 4; ++i) {
+            x += 0x9E3779B97F4A7C15ULL;
+            uint64_t z = x;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+            s[i] = z ^ (z >> 31);
+        }
+    }
+    uint32_t next_u32() {
+        uint64_t result = rotl(s[0] + s[3], 23) + s[0];
+        uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return uint32_t(result >> 32);
+    }
+    float random_range(float low, float high) {  // rng.random_range(low..high)
+        const float scale = high - low;
+        for (;;) {
+            uint32_t bits = (next_u32() >> 9) | 0x3f800000u;
+            float v12; std::memcpy(&v12, &bits, 4);
+            volatile float v01 = v12 - 1.0f;
+            volatile float prod = v01 * scale;   // mul and add rounded separately (no contraction)
+            float res = prod + low;
+            if (res < high) return res;
+        }
+    }
+};
+
+constexpr uint32_t kMaxSpawnVals = 1u << 16;  // particles spawned by one request vector
+
 // Every host-side resource handle_requests / the schedules mutate.  A request vector is compiled
 // against a copy and committed only if the whole vector is valid.
 struct HostState {
@@ -63,6 +103,8 @@ struct HostState {
     uint64_t elapsed_ns = 0;                // Time<GgrsTime>::elapsed
     uint32_t n_rows = 0;                    // RollbackOrdered::len()
     uint32_t call_count = 0;                // un-rolled-back counter of BGR_SYS_U32_STORE_CALL_COUNT
+    ParticleRng rng;                        // ParticleRng resource (particles.rs:128)
+    std::vector<ParticleRng> slot_rng;      // its per-snapshot clones
 };
 
 struct Pending {
@@ -110,6 +152,9 @@ struct bgr_engine {
     static constexpr int kBufs = 4;
     unsigned long long* d_accum = nullptr;
     unsigned int* d_ticket = nullptr;
+    float2* h_spawn[kBufs] = {nullptr, nullptr, nullptr, nullptr};  // host-mapped (vx, vy) of spawned particles
+    float2* d_spawn[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    int spawn_sys = -1;             // index of BGR_SYS_PARTICLES_SPAWN in `systems`, or -1
     unsigned long long* h_out[kBufs] = {nullptr, nullptr, nullptr, nullptr};
     unsigned long long* d_out[kBufs] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t ev[kBufs] = {nullptr, nullptr, nullptr, nullptr};
@@ -156,7 +201,8 @@ struct Program {
     int32_t save_frames[kMaxSaves];
     uint32_t save_totals[kMaxSaves];
     uint32_t max_rows = 0, live_rows = 0;
-    bool has_load = false, has_advance = false, first_is_load = false;
+    bool has_load = false, has_advance = false, first_is_load = false, has_spawn = false;
+    std::vector<float2> spawn_vals;
 };
 
 int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, const bgr_request* reqs, uint32_t n,
@@ -205,6 +251,7 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
                 op.image_off256 = e->image_off256(slot + 1);
                 s.slot_rows[slot] = s.n_rows;
                 s.slot_elapsed_ns[slot] = s.elapsed_ns;
+                s.slot_rng[slot] = s.rng;
             }
             op.n_rows = s.n_rows;
             op.save_index = pg.n_saves;
@@ -221,6 +268,7 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
             if (!s.ring.get(&slot, &err)) return fail(BGR_ERR_NO_SNAPSHOT, err);
             s.n_rows = s.slot_rows[slot];
             s.elapsed_ns = s.slot_elapsed_ns[slot];
+            s.rng = s.slot_rng[slot];
             op.kind = OP_LOAD;
             op.image_off256 = e->image_off256(slot + 1);
             op.n_rows = s.n_rows;
@@ -245,6 +293,31 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
             s.call_count += n_counter_systems;
             for (uint32_t k = 0; k < 4 && k < rq.n_players; ++k) op.inputs[k] = rq.inputs[k];
             pg.has_advance = true;
+            if (e->spawn_sys >= 0) {  // spawn_particles.run_if(spawn_pressed) (particles.rs:236, 254-256)
+                bool pressed = false;
+                for (uint32_t k = 0; k < rq.n_players; ++k) pressed = pressed || (rq.inputs[k] & BGR_INPUT_SPAWN);
+                if (pressed) {
+                    const SystemReg& sy = e->systems[size_t(e->spawn_sys)];
+                    const uint32_t rate = sy.params[0];
+                    if (uint64_t(s.n_rows) + rate > e->cfg.max_entities)
+                        return fail(BGR_ERR_CAPACITY, "spawn_particles exceeds max_entities");
+                    if (pg.spawn_vals.size() + rate > kMaxSpawnVals)
+                        return fail(BGR_ERR_CAPACITY, "too many particles spawned by one request vector");
+                    op.flags |= OPF_SPAWN;
+                    op.image_off256 = s.n_rows;                      // first spawned row
+                    op.save_index = rate;                            // count
+                    op.call_count = uint32_t(pg.spawn_vals.size());  // offset into spawn_vals
+                    for (uint32_t k = 0; k < rate; ++k) {            // particles.rs:262-268
+                        float2 v;
+                        v.x = s.rng.random_range(-200.0f, 200.0f);
+                        v.y = s.rng.random_range(-200.0f, 200.0f);
+                        pg.spawn_vals.push_back(v);
+                    }
+                    s.n_rows += rate;  // Rollback on_add -> RollbackOrdered.push, applied at the end of the frame
+                    pg.has_spawn = true;
+                    pg.max_rows = std::max(pg.max_rows, s.n_rows);
+                }
+            }
             break;
         }
         default: return fail(BGR_ERR_INVALID_ARGUMENT, "unknown request kind");
@@ -299,7 +372,12 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
     for (uint32_t i = 0; i < pg.n_ops; ++i) n_loads += (pg.ops[i].kind == OP_LOAD);
     const bool simple = n_loads == 0 || (n_loads == 1 && pg.first_is_load);
     if (e->tune_dynamic) pp.flags |= PF_DYNAMIC_TILES;
-    if (simple && e->tune_passive_tma && !e->runs.empty() && 2u * e->passive_bytes <= 96u * 1024u) pp.flags |= PF_PASSIVE_TMA;
+    pp.spawn_vals = e->d_spawn[buf];
+    if (e->spawn_sys >= 0) {
+        const uint64_t ttl = e->systems[size_t(e->spawn_sys)].params[1];
+        pp.spawn_ttl_lo = uint32_t(ttl); pp.spawn_ttl_hi = uint32_t(ttl >> 32);
+    }
+    if (!pg.has_spawn && simple && e->tune_passive_tma && !e->runs.empty() && 2u * e->passive_bytes <= 96u * 1024u) pp.flags |= PF_PASSIVE_TMA;
     const Column& ct = e->cols[e->bt]; const Column& cv = e->cols[e->bv];
     if (ct.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_T; if (ct.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_T; pp.ck_t_slot = uint32_t(ct.ck_slot); }
     if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_V; pp.ck_v_slot = uint32_t(cv.ck_slot); }
@@ -308,7 +386,12 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
     pp.n_runs = uint32_t(e->runs.size()); pp.passive_bytes = e->passive_bytes;
     for (size_t i = 0; i < e->runs.size(); ++i) pp.runs[i] = e->runs[i];
     pp.n_passive = uint32_t(e->passive.size());
-    for (size_t i = 0; i < e->passive.size(); ++i) pp.passive[i] = e->passive[i];
+    for (size_t i = 0; i < e->passive.size(); ++i) {
+        pp.passive[i] = e->passive[i];
+        // Transform::default(): rotation = (0,0,0,1), scale = (1,1,1); every other passive word of a newborn row is 0
+        const uint32_t tw = uint32_t(e->passive[i]) - ct.first_plane;
+        pp.passive_template[i] = (uint32_t(e->passive[i]) >= ct.first_plane && tw >= 6 && tw <= 9) ? 0x3f800000u : 0u;
+    }
     std::memcpy(pp.ops, pg.ops, sizeof(Op) * pg.n_ops);
     const int v = e->tune_vec;
     const bool st = e->bundle_static_ck;
@@ -416,9 +499,9 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
             bool any_despawn = false;
             uint32_t counter = op.call_count;
             uint32_t n = op.n_rows;
-            if (n == 0) break;
-            uint32_t grid = e->grid_for(n, 256);
+            uint32_t grid = e->grid_for(std::max(1u, n), 256);
             for (const SystemReg& sy : e->systems) {
+                if (n == 0) break;
                 switch (sy.id) {
                 case BGR_SYS_PARTICLES_UPDATE:
                     k_sys_particles_update<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane,
@@ -438,6 +521,8 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
                 case BGR_SYS_U32_STORE_CALL_COUNT:
                     k_sys_u32_store<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, counter++);
                     break;
+                case BGR_SYS_PARTICLES_SPAWN:
+                    continue;  // Commands: applied after the schedule (below)
                 default: return fail(BGR_ERR_UNSUPPORTED, "system has no GPU implementation yet");
                 }
                 e->launches += 1;
@@ -449,6 +534,15 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
             break;
         }
         default: break;
+        }
+        if (op.kind == OP_ADVANCE && (op.flags & OPF_SPAWN)) {
+            const SystemReg& sy = e->systems[size_t(e->spawn_sys)];
+            const uint64_t ttl = sy.params[1];
+            k_sys_particles_spawn<<<e->grid_for(op.save_index, 256), 256, 0, e->stream>>>(
+                live, e->words, e->cols[sy.cols[0]].first_plane, e->cols[sy.cols[1]].first_plane, e->cols[sy.cols[2]].first_plane,
+                op.image_off256, op.save_index, e->d_spawn[buf] + op.call_count, uint32_t(ttl), uint32_t(ttl >> 32));
+            e->launches += 1;
+            live_rows = std::max(live_rows, op.image_off256 + op.save_index);
         }
     }
     k_publish<<<1, 128, 0, e->stream>>>(e->d_accum, e->d_out[buf], std::max(1u, pg.n_saves) * kAccStride, e->seq);
@@ -467,6 +561,7 @@ int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs,
     int rc = compile_requests(e, s, sess, reqs, n, pg);
     if (rc != BGR_OK) return rc;  // nothing executed, nothing committed
     uint32_t buf = e->next_buf;
+    if (!pg.spawn_vals.empty()) std::memcpy(e->h_spawn[buf], pg.spawn_vals.data(), pg.spawn_vals.size() * sizeof(float2));
     e->seq += 1;
     bool fused = e->bundle_particles && !(e->cfg.flags & BGR_CFG_FORCE_STEPWISE);
     rc = fused ? run_fused(e, pg, buf) : run_stepwise(e, pg, buf);
@@ -607,14 +702,16 @@ int read_alive_image(bgr_engine* e, uint32_t image_idx, uint32_t first, uint32_t
 void detect_bundles(bgr_engine* e) {
     e->bundle_particles = false;
     e->passive.clear();
-    if (e->systems.size() != 2) return;
-    const SystemReg* up = nullptr; const SystemReg* de = nullptr;
+    const SystemReg* up = nullptr; const SystemReg* de = nullptr; const SystemReg* sp = nullptr;
     for (auto& s : e->systems) {
-        if (s.id == BGR_SYS_PARTICLES_UPDATE) up = &s;
-        if (s.id == BGR_SYS_PARTICLES_DESPAWN) de = &s;
+        if (s.id == BGR_SYS_PARTICLES_UPDATE && !up) up = &s;
+        else if (s.id == BGR_SYS_PARTICLES_DESPAWN && !de) de = &s;
+        else if (s.id == BGR_SYS_PARTICLES_SPAWN && !sp) sp = &s;
+        else return;  // any other system: generic path
     }
     if (!up || !de) return;
     uint32_t t = up->cols[0], v = up->cols[1], l = de->cols[0];
+    if (sp && (sp->cols[0] != t || sp->cols[1] != v || sp->cols[2] != l)) return;
     if (t == v || t == l || v == l) return;
     auto ck_ok = [&](const Column& c) {
         return c.hash_kind == BGR_HASH_NONE || (c.hash_kind == BGR_HASH_BYTES && c.hash_off == 0 && c.hash_len == 12);
@@ -700,6 +797,7 @@ BGR_API void bgr_engine_destroy(bgr_engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (int i = 0; i < bgr_engine::kBufs; ++i) {
         if (e->h_out[i]) cudaFreeHost(e->h_out[i]);
+        if (e->h_spawn[i]) cudaFreeHost(e->h_spawn[i]);
         if (e->ev[i]) cudaEventDestroy(e->ev[i]);
     }
     if (e->arena) cudaFree(e->arena);
@@ -772,6 +870,14 @@ BGR_API int bgr_add_system(bgr_engine* e, uint32_t system, const uint32_t* colum
         if (!need(1, 1) || (s.params[0] & 3u) || s.params[0] + 4 > eb(0))
             return fail(BGR_ERR_INVALID_ARGUMENT, "store_call_count binds {C} with params {aligned byte_offset}");
         break;
+    case BGR_SYS_PARTICLES_SPAWN:
+        if (!need(3, 4) || eb(0) != 40 || eb(1) != 12 || eb(2) != 8)
+            return fail(BGR_ERR_INVALID_ARGUMENT, "spawn_particles binds {Transform(40B), Velocity(12B), Ttl(8B)} with params {rate, ttl, seed_lo, seed_hi}");
+        if (e->spawn_sys >= 0) return fail(BGR_ERR_INVALID_ARGUMENT, "spawn_particles registered twice");
+        if (s.params[0] == 0 || s.params[0] > 4096) return fail(BGR_ERR_INVALID_ARGUMENT, "spawn rate must be in 1..4096");
+        e->spawn_sys = int(e->systems.size());
+        e->st.rng.seed_from_u64(uint64_t(s.params[2]) | (uint64_t(s.params[3]) << 32));  // insert_resource(ParticleRng(seed_from_u64(seed)))
+        break;
     case BGR_SYS_BOX_MOVE:
         return fail(BGR_ERR_UNSUPPORTED, "move_cube_system (box_game) runs on the CPU plumbing config only; no GPU system yet");
     default: return fail(BGR_ERR_INVALID_ARGUMENT, "unknown system id");
@@ -819,6 +925,12 @@ BGR_API int bgr_build(bgr_engine* e) {
     e->st.ring.reset(e->cfg.max_depth);
     e->st.slot_rows.assign(e->cfg.max_depth, 0);
     e->st.slot_elapsed_ns.assign(e->cfg.max_depth, 0);
+    e->st.slot_rng.assign(e->cfg.max_depth, ParticleRng());
+    if (e->spawn_sys >= 0)
+        for (int i = 0; i < bgr_engine::kBufs; ++i) {
+            CUDA_TRY(cudaHostAlloc(&e->h_spawn[i], sizeof(float2) * kMaxSpawnVals, cudaHostAllocMapped));
+            CUDA_TRY(cudaHostGetDevicePointer(&e->d_spawn[i], e->h_spawn[i], 0));
+        }
     detect_bundles(e);
     {   // TMA stage: kTmaStages x (stage_tiles tiles) must fit ~200 KB of shared memory, ~64 KB per stage
         size_t per_stage = (200u * 1024u) / size_t(kTmaStages);
@@ -831,6 +943,30 @@ BGR_API int bgr_build(bgr_engine* e) {
     }
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->built = true;
+    return BGR_OK;
+}
+
+BGR_API int bgr_run_startup_system(bgr_engine* e, uint32_t system) {
+    if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
+    if (system != BGR_SYS_PARTICLES_SPAWN || e->spawn_sys < 0)
+        return fail(BGR_ERR_INVALID_ARGUMENT, "only a registered spawn_particles system can run at Startup");
+    int rc = drain(e);
+    if (rc != BGR_OK) return rc;
+    const SystemReg& sy = e->systems[size_t(e->spawn_sys)];
+    const uint32_t rate = sy.params[0];
+    if (uint64_t(e->st.n_rows) + rate > e->cfg.max_entities) return fail(BGR_ERR_CAPACITY, "spawn_particles exceeds max_entities");
+    for (uint32_t k = 0; k < rate; ++k) {
+        e->h_spawn[0][k].x = e->st.rng.random_range(-200.0f, 200.0f);
+        e->h_spawn[0][k].y = e->st.rng.random_range(-200.0f, 200.0f);
+    }
+    const uint64_t ttl = sy.params[1];
+    k_sys_particles_spawn<<<e->grid_for(rate, 256), 256, 0, e->stream>>>(
+        e->image(0), e->words, e->cols[sy.cols[0]].first_plane, e->cols[sy.cols[1]].first_plane, e->cols[sy.cols[2]].first_plane,
+        e->st.n_rows, rate, e->d_spawn[0], uint32_t(ttl), uint32_t(ttl >> 32));
+    e->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->st.n_rows += rate;
     return BGR_OK;
 }
 

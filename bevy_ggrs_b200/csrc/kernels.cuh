@@ -51,16 +51,19 @@ __host__ __device__ inline size_t alive_offset(uint32_t words, uint32_t row) {
 }
 
 enum OpKind : uint32_t { OP_SAVE = 0, OP_LOAD = 1, OP_ADVANCE = 2 };
-enum OpFlags : uint32_t { OPF_NO_STORE = 1u };  // ring depth 0: checksum only
+enum OpFlags : uint32_t {
+    OPF_NO_STORE = 1u,  // SAVE with ring depth 0: checksum only
+    OPF_SPAWN = 2u,     // ADVANCE: spawn_particles fired; rows [spawn_first, spawn_first+spawn_count) are born at the end of the frame
+};
 
 struct Op {
     uint32_t kind;
-    uint32_t image_off256;  // byte offset of the image the op reads (LOAD) / writes (SAVE), in 256-byte units
+    uint32_t image_off256;  // LOAD/SAVE: byte offset of the image read / written, in 256-byte units.  ADVANCE+SPAWN: first spawned row
     uint32_t dt_bits;       // ADVANCE: Time<GgrsTime>::delta_secs as f32 bits (time.rs:63-76)
     uint32_t n_rows;        // rows that exist while this op runs (RollbackOrdered::len())
-    uint32_t save_index;    // SAVE: which accumulator row
+    uint32_t save_index;    // SAVE: which accumulator row.  ADVANCE+SPAWN: number of spawned rows
     uint32_t flags;
-    uint32_t call_count;    // ADVANCE: value of the un-rolled-back host counter (test system only)
+    uint32_t call_count;    // ADVANCE: value of the un-rolled-back host counter (test system).  ADVANCE+SPAWN: offset into spawn_vals
     uint8_t inputs[4];      // ADVANCE: first 4 player inputs (u8)
 };
 static_assert(sizeof(Op) == 32, "Op must stay 32 bytes");
@@ -82,6 +85,7 @@ struct ProgramParams {
     unsigned long long* accum;  // device [kMaxSaves][kAccStride]
     unsigned long long* out;    // host-mapped [kMaxSaves][kAccStride]
     unsigned int* ticket;       // [0] block-completion ticket, [1] dynamic tile counter
+    const float2* spawn_vals;   // (vx, vy) of every particle spawned by this program (host-mapped), particles.rs:265
     unsigned long long seq;     // written to out[kSeqIndex] after the results (completion flag the host polls)
     uint32_t words, tile_bytes, n_tiles, n_ops, n_saves;
     uint32_t live_rows, flags;
@@ -89,8 +93,10 @@ struct ProgramParams {
     uint32_t ck_t_slot, ck_v_slot;            // accumulator column of each checksummed type
     uint32_t n_runs, passive_bytes;           // TMA path
     uint32_t n_passive;                       // per-thread fallback path
+    uint32_t spawn_ttl_lo, spawn_ttl_hi;      // Ttl of a spawned particle (fps * 5, particles.rs:260)
     PassiveRun runs[kMaxRuns];
     uint16_t passive[kMaxPassive];
+    uint32_t passive_template[kMaxPassive];   // value of each passive word in a freshly spawned row (Transform::default())
     Op ops[kMaxOps];
 };
 static_assert(sizeof(ProgramParams) <= 4000, "kernel parameter block must fit 4 KB");
@@ -313,6 +319,22 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                     tl[0][j] = lo; tl[1][j] = hi;
                     alive &= ((lo | hi) == 0u) ? ~(0xFFu << (8 * j)) : 0xFFFFFFFFu;
                 }
+                if (p.ops[i].flags & OPF_SPAWN) {
+                    // spawn_particles (particles.rs:258-270): Commands are applied after the schedule, so the
+                    // newborn rows appear now, un-updated: Transform::default(), Velocity(vx, vy, 0), Ttl(ttl)
+                    const uint32_t first = p.ops[i].image_off256, count = p.ops[i].save_index, off = p.ops[i].call_count;
+#pragma unroll
+                    for (int j = 0; j < VEC; ++j) {
+                        const uint32_t k = row0 + j - first;
+                        if (k < count) {
+                            const float2 v = p.spawn_vals[off + k];
+                            tr[0][j] = 0u; tr[1][j] = 0u; tr[2][j] = 0u;
+                            vl[0][j] = __float_as_uint(v.x); vl[1][j] = __float_as_uint(v.y); vl[2][j] = 0u;
+                            tl[0][j] = p.spawn_ttl_lo; tl[1][j] = p.spawn_ttl_hi;
+                            alive |= 1u << (8 * j);
+                        }
+                    }
+                }
             } else if (kind == OP_SAVE) {
                 uint8_t* img = p.arena + (size_t(p.ops[i].image_off256) << 8);
                 if (!(p.ops[i].flags & OPF_NO_STORE)) store_active(img);
@@ -391,6 +413,15 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             if (k < nk) vec_store<VEC>(img + size_t(p.passive[pp + k]) * kPlaneBytes + woff, v[k]);
+                    } else if (kind == OP_ADVANCE && (p.ops[i].flags & OPF_SPAWN)) {
+                        const uint32_t first = p.ops[i].image_off256, count = p.ops[i].save_index;
+#pragma unroll
+                        for (int j = 0; j < VEC; ++j)
+                            if (row0 + j - first < count) {
+#pragma unroll
+                                for (int k = 0; k < 4; ++k)
+                                    if (k < nk) v[k][j] = p.passive_template[pp + k];
+                            }
                     }
                 }
                 if (p.flags & PF_WRITE_LIVE_PASSIVE) {
@@ -606,6 +637,26 @@ __global__ void __launch_bounds__(256) k_sys_u32_satsub_despawn(uint8_t* img, ui
 __global__ void __launch_bounds__(256) k_sys_u32_store(uint8_t* img, uint32_t words, uint32_t plane, uint32_t n_rows, uint32_t value) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
         if (img[alive_offset(words, r)]) *reinterpret_cast<uint32_t*>(img + word_offset(words, r, plane)) = value;
+}
+
+// spawn_particles (particles.rs:258-270) on the live image: rows [first, first+count) become
+// Transform::default(), Velocity(vx, vy, 0), Ttl(ttl), alive; every other registered word is zero.
+__global__ void __launch_bounds__(256) k_sys_particles_spawn(uint8_t* img, uint32_t words, uint32_t t_plane, uint32_t v_plane,
+                                                             uint32_t l_plane, uint32_t first, uint32_t count,
+                                                             const float2* __restrict__ vals, uint32_t ttl_lo, uint32_t ttl_hi) {
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const uint32_t r = first + k;
+        for (uint32_t w = 0; w < words; ++w) *reinterpret_cast<uint32_t*>(img + word_offset(words, r, w)) = 0u;
+        uint32_t* t = reinterpret_cast<uint32_t*>(img + word_offset(words, r, t_plane));
+        t[6 * kTileRows] = 0x3f800000u;                                                          // rotation.w = 1
+        t[7 * kTileRows] = 0x3f800000u; t[8 * kTileRows] = 0x3f800000u; t[9 * kTileRows] = 0x3f800000u;  // scale = 1
+        uint32_t* v = reinterpret_cast<uint32_t*>(img + word_offset(words, r, v_plane));
+        const float2 xy = vals[k];
+        v[0] = __float_as_uint(xy.x); v[kTileRows] = __float_as_uint(xy.y);
+        uint32_t* l = reinterpret_cast<uint32_t*>(img + word_offset(words, r, l_plane));
+        l[0] = ttl_lo; l[kTileRows] = ttl_hi;
+        img[alive_offset(words, r)] = 1;
+    }
 }
 
 // apply deferred despawn commands: alive &= !kill ; kill = 0

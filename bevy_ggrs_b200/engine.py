@@ -61,6 +61,9 @@ class Engine:
     def build(self) -> None:
         self._check(self._lib.bgr_build(self._h))
 
+    def run_startup_system(self, system: int) -> None:
+        self._check(self._lib.bgr_run_startup_system(self._h, system))
+
     # ---- entities ----
     def spawn(self, count: int) -> int:
         first = C.c_uint32()

@@ -87,8 +87,16 @@ typedef enum bgr_system {
     /* writes a host-side call counter that is NOT rolled back into a u32 field — the
      * deliberately non-deterministic system of tests/synctest.rs:83-125.
      * cols = {C}; params = {byte_offset} */
-    BGR_SYS_U32_STORE_CALL_COUNT = 6
+    BGR_SYS_U32_STORE_CALL_COUNT = 6,
+    /* spawn_particles.run_if(spawn_pressed), particles.rs:243-270: when any player's input has INPUT_SPAWN
+     * (1 << 4) set, appends `rate` rows: Transform::default(), Velocity(random_range(-200..200) x2, 0), Ttl(ttl),
+     * Rollback.  Draws from the ParticleRng resource (Xoshiro256PlusPlus::seed_from_u64(seed)), which the engine
+     * keeps host-side and rolls back with every snapshot (rollback_resource_with_clone::<ParticleRng>, :200).
+     * Commands are deferred: the new rows exist from the end of the frame on and are not updated in it.
+     * cols = {Transform(40B), Velocity(12B), Ttl(8B)}; params = {rate, ttl, seed_lo, seed_hi} */
+    BGR_SYS_PARTICLES_SPAWN = 7
 } bgr_system;
+#define BGR_INPUT_SPAWN 0x10u /* INPUT_SPAWN, particles.rs:75 */
 
 /* GgrsRequest<T> (ggrs; consumed at schedule_systems.rs:222-269). Input type is u8
  * (particles.rs:73 `GgrsConfig<u8>`, box_game.rs:27-29 `BoxInput(u8)`). */
@@ -167,6 +175,9 @@ BGR_API int bgr_add_system(bgr_engine* e, uint32_t system, const uint32_t* colum
                            const uint32_t* params, uint32_t n_params);
 /* end of App::build: allocates live columns + max_depth frame slots in HBM */
 BGR_API int bgr_build(bgr_engine* e);
+/* add_systems(Startup, system): run a registered GgrsSchedule system once, outside the rollback loop
+ * (particles.rs:232 `add_systems(Startup, spawn_particles)` — the initial burst).  Only BGR_SYS_PARTICLES_SPAWN. */
+BGR_API int bgr_run_startup_system(bgr_engine* e, uint32_t system);
 
 /* ---- entity population (Rollback marker, src/snapshot/rollback.rs:23-94) ---------------- */
 /* `commands.spawn((..., Rollback))` x count: appends rows, RollbackOrdered index = order_base + row */

@@ -94,8 +94,26 @@ ORC_API int orc_rollback_resource(World* w, const char* name, const void* init, 
 ORC_API int orc_add_system(World* w, uint32_t sys, const uint32_t* cols, uint32_t n_cols, const uint32_t* params, uint32_t n_params) {
     return guarded([&] {
         SystemDesc s; s.id = sys; s.cols.assign(cols, cols + n_cols); s.params.assign(params, params + n_params);
+        if (sys == BGR_SYS_PARTICLES_SPAWN) {  // insert_resource(ParticleRng(GameRng::seed_from_u64(seed)))
+            w->particle_rng.seed_from_u64(uint64_t(params[2]) | (uint64_t(params[3]) << 32));
+            w->has_particle_rng = true;
+        }
         w->systems.push_back(std::move(s));
     });
+}
+// add_systems(Startup, spawn_particles): the initial burst, outside the rollback loop
+ORC_API int orc_run_startup_system(World* w, uint32_t sys) {
+    return guarded([&] {
+        for (const SystemDesc& s : w->systems)
+            if (s.id == sys && sys == BGR_SYS_PARTICLES_SPAWN) { w->pending_spawns.clear(); w->spawn_particles(s); w->apply_spawns(); return; }
+        throw std::runtime_error("startup system not registered");
+    });
+}
+// raw RNG stream for the golden-vector test
+ORC_API void orc_xoshiro_stream(uint64_t seed, uint32_t n, uint64_t* u64_out, float* f32_out, float low, float high) {
+    Xoshiro256pp a, b;
+    a.seed_from_u64(seed); b.seed_from_u64(seed);
+    for (uint32_t i = 0; i < n; ++i) { u64_out[i] = a.next_u64(); f32_out[i] = b.random_range_f32(low, high); }
 }
 ORC_API int orc_spawn(World* w, uint32_t count, uint32_t* first_out) { return guarded([&] { *first_out = w->spawn(count); }); }
 ORC_API uint32_t orc_row_count(World* w) { return uint32_t(w->rollback_ordered.len()); }

@@ -160,6 +160,47 @@ inline float duration_as_secs_f32(uint64_t ns) {
 
 struct NonFinitePanic : std::runtime_error { using std::runtime_error::runtime_error; };
 
+// ParticleRng(rand_xoshiro::Xoshiro256PlusPlus) (particles.rs:125-128) — third-party arithmetic, not under
+// /root/reference; restated from the published algorithms, PARITY UNPINNED (no golden upstream, no cargo here):
+//   rand_xoshiro 0.7  Xoshiro256PlusPlus::seed_from_u64(s): state = 4 outputs of SplitMix64(s)
+//                     next_u64: rotl(s0 + s3, 23) + s0, then the xoshiro256 state update
+//                     next_u32: upper 32 bits of next_u64
+//   rand 0.9          random_range(low..high) for f32: v = f32::from_bits((next_u32 >> 9) | 0x3f800000) - 1.0;
+//                     res = v * (high - low) + low   (mul then add, separately rounded); retried only if res >= high
+struct Xoshiro256pp {
+    uint64_t s[4] = {0, 0, 0, 0};
+    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    void seed_from_u64(uint64_t seed) {
+        uint64_t x = seed;
+        for (int i = 0; i < 4; ++i) {
+            x += 0x9E3779B97F4A7C15ULL;
+            uint64_t z = x;
+            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+            z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+            s[i] = z ^ (z >> 31);
+        }
+    }
+    uint64_t next_u64() {
+        uint64_t result = rotl(s[0] + s[3], 23) + s[0];
+        uint64_t t = s[1] << 17;
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
+        s[2] ^= t;
+        s[3] = rotl(s[3], 45);
+        return result;
+    }
+    uint32_t next_u32() { return uint32_t(next_u64() >> 32); }
+    float random_range_f32(float low, float high) {
+        const float scale = high - low;
+        for (;;) {
+            uint32_t bits = (next_u32() >> 9) | 0x3f800000u;
+            float value1_2; std::memcpy(&value1_2, &bits, 4);
+            float value0_1 = value1_2 - 1.0f;
+            float res = value0_1 * scale + low;
+            if (res < high) return res;
+        }
+    }
+};
+
 struct World {
     // ---- registration ----
     std::vector<ColumnDesc> columns;
@@ -185,6 +226,9 @@ struct World {
     int32_t confirmed_frame_count = 0;  // mod.rs:76-77 (init_resource -> Default 0)
     std::optional<uint32_t> max_prediction;  // MaxPredictionWindow, lib.rs:116-117
     GgrsTimeState ggrs_time;
+    Xoshiro256pp particle_rng;          // ParticleRng resource (particles.rs:128), rolled back with clone (:200)
+    bool has_particle_rng = false;
+    GgrsSnapshots<std::optional<Xoshiro256pp>> rng_snaps;
     uint8_t player_inputs[BGR_MAX_PLAYERS] = {0};
     uint32_t n_players = 0;
 
@@ -340,6 +384,12 @@ struct World {
             time_snaps.confirm(confirmed_frame_count);
             time_snaps.push(rollback_frame_count, std::optional<GgrsTimeState>(ggrs_time));
         });
+        if (has_particle_rng)
+            tasks.push_back([this] {  // rollback_resource_with_clone::<ParticleRng>() (particles.rs:200)
+                if (max_prediction) rng_snaps.set_depth(*max_prediction);
+                rng_snaps.confirm(confirmed_frame_count);
+                rng_snaps.push(rollback_frame_count, std::optional<Xoshiro256pp>(particle_rng));
+            });
         for (size_t i = 0; i < resources.size(); ++i)
             tasks.push_back([this, i] {  // resource_snapshot.rs:65-73
                 if (max_prediction) res_snaps[i].set_depth(*max_prediction);
@@ -433,6 +483,10 @@ struct World {
             auto& s = time_snaps.rollback(frame).get();
             if (s) ggrs_time = *s;
         }
+        if (has_particle_rng) {
+            auto& s = rng_snaps.rollback(frame).get();
+            if (s) particle_rng = *s;
+        }
         for (size_t i = 0; i < resources.size(); ++i) {
             auto& s = res_snaps[i].rollback(frame).get();
             if (s) { res_data[i] = *s; res_present[i] = 1; } else { res_present[i] = 0; }
@@ -460,13 +514,46 @@ struct World {
         ggrs_time.delta_secs = duration_as_secs_f32(ggrs_time.delta_ns);
         // Main: world.run_schedule(GgrsSchedule); commands apply at the end
         std::vector<size_t> despawn;
+        pending_spawns.clear();
         for (const SystemDesc& s : systems) run_system(s, despawn);
         apply_despawns(despawn);
+        apply_spawns();
+    }
+
+    // commands.spawn((Sprite, Velocity, Ttl, Rollback)) queued by spawn_particles; applied at the flush
+    struct PendingSpawn { uint32_t tc, vc, lc; float vx, vy; uint64_t ttl; };
+    std::vector<PendingSpawn> pending_spawns;
+    void apply_spawns() {
+        for (const PendingSpawn& ps : pending_spawns) {
+            uint32_t r = spawn(1);  // Rollback on_add hook: RollbackId + RollbackOrdered.push
+            size_t row = rows() - 1; (void)r;
+            float tf[10] = {0, 0, 0, 0, 0, 0, 1.0f, 1.0f, 1.0f, 1.0f};  // Transform::default() (Sprite requires Transform)
+            std::memcpy(&data[ps.tc][row * 40], tf, 40);
+            float v[3] = {ps.vx, ps.vy, 0.0f};
+            std::memcpy(&data[ps.vc][row * 12], v, 12);
+            std::memcpy(&data[ps.lc][row * 8], &ps.ttl, 8);
+        }
+        pending_spawns.clear();
+    }
+    void spawn_particles(const SystemDesc& s) {  // particles.rs:258-270
+        const float sp = 200.0f;
+        for (uint32_t k = 0; k < s.params[0]; ++k) {
+            PendingSpawn ps{s.cols[0], s.cols[1], s.cols[2], 0, 0, uint64_t(s.params[1])};
+            ps.vx = particle_rng.random_range_f32(-sp, sp);
+            ps.vy = particle_rng.random_range_f32(-sp, sp);
+            pending_spawns.push_back(ps);
+        }
     }
 
     void run_system(const SystemDesc& s, std::vector<size_t>& despawn) {
         const float dt = ggrs_time.delta_secs;
         switch (s.id) {
+        case BGR_SYS_PARTICLES_SPAWN: {  // .run_if(spawn_pressed), particles.rs:254-256
+            bool pressed = false;
+            for (uint32_t i = 0; i < n_players; ++i) pressed = pressed || (player_inputs[i] & BGR_INPUT_SPAWN);
+            if (pressed) spawn_particles(s);
+            break;
+        }
         case BGR_SYS_PARTICLES_UPDATE: {  // particles.rs:272-280
             uint32_t tc = s.cols[0], vc = s.cols[1];
             const float gx = 0.0f * 200.0f, gy = -1.0f * 200.0f, gz = 0.0f * 200.0f;  // Vec3::NEG_Y * 200.0

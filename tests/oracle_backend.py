@@ -66,6 +66,8 @@ def load_oracle() -> C.CDLL:
         "orc_rollback_resource": (C.c_int, [vp, C.c_char_p, vp, u32, C.c_int, u32p]),
         "orc_add_system": (C.c_int, [vp, u32, u32p, u32, u32p, u32]),
         "orc_spawn": (C.c_int, [vp, u32, u32p]),
+        "orc_run_startup_system": (C.c_int, [vp, u32]),
+        "orc_xoshiro_stream": (None, [u64, u32, u64p, C.POINTER(C.c_float), C.c_float, C.c_float]),
         "orc_row_count": (u32, [vp]),
         "orc_active_count": (u64, [vp]),
         "orc_write_component": (C.c_int, [vp, u32, u32, u32, vp, u32]),
@@ -150,6 +152,9 @@ class OracleWorld:
 
     def build(self):
         pass
+
+    def run_startup_system(self, system):
+        self._check(self._lib.orc_run_startup_system(self._h, system))
 
     def spawn(self, count):
         first = C.c_uint32()

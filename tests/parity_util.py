@@ -18,11 +18,19 @@ def input_system(app):
     app.insert_resource(LocalInputs({h: 0 for h in app.local_players.handles}))
 
 
-def make_particles_app(backend, n_entities, seed, session, ttl_lo, ttl_hi, noop_inputs=False):
+def make_particles_app(backend, n_entities, seed, session, ttl_lo, ttl_hi, noop_inputs=False, spawn_rate=0,
+                       spawn_ttl=300, startup_burst=False):
     app = App(backend)
     app.add_plugins(GgrsPlugin())
     app.insert_resource(RollbackFrameRate(60))
-    if noop_inputs:
+    if spawn_rate:
+        # INPUT_SPAWN = 1 << 4 held by player 0 on two frames out of five, INPUT_NOOP noise on player 1
+        def read(app_):
+            app_.insert_resource(LocalInputs({h: ((1 << 4) if (h == 0 and app_.ticks % 5 in (1, 2)) else 0) |
+                                              ((1 << 5) if (app_.ticks + h) % 3 == 0 else 0)
+                                              for h in app_.local_players.handles}))
+        app.add_systems(ReadInputs, read)
+    elif noop_inputs:
         # INPUT_NOOP = 1 << 5 on a seeded schedule (particles.rs:75-76): inputs never change the simulation
         def read(app_):
             app_.insert_resource(LocalInputs({h: (1 << 5) if (app_.ticks + h) % 3 == 0 else 0
@@ -30,13 +38,15 @@ def make_particles_app(backend, n_entities, seed, session, ttl_lo, ttl_hi, noop_
         app.add_systems(ReadInputs, read)
     else:
         app.add_systems(ReadInputs, input_system)
-    cols = register_particles(backend)
+    cols = register_particles(backend, spawn_rate=spawn_rate, spawn_ttl=spawn_ttl)
     app.insert_resource(session)
     mism = []
     app.add_observer(SyncTestMismatch, lambda ev: mism.append(ev))
     app._finish()
     tf, vel, ttl = synth_particles(n_entities, seed, ttl_lo, ttl_hi)
     populate(backend, cols, tf, vel, ttl)
+    if startup_burst:
+        backend.run_startup_system(capi.BGR_SYS_PARTICLES_SPAWN)  # add_systems(Startup, spawn_particles), particles.rs:232
     return app, cols, mism
 
 
@@ -55,17 +65,20 @@ def compare_state(eng, orc, cols, n):
 
 
 def run_particles_synctest_pair(n_entities, check_distance, ticks, seed, max_prediction=None, ttl_lo=None,
-                                ttl_hi=None, flags=0, tune=None):
+                                ttl_hi=None, flags=0, tune=None, spawn_rate=0, spawn_ttl=300, startup_burst=False):
     """SyncTest on the GPU engine and on the oracle with identical inputs; returns comparison facts."""
     maxp = max_prediction or max(8, check_distance + 1)
     ttl_lo = ttl_lo if ttl_lo is not None else 300 + check_distance
     ttl_hi = ttl_hi if ttl_hi is not None else ttl_lo
-    eng = Engine(max_entities=n_entities, max_depth=maxp, fps=60, flags=flags)
+    cap = n_entities + spawn_rate * (ticks + 2)
+    eng = Engine(max_entities=cap, max_depth=maxp, fps=60, flags=flags)
     orc = OracleWorld(fps=60)
     app_e, cols_e, mism_e = make_particles_app(eng, n_entities, seed, Session.SyncTest(
-        SyncTestSession(2, check_distance, maxp, input_delay=2)), ttl_lo, ttl_hi, noop_inputs=True)
+        SyncTestSession(2, check_distance, maxp, input_delay=2)), ttl_lo, ttl_hi, noop_inputs=True,
+        spawn_rate=spawn_rate, spawn_ttl=spawn_ttl, startup_burst=startup_burst)
     app_o, cols_o, mism_o = make_particles_app(orc, n_entities, seed, Session.SyncTest(
-        SyncTestSession(2, check_distance, maxp, input_delay=2)), ttl_lo, ttl_hi, noop_inputs=True)
+        SyncTestSession(2, check_distance, maxp, input_delay=2)), ttl_lo, ttl_hi, noop_inputs=True,
+        spawn_rate=spawn_rate, spawn_ttl=spawn_ttl, startup_burst=startup_burst)
     all_e, all_o = [], []
     launches0 = eng.launch_count()
     for _ in range(ticks):
@@ -78,7 +91,8 @@ def run_particles_synctest_pair(n_entities, check_distance, ticks, seed, max_pre
     res = {
         "checksums_equal": all_e == all_o and len(all_e) > 0,
         "n_checksums": len(all_e),
-        "state_equal": compare_state(eng, orc, cols_e, n_entities),
+        "state_equal": eng.row_count() == orc.row_count() and compare_state(eng, orc, cols_e, eng.row_count()),
+        "rows": (eng.row_count(), orc.row_count()),
         "mismatch_events": (len(mism_e), len(mism_o)),
         "fused": fused,
         "launches": tick_launches,

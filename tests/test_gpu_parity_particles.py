@@ -48,3 +48,18 @@ def test_fused_and_stepwise_agree_checksum_for_checksum():
     # one launch per tick on the fused path (+0 for setup): stepwise needs dozens
     assert a["launches"] == 12
     assert b["launches"] > 10 * a["launches"]
+
+
+@pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])
+def test_spawn_particles_inside_the_rollback_window(flags):
+    """spawn_particles.run_if(spawn_pressed) with the rolled-back ParticleRng — rows are born
+    (and, with ttl 9, die) inside the rollback window; Load shrinks RollbackOrdered and the resimulation must
+    re-spawn the same particles.  Row count, alive mask, columns and every checksum track the oracle."""
+    r = run_particles_synctest_pair(300, 6, 36, seed=11, ttl_lo=3, ttl_hi=40, flags=flags, spawn_rate=40,
+                                    spawn_ttl=9, startup_burst=True)
+    assert r["fused"] == (flags == 0)
+    assert r["rows"][0] == r["rows"][1] > 300 + 40 * 10
+    assert r["checksums_equal"] and r["state_equal"]
+    assert r["active"][0] == r["active"][1]
+    assert r["mismatch_events"] == (0, 0)
+    assert r["ring"][0] == r["ring"][1]
