@@ -110,6 +110,7 @@ PROTOTYPES = {
     "bgr_fold_partials": (C.c_int, [C.POINTER(bgr_partial), C.POINTER(bgr_checksum)]),
     "bgr_collect_partials": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, u32p]),
     "bgr_fold_partials_n": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
+    "bgr_seahash": (C.c_uint64, [C.c_void_p, C.c_uint64]),
     "bgr_ggrs_time_delta_bits": (C.c_uint32, [C.c_uint32, C.c_int32]),
     "bgr_launch_count": (C.c_int, [C.c_void_p, u64p]),
     "bgr_slot_bytes": (C.c_int, [C.c_void_p, u64p]),

@@ -292,6 +292,7 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
             op.call_count = s.call_count;
             s.call_count += n_counter_systems;
             for (uint32_t k = 0; k < 4 && k < rq.n_players; ++k) op.inputs[k] = rq.inputs[k];
+            op.flags |= (rq.n_players & 0xFu) << 8;  // PlayerInputs<T>.len() for systems that index it (box_game.rs:171)
             pg.has_advance = true;
             if (e->spawn_sys >= 0) {  // spawn_particles.run_if(spawn_pressed) (particles.rs:236, 254-256)
                 bool pressed = false;
@@ -523,6 +524,12 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
                     break;
                 case BGR_SYS_PARTICLES_SPAWN:
                     continue;  // Commands: applied after the schedule (below)
+                case BGR_SYS_BOX_MOVE: {
+                    uint32_t packed = uint32_t(op.inputs[0]) | (uint32_t(op.inputs[1]) << 8) | (uint32_t(op.inputs[2]) << 16) | (uint32_t(op.inputs[3]) << 24);
+                    k_sys_box_move<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane, e->cols[sy.cols[1]].first_plane,
+                                                                 n, op.dt_bits, packed, (op.flags >> 8) & 0xFu, e->cfg.order_base);
+                    break;
+                }
                 default: return fail(BGR_ERR_UNSUPPORTED, "system has no GPU implementation yet");
                 }
                 e->launches += 1;
@@ -879,7 +886,9 @@ BGR_API int bgr_add_system(bgr_engine* e, uint32_t system, const uint32_t* colum
         e->st.rng.seed_from_u64(uint64_t(s.params[2]) | (uint64_t(s.params[3]) << 32));  // insert_resource(ParticleRng(seed_from_u64(seed)))
         break;
     case BGR_SYS_BOX_MOVE:
-        return fail(BGR_ERR_UNSUPPORTED, "move_cube_system (box_game) runs on the CPU plumbing config only; no GPU system yet");
+        if (!need(2, 0) || eb(0) != 40 || eb(1) != 12)
+            return fail(BGR_ERR_INVALID_ARGUMENT, "move_cube_system binds {Transform(40B), Velocity(12B)}");
+        break;
     default: return fail(BGR_ERR_INVALID_ARGUMENT, "unknown system id");
     }
     e->systems.push_back(std::move(s));
@@ -1158,6 +1167,24 @@ BGR_API int bgr_fold_partials_n(const bgr_partial* combined, uint32_t n, bgr_che
     if ((!combined || !out) && n) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
     for (uint32_t i = 0; i < n; ++i) fold(combined[i], &out[i]);
     return BGR_OK;
+}
+
+BGR_API uint64_t bgr_seahash(const void* bytes, uint64_t len) {
+    const uint8_t* p = static_cast<const uint8_t*>(bytes);
+    uint64_t a = kSeaA, b = kSeaB, c = kSeaC, d = kSeaD;
+    uint64_t i = 0;
+    for (; i + 8 <= len; i += 8) {
+        uint64_t w;
+        std::memcpy(&w, p + i, 8);  // little-endian host
+        uint64_t t = sea_diffuse(a ^ w);
+        a = b; b = c; c = d; d = t;
+    }
+    if (i < len) {
+        uint64_t w = 0;
+        std::memcpy(&w, p + i, size_t(len - i));
+        a = sea_diffuse(a ^ w);
+    }
+    return sea_diffuse(a ^ b ^ c ^ d ^ len);
 }
 
 BGR_API uint32_t bgr_ggrs_time_delta_bits(uint32_t fps, int32_t frame) {

@@ -54,6 +54,7 @@ enum OpKind : uint32_t { OP_SAVE = 0, OP_LOAD = 1, OP_ADVANCE = 2 };
 enum OpFlags : uint32_t {
     OPF_NO_STORE = 1u,  // SAVE with ring depth 0: checksum only
     OPF_SPAWN = 2u,     // ADVANCE: spawn_particles fired; rows [spawn_first, spawn_first+spawn_count) are born at the end of the frame
+    // bits 8..11 of an ADVANCE op's flags: number of players (PlayerInputs<T>.len())
 };
 
 struct Op {
@@ -656,6 +657,46 @@ __global__ void __launch_bounds__(256) k_sys_particles_spawn(uint8_t* img, uint3
         uint32_t* l = reinterpret_cast<uint32_t*>(img + word_offset(words, r, l_plane));
         l[0] = ttl_lo; l[kTileRows] = ttl_hi;
         img[alive_offset(words, r)] = 1;
+    }
+}
+
+// move_cube_system (box_game.rs:154-206), BASELINE config C1.  player handle == RollbackOrdered index.
+// `FRICTION.powf(dt)` is libm on the CPU and CUDA powf here: this is the one system of the path whose f32
+// results are only guaranteed within a tolerance (|d| <= 1e-5 * max(1, |x|), tested), not bit-exact.
+__global__ void k_sys_box_move(uint8_t* img, uint32_t words, uint32_t t_plane, uint32_t v_plane, uint32_t n_rows,
+                               uint32_t dt_bits, uint32_t inputs_packed, uint32_t n_players, unsigned long long order_base) {
+    const float dt = __uint_as_float(dt_bits);
+    const float ACCELERATION = 18.0f, MAX_SPEED = 3.0f, FRICTION = 0.0018f, PLANE_SIZE = 5.0f, CUBE_SIZE = 0.2f;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
+        if (!img[alive_offset(words, r)]) continue;
+        float* t = reinterpret_cast<float*>(img + word_offset(words, r, t_plane));
+        float* v = reinterpret_cast<float*>(img + word_offset(words, r, v_plane));
+        float tx = t[0], ty = t[kTileRows], tz = t[2 * kTileRows];
+        float vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
+        const unsigned long long handle = order_base + r;
+        const uint32_t input = handle < n_players && handle < 4 ? (inputs_packed >> (8 * uint32_t(handle))) & 0xffu : 0u;
+        const bool up = input & 1u, down = input & 2u, left = input & 4u, right = input & 8u;
+        const float a = __fmul_rn(ACCELERATION, dt);
+        if (up && !down) vz = __fsub_rn(vz, a);
+        if (!up && down) vz = __fadd_rn(vz, a);
+        if (left && !right) vx = __fsub_rn(vx, a);
+        if (!left && right) vx = __fadd_rn(vx, a);
+        const float fr = powf(FRICTION, dt);
+        if (!up && !down) vz = __fmul_rn(vz, fr);
+        if (!left && !right) vx = __fmul_rn(vx, fr);
+        vy = __fmul_rn(vy, fr);
+        // glam Vec3::clamp_length_max(MAX_SPEED)
+        const float len_sq = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+        if (len_sq > __fmul_rn(MAX_SPEED, MAX_SPEED)) {
+            const float l = __fsqrt_rn(len_sq);
+            vx = __fmul_rn(MAX_SPEED, __fdiv_rn(vx, l)); vy = __fmul_rn(MAX_SPEED, __fdiv_rn(vy, l)); vz = __fmul_rn(MAX_SPEED, __fdiv_rn(vz, l));
+        }
+        tx = __fadd_rn(tx, __fmul_rn(vx, dt)); ty = __fadd_rn(ty, __fmul_rn(vy, dt)); tz = __fadd_rn(tz, __fmul_rn(vz, dt));
+        const float hw = __fmul_rn(__fsub_rn(PLANE_SIZE, CUBE_SIZE), 0.5f);
+        tx = tx < -hw ? -hw : (tx > hw ? hw : tx);
+        tz = tz < -hw ? -hw : (tz > hw ? hw : tz);
+        t[0] = tx; t[kTileRows] = ty; t[2 * kTileRows] = tz;
+        v[0] = vx; v[kTileRows] = vy; v[2 * kTileRows] = vz;
     }
 }
 

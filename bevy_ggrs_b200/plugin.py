@@ -94,6 +94,15 @@ class System:
     params: Sequence[int] = ()
 
 
+@dataclass
+class ResourceSystem:
+    """A GgrsSchedule system that only touches host-side resources (e.g. box_game's increase_frame_system,
+    box_game.rs:146-148): ``fn(resources: dict[str, bytearray])``.  Resources are a few bytes and not
+    data-parallel, so they stay on the host; the shim rolls them back per frame and XORs
+    their checksum parts into the engine's checksum."""
+    fn: Callable
+
+
 class GgrsPlugin:  # lib.rs:198-258
     def build(self, app: "App") -> None:
         app._ggrs = True
@@ -121,6 +130,12 @@ class App:
         self._first_update = True
         self.last_checksums: List[tuple] = []
         self.ticks = 0
+        # host-side resources (rollback_resource_with_copy / checksum_resource_with_hash)
+        self.resources: Dict[str, bytearray] = {}
+        self._res_checksummed: List[str] = []
+        self._res_systems: List[Callable] = []
+        self._res_store: Dict[int, Dict[str, bytes]] = {}
+        self._res_frame = 0
 
     # ---- App ----
     def add_plugins(self, plugin) -> "App":
@@ -140,7 +155,10 @@ class App:
 
     def add_systems(self, schedule, system) -> "App":
         if schedule is GgrsSchedule:
-            assert isinstance(system, System), "GgrsSchedule systems are compiled-in GPU systems"
+            if isinstance(system, ResourceSystem):
+                self._res_systems.append(system.fn)
+                return self
+            assert isinstance(system, System), "GgrsSchedule systems are compiled-in GPU systems or ResourceSystems"
             self.world.add_system(system.system, list(system.columns), list(system.params))
         elif schedule is ReadInputs:
             self._read_inputs.append(system)
@@ -169,6 +187,16 @@ class App:
 
     def checksum_component_with_hash(self, column: int) -> "App":
         return self.checksum_component(column, 0, self.world.elem_bytes[column])
+
+    def rollback_resource_with_copy(self, type_name: str, initial: bytes) -> "App":  # rollback_app.rs:171-176
+        self.resources[type_name] = bytearray(initial)
+        return self
+
+    rollback_resource_with_clone = rollback_resource_with_copy
+
+    def checksum_resource_with_hash(self, type_name: str) -> "App":  # rollback_app.rs:213-218
+        self._res_checksummed.append(type_name)
+        return self
 
     # ---- frame resources ----
     def rollback_frame_count(self) -> int:
@@ -238,7 +266,38 @@ class App:
     def handle_requests(self, requests: Sequence[Request]) -> None:
         inner = self._session.inner
         checksums = self.world.handle_requests(inner.info(), requests)
+        if self.resources:
+            checksums = self._handle_resource_requests(requests, checksums)
         # cell.save(frame, None, checksum) (:236)
         for frame, cs in checksums:
             inner.save_cell(frame, cs)
         self.last_checksums = checksums
+
+    # host-side half of handle_requests for resources (resource_snapshot.rs:65-93, resource_checksum.rs:63-82):
+    # the same request vector, replayed on a few bytes of host state; parts are XORed into the engine's
+    # checksum exactly like ChecksumPlugin::update folds every ChecksumPart (checksum.rs:88-99).
+    def _handle_resource_requests(self, requests, checksums):
+        import ctypes as C
+        lib = capi.load_library()
+        out, k = [], 0
+        for r in requests:
+            if r.kind == SAVE:
+                self._res_store[self._res_frame] = {n: bytes(v) for n, v in self.resources.items()}
+                part = 0
+                for name in self._res_checksummed:
+                    b = bytes(self.resources[name])
+                    part ^= lib.bgr_seahash(C.create_string_buffer(b, len(b)), len(b))
+                frame, cs = checksums[k]
+                out.append((frame, cs ^ part))
+                k += 1
+            elif r.kind == LOAD:
+                self._res_frame = r.frame
+                for n, v in self._res_store[r.frame].items():
+                    self.resources[n] = bytearray(v)
+            else:
+                self._res_frame += 1
+                for fn in self._res_systems:
+                    fn(self.resources)
+        alive = set(self.world.snapshot_frames())
+        self._res_store = {f: v for f, v in self._res_store.items() if f in alive}
+        return out

@@ -237,6 +237,12 @@ BGR_API int bgr_fold_partials(const bgr_partial* combined, bgr_checksum* out);
 BGR_API int bgr_collect_partials(bgr_engine* e, bgr_partial* partials_out, uint32_t cap, uint32_t* n_out);
 BGR_API int bgr_fold_partials_n(const bgr_partial* combined, uint32_t n, bgr_checksum* out);
 
+/* ---- checksum_hasher() (src/snapshot/mod.rs:315-317) for host-side parts -------------------------------
+ * Resources stay on the host (a few bytes, not data-parallel).  A shim that registers
+ * `checksum_resource_with_hash::<R>()` (resource_checksum.rs:63-82) computes `part = bgr_seahash(bytes of R)`
+ * per Save and XORs it into the engine's checksum (ChecksumPlugin::update, checksum.rs:88-99). */
+BGR_API uint64_t bgr_seahash(const void* bytes, uint64_t len);
+
 /* ---- GgrsTime (src/time.rs:63-76): delta_secs of the step that ends at `frame` ---------- */
 BGR_API uint32_t bgr_ggrs_time_delta_bits(uint32_t fps, int32_t frame);
 

@@ -1,0 +1,76 @@
+"""BASELINE config C1 on the GPU: box_game SyncTest, 2 players, check_distance 8 (max_prediction 9),
+input_delay 2 (examples/box_game/box_game_synctest.rs).  move_cube_system uses powf, so Transform / Velocity
+are compared with the north_star's stated f32 tolerance |d| <= 1e-5 * max(1, |x|); the checksum
+(FrameCount resource part ^ entity part, box_game_synctest.rs:55) must be bit-identical."""
+import struct
+
+import numpy as np
+import pytest
+
+from bevy_ggrs_b200 import capi
+from bevy_ggrs_b200.engine import Engine
+from bevy_ggrs_b200.plugin import (App, GgrsPlugin, GgrsSchedule, LocalInputs, ReadInputs, ResourceSystem, Session,
+                                   Startup, SyncTestMismatch, System)
+from bevy_ggrs_b200.session import SyncTestSession
+from oracle_backend import ORC_SYS_RESOURCE_U32_ADD, OracleWorld
+
+pytestmark = pytest.mark.gpu
+SEQ = [0b0001, 0b1000, 0b0101, 0, 0b0010, 0b1010, 0b0100, 0b1001]
+
+
+def _setup(a, tf):
+    first = a.world.spawn(2)
+    t = np.zeros((2, 10), np.float32)
+    r = 5.0 / 4.0
+    for h in range(2):
+        rot = np.float32(h) / np.float32(2) * np.float32(2.0) * np.float32(np.pi)
+        t[h, 0] = r * np.cos(rot); t[h, 1] = 0.1; t[h, 2] = r * np.sin(rot)
+        t[h, 6] = 1.0; t[h, 7:10] = 1.0
+    a.world.write_component(tf, first, t)
+
+
+def _app(backend, native_resource):
+    app = App(backend)
+    app.insert_resource(Session.SyncTest(SyncTestSession(2, 8, 9, input_delay=2)))
+    app.add_plugins(GgrsPlugin())
+    app.add_systems(ReadInputs, lambda a: a.insert_resource(
+        LocalInputs({h: SEQ[(a.ticks + 3 * h) % len(SEQ)] for h in a.local_players.handles})))
+    vel = app.rollback_component_with_copy("Velocity", 12)
+    tf = app.rollback_component_with_clone("Transform", 40)
+    app.add_systems(GgrsSchedule, System(capi.BGR_SYS_BOX_MOVE, [tf, vel]))
+    if native_resource:  # the oracle restates resource rollback + checksum itself
+        fc = backend.rollback_resource("FrameCount", bytes(4), checksum=True)
+        app.add_systems(GgrsSchedule, System(ORC_SYS_RESOURCE_U32_ADD, [], [fc]))
+    else:                # product: resources stay host-side in the shim
+        app.rollback_resource_with_copy("FrameCount", bytes(4)).checksum_resource_with_hash("FrameCount")
+
+        def increase_frame_system(res):  # box_game.rs:146-148
+            res["FrameCount"][:] = struct.pack("<I", (struct.unpack("<I", res["FrameCount"])[0] + 1) & 0xFFFFFFFF)
+        app.add_systems(GgrsSchedule, ResourceSystem(increase_frame_system))
+    app.add_systems(Startup, lambda a: _setup(a, tf))
+    bad = []
+    app.add_observer(SyncTestMismatch, lambda ev: bad.append(ev))
+    return app, tf, vel, bad
+
+
+def test_box_game_synctest_c1_gpu_vs_oracle():
+    eng, orc = Engine(max_entities=4, max_depth=9), OracleWorld()
+    app_e, tf, vel, bad_e = _app(eng, native_resource=False)
+    app_o, _, _, bad_o = _app(orc, native_resource=True)
+    cs_e, cs_o = [], []
+    for _ in range(120):
+        app_e.update(); app_o.update()
+        cs_e += app_e.last_checksums; cs_o += app_o.last_checksums
+    assert not bad_e and not bad_o                     # SyncTest self-consistent on both
+    assert cs_e == cs_o and len(cs_e) > 500            # FrameCount part ^ entity part: bit-identical
+    assert app_e.rollback_frame_count() == app_o.rollback_frame_count() == 119
+    assert struct.unpack("<I", app_e.resources["FrameCount"])[0] == 119
+    for col in (tf, vel):
+        a = eng.read_component(col, 0, 2).view(np.float32)
+        b = orc.read_component(col, 0, 2).view(np.float32)
+        assert np.all(np.abs(a - b) <= 1e-5 * np.maximum(1.0, np.abs(b))), (a, b)
+    t = eng.read_component(tf, 0, 2).view(np.float32)
+    assert np.all(np.abs(t[:, [0, 2]]) <= 2.4 + 1e-6)   # constrained to the plane
+    v = eng.read_component(vel, 0, 2).view(np.float32)
+    assert np.all(np.linalg.norm(v, axis=1) <= 3.0 + 1e-5) and np.any(v != 0)
+    assert not eng.last_path_fused()                    # box_game has no fused bundle: stepwise path

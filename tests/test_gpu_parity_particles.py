@@ -63,3 +63,62 @@ def test_spawn_particles_inside_the_rollback_window(flags):
     assert r["active"][0] == r["active"][1]
     assert r["mismatch_events"] == (0, 0)
     assert r["ring"][0] == r["ring"][1]
+
+
+def test_extra_passive_columns_of_odd_sizes_ride_along():
+    """the example also registers render-side PODs (GlobalTransform 48 B, Visibility /
+    InheritedVisibility / ViewVisibility 1 B each).  No compiled system touches them: they are passive planes
+    (several TMA runs, sub-word elements) and must survive save / load / resimulation byte for byte."""
+    import numpy as np
+    from bevy_ggrs_b200.engine import Engine
+    from bevy_ggrs_b200.plugin import App, GgrsPlugin, LocalInputs, ReadInputs, Session
+    from bevy_ggrs_b200.session import SyncTestSession
+    from bevy_ggrs_b200.stress import synth_particles
+    from oracle_backend import OracleWorld
+
+    n, d, ticks = 3000, 5, 20
+    rng = np.random.default_rng(3)
+    gt = rng.integers(0, 256, size=(n, 48), dtype=np.uint8)
+    vis = rng.integers(0, 3, size=(n, 1), dtype=np.uint8)
+    odd = rng.integers(0, 256, size=(n, 6), dtype=np.uint8)      # a 6-byte POD: 1.5 words
+    worlds, apps, colsets = [], [], []
+    for backend in (Engine(max_entities=n, max_depth=8), OracleWorld()):
+        app = App(backend)
+        app.add_plugins(GgrsPlugin())
+        app.add_systems(ReadInputs, lambda a: a.insert_resource(LocalInputs({h: 0 for h in a.local_players.handles})))
+        c_gt = app.rollback_component_with_clone("GlobalTransform", 48)
+        c_t = app.rollback_component_with_clone("Transform", 40)
+        c_vis = app.rollback_component_with_clone("Visibility", 1)
+        c_v = app.rollback_component_with_copy("Velocity", 12)
+        c_odd = app.rollback_component_with_copy("Odd6", 6)
+        c_l = app.rollback_component_with_copy("Ttl", 8)
+        app.checksum_component(c_v, 0, 12, assert_finite=True).checksum_component(c_t, 0, 12, assert_finite=True)
+        backend.add_system(capi.BGR_SYS_PARTICLES_UPDATE, [c_t, c_v])
+        backend.add_system(capi.BGR_SYS_PARTICLES_DESPAWN, [c_l])
+        app.insert_resource(Session.SyncTest(SyncTestSession(1, d, 8)))
+        app._finish()
+        tf, vel, ttl = synth_particles(n, 21, 4, 30)
+        first = backend.spawn(n)
+        for c, a in ((c_gt, gt), (c_t, tf), (c_vis, vis), (c_v, vel), (c_odd, odd), (c_l, ttl)):
+            backend.write_component(c, first, a)
+        worlds.append(backend); apps.append(app); colsets.append((c_gt, c_t, c_vis, c_v, c_odd, c_l))
+    cs = [[], []]
+    for _ in range(ticks):
+        for i, app in enumerate(apps):
+            app.step()
+            cs[i] += app.last_checksums
+    eng, orc = worlds
+    assert eng.last_path_fused()
+    assert cs[0] == cs[1] and len(cs[0]) > ticks
+    alive = orc.read_alive(0, n).astype(bool)
+    assert np.array_equal(eng.read_alive(0, n).astype(bool), alive) and alive.any() and not alive.all()
+    for c in colsets[0]:
+        assert np.array_equal(eng.read_component(c, 0, n)[alive], orc.read_component(c, 0, n)[alive])
+    # passive columns are untouched by 20 frames of rollback
+    assert np.array_equal(eng.read_component(colsets[0][0], 0, n)[alive], gt[alive])
+    assert np.array_equal(eng.read_component(colsets[0][4], 0, n)[alive], odd[alive])
+    # peek a snapshot: same bytes as the oracle's snapshot of that frame
+    f = eng.snapshot_frames()[-1]
+    pe, po = eng.peek(f, colsets[0][0], 0, n), orc.peek(f, colsets[0][0], 0, n)
+    m = po[1].astype(bool)
+    assert np.array_equal(pe[1].astype(bool), m) and np.array_equal(pe[0][m], po[0][m])
