@@ -292,9 +292,11 @@ def run_ours(args):
     if rank == 0 and world_size == 1 and not args.no_cpu_baseline:
         cpu = run_cpu_sample(n, d, maxp, rollback_ticks=3)
     snap = None
+    skip = None
     if rank == 0 and world_size == 1 and not args.no_snapshot_bench:
         eng.close()
         snap = snapshot_bench(n, maxp, local_rank)
+        skip = skip_unchanged_bench(n, d, maxp, local_rank, ticks, fill, W, K, history)
 
     if rank == 0:
         value = world_size * adv_total / (ms * 1e-3)
@@ -323,12 +325,62 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if snap:
             line["snapshot_save_restore"] = snap
+        if skip:
+            line["opt_in_skip_unchanged_planes"] = skip
         print(json.dumps(line), flush=True)
     eng.close()
     if sharded:
         dist.destroy_process_group()
     if not consistent:
         sys.exit(3)
+
+
+def skip_unchanged_bench(n, d, maxp, device_index, ticks, fill, W, K, reference_history):
+    """Same workload with BGR_CFG_SKIP_UNCHANGED_PLANES (opt-in, NOT the headline): planes no registered system
+    writes (Transform.rotation/scale, 28 of 61 B/entity) are not rewritten into slots that already hold them.
+    Every checksum must equal the default run's.  Bytes are counted as actually moved: 33 B/entity/image."""
+    import torch
+    from bevy_ggrs_b200 import capi
+    from bevy_ggrs_b200.engine import Engine
+    stream = torch.cuda.Stream()
+    eng = Engine(max_entities=n, max_depth=maxp, fps=60, device=device_index, flags=capi.BGR_CFG_SKIP_UNCHANGED_PLANES,
+                 stream=stream.cuda_stream)
+    build_world(eng, n, d, SEED)
+    hist = []
+
+    def run(tl):
+        inflight = 0
+        for arr, nreq, _, info, _ in tl:
+            eng.submit_prepared(info, arr, nreq)
+            inflight += 1
+            if inflight > 2:
+                hist.extend(eng.collect()); inflight -= 1
+        while inflight:
+            hist.extend(eng.collect()); inflight -= 1
+
+    with torch.cuda.stream(stream):
+        run(ticks[:fill + W])
+        torch.cuda.synchronize()
+        timed = ticks[fill + W: fill + W + K]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run(timed)
+        e1.record(stream)
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    rows = eng.row_count()
+    eng.close()
+    ref = {}
+    for f, c in reference_history:
+        ref.setdefault(f, c)
+    same = all(ref.get(f, c) == c for f, c in hist)
+    moved = sum(len(t[4]) + 2 for t in timed) / K * rows * 33
+    peak, _ = measured_hbm_peak()
+    return {"value": sum(t[2] for t in timed) / (ms * 1e-3), "unit": "rollback frames/s", "ms_per_step": ms / K,
+            "checksums_equal_default_run": same, "bytes_moved_per_step": moved,
+            "achieved_gbps": moved / (ms / K * 1e-3) / 1e9, "frac_of_measured_hbm": moved / (ms / K * 1e-3) / 1e9 / peak,
+            "note": "opt-in BGR_CFG_SKIP_UNCHANGED_PLANES: redundant stores of planes no system writes are elided "
+                    "(content-version tracking); NOT used for the headline value"}
 
 
 def snapshot_bench(n, maxp, device_index, iters=50):

@@ -40,6 +40,7 @@ BGR_SESSION_NONE, BGR_SESSION_SYNCTEST, BGR_SESSION_P2P, BGR_SESSION_SPECTATOR =
 # bgr_config.flags
 BGR_CFG_FORCE_STEPWISE = 1
 BGR_CFG_SHARDED = 2
+BGR_CFG_SKIP_UNCHANGED_PLANES = 4
 
 
 class bgr_request(C.Structure):

@@ -105,6 +105,9 @@ struct HostState {
     uint32_t call_count = 0;                // un-rolled-back counter of BGR_SYS_U32_STORE_CALL_COUNT
     ParticleRng rng;                        // ParticleRng resource (particles.rs:128)
     std::vector<ParticleRng> slot_rng;      // its per-snapshot clones
+    // content versions of the passive planes (BGR_CFG_SKIP_UNCHANGED_PLANES): equal ids <=> identical bytes
+    uint64_t live_passive_ver = 1, ver_counter = 1;
+    std::vector<uint64_t> slot_passive_ver;  // 0 = never written
 };
 
 struct Pending {
@@ -202,6 +205,8 @@ struct Program {
     uint32_t save_totals[kMaxSaves];
     uint32_t max_rows = 0, live_rows = 0;
     bool has_load = false, has_advance = false, first_is_load = false, has_spawn = false;
+    bool passive_to_slots = false;   // at least one SAVE must (re)write the passive planes
+    bool passive_to_live = false;    // a LOAD changed the content of the live passive planes
     std::vector<float2> spawn_vals;
 };
 
@@ -252,6 +257,11 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
                 s.slot_rows[slot] = s.n_rows;
                 s.slot_elapsed_ns[slot] = s.elapsed_ns;
                 s.slot_rng[slot] = s.rng;
+                if ((e->cfg.flags & BGR_CFG_SKIP_UNCHANGED_PLANES) && s.slot_passive_ver[slot] == s.live_passive_ver)
+                    op.flags |= OPF_SKIP_PASSIVE;
+                else
+                    pg.passive_to_slots = true;
+                s.slot_passive_ver[slot] = s.live_passive_ver;
             }
             op.n_rows = s.n_rows;
             op.save_index = pg.n_saves;
@@ -269,6 +279,9 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
             s.n_rows = s.slot_rows[slot];
             s.elapsed_ns = s.slot_elapsed_ns[slot];
             s.rng = s.slot_rng[slot];
+            if (!(e->cfg.flags & BGR_CFG_SKIP_UNCHANGED_PLANES) || s.slot_passive_ver[slot] != s.live_passive_ver)
+                pg.passive_to_live = true;
+            s.live_passive_ver = s.slot_passive_ver[slot];
             op.kind = OP_LOAD;
             op.image_off256 = e->image_off256(slot + 1);
             op.n_rows = s.n_rows;
@@ -315,6 +328,7 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
                         pg.spawn_vals.push_back(v);
                     }
                     s.n_rows += rate;  // Rollback on_add -> RollbackOrdered.push, applied at the end of the frame
+                    s.live_passive_ver = ++s.ver_counter;  // newborn rows carry Transform::default() rotation / scale
                     pg.has_spawn = true;
                     pg.max_rows = std::max(pg.max_rows, s.n_rows);
                 }
@@ -368,7 +382,8 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
     pp.flags = 0;
     if (!pg.first_is_load) pp.flags |= PF_READ_LIVE;
     if (pg.has_load || pg.has_advance) pp.flags |= PF_WRITE_LIVE_ACTIVE;
-    if (pg.has_load) pp.flags |= PF_WRITE_LIVE_PASSIVE;
+    if ((pg.has_load && pg.passive_to_live) || pg.has_spawn) pp.flags |= PF_WRITE_LIVE_PASSIVE;
+    const bool passive_needed = pg.passive_to_slots || (pp.flags & PF_WRITE_LIVE_PASSIVE) || pg.has_spawn;
     uint32_t n_loads = 0;
     for (uint32_t i = 0; i < pg.n_ops; ++i) n_loads += (pg.ops[i].kind == OP_LOAD);
     const bool simple = n_loads == 0 || (n_loads == 1 && pg.first_is_load);
@@ -384,9 +399,9 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
     if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_V; pp.ck_v_slot = uint32_t(cv.ck_slot); }
     pp.t_off = ct.first_plane * kPlaneBytes; pp.v_off = cv.first_plane * kPlaneBytes;
     pp.l_off = e->cols[e->bl].first_plane * kPlaneBytes; pp.alive_off = e->words * kPlaneBytes;
-    pp.n_runs = uint32_t(e->runs.size()); pp.passive_bytes = e->passive_bytes;
+    pp.n_runs = passive_needed ? uint32_t(e->runs.size()) : 0u; pp.passive_bytes = e->passive_bytes;
     for (size_t i = 0; i < e->runs.size(); ++i) pp.runs[i] = e->runs[i];
-    pp.n_passive = uint32_t(e->passive.size());
+    pp.n_passive = passive_needed ? uint32_t(e->passive.size()) : 0u;
     for (size_t i = 0; i < e->passive.size(); ++i) {
         pp.passive[i] = e->passive[i];
         // Transform::default(): rotation = (0,0,0,1), scale = (1,1,1); every other passive word of a newborn row is 0
@@ -675,6 +690,7 @@ int transfer_column(bgr_engine* e, uint32_t image_idx, uint32_t column, uint32_t
     uint8_t* img = e->image(image_idx);
     uint32_t grid = e->grid_for(uint32_t(std::min<size_t>(size_t(count) * c.words, 0x7fffffffu)), 256);
     if (to_device) {
+        e->st.live_passive_ver = ++e->st.ver_counter;  // host wrote a column: live content is new
         CUDA_TRY(cudaMemcpyAsync(e->d_stage, host, bytes, cudaMemcpyHostToDevice, e->stream));
         k_scatter_column<<<grid, 256, 0, e->stream>>>(img, e->words, c.first_plane, c.words, c.elem_bytes, first, count, e->d_stage, stride);
         e->launches += 1;
@@ -935,6 +951,7 @@ BGR_API int bgr_build(bgr_engine* e) {
     e->st.slot_rows.assign(e->cfg.max_depth, 0);
     e->st.slot_elapsed_ns.assign(e->cfg.max_depth, 0);
     e->st.slot_rng.assign(e->cfg.max_depth, ParticleRng());
+    e->st.slot_passive_ver.assign(e->cfg.max_depth, 0);
     if (e->spawn_sys >= 0)
         for (int i = 0; i < bgr_engine::kBufs; ++i) {
             CUDA_TRY(cudaHostAlloc(&e->h_spawn[i], sizeof(float2) * kMaxSpawnVals, cudaHostAllocMapped));
@@ -976,6 +993,7 @@ BGR_API int bgr_run_startup_system(bgr_engine* e, uint32_t system) {
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     e->st.n_rows += rate;
+    e->st.live_passive_ver = ++e->st.ver_counter;
     return BGR_OK;
 }
 
@@ -992,6 +1010,7 @@ BGR_API int bgr_spawn(bgr_engine* e, uint32_t count, uint32_t* first_row_out) {
         CUDA_TRY(cudaStreamSynchronize(e->stream));
     }
     e->st.n_rows += count;
+    e->st.live_passive_ver = ++e->st.ver_counter;
     if (first_row_out) *first_row_out = first;
     return BGR_OK;
 }

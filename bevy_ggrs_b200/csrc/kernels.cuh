@@ -54,6 +54,7 @@ enum OpKind : uint32_t { OP_SAVE = 0, OP_LOAD = 1, OP_ADVANCE = 2 };
 enum OpFlags : uint32_t {
     OPF_NO_STORE = 1u,  // SAVE with ring depth 0: checksum only
     OPF_SPAWN = 2u,     // ADVANCE: spawn_particles fired; rows [spawn_first, spawn_first+spawn_count) are born at the end of the frame
+    OPF_SKIP_PASSIVE = 4u,  // SAVE: the slot already holds the current content of the passive planes (BGR_CFG_SKIP_UNCHANGED_PLANES)
     // bits 8..11 of an ADVANCE op's flags: number of players (PlayerInputs<T>.len())
 };
 
@@ -380,7 +381,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                 mbar_wait(&s_bar[buf], (it >> 1) & 1u);
                 const uint8_t* src = s_passive + size_t(buf) * p.passive_bytes;
                 for (uint32_t i = 0; i < p.n_ops; ++i) {
-                    if (p.ops[i].kind != OP_SAVE || (p.ops[i].flags & OPF_NO_STORE)) continue;
+                    if (p.ops[i].kind != OP_SAVE || (p.ops[i].flags & (OPF_NO_STORE | OPF_SKIP_PASSIVE))) continue;
                     uint8_t* img = p.arena + (size_t(p.ops[i].image_off256) << 8) + tile_off;
                     uint32_t o = 0;
                     for (uint32_t r = 0; r < p.n_runs; ++r) { tma_store_1d(img + p.runs[r].off, src + o, p.runs[r].bytes); o += p.runs[r].bytes; }
@@ -410,7 +411,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             if (k < nk) vec_load<VEC>(img + size_t(p.passive[pp + k]) * kPlaneBytes + woff, v[k]);
-                    } else if (kind == OP_SAVE && !(p.ops[i].flags & OPF_NO_STORE)) {
+                    } else if (kind == OP_SAVE && !(p.ops[i].flags & (OPF_NO_STORE | OPF_SKIP_PASSIVE))) {
 #pragma unroll
                         for (int k = 0; k < 4; ++k)
                             if (k < nk) vec_store<VEC>(img + size_t(p.passive[pp + k]) * kPlaneBytes + woff, v[k]);

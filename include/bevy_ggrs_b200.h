@@ -154,6 +154,13 @@ typedef struct bgr_config {
 } bgr_config;
 #define BGR_CFG_FORCE_STEPWISE 1u  /* never use the fused one-launch program kernel (debug / A-B tests) */
 #define BGR_CFG_SHARDED 2u         /* handle_requests returns partials only; caller folds across shards */
+/* OPT-IN, off by default: do not rewrite word planes whose content is provably identical to what the target
+ * image already holds.  The engine tracks a content version for the planes no registered system writes
+ * (e.g. Transform.rotation/scale in the stress test): a Save into a slot that already holds the current version
+ * skips those planes, and so does a Load.  Snapshots stay complete images (peek / load need no indirection) and
+ * every observable result is unchanged; only redundant HBM stores are elided.  The reference clones every
+ * registered component on every save (component_snapshot.rs:71-75), so the default keeps doing exactly that. */
+#define BGR_CFG_SKIP_UNCHANGED_PLANES 4u
 
 typedef struct bgr_engine bgr_engine;
 

@@ -65,7 +65,8 @@ def compare_state(eng, orc, cols, n):
 
 
 def run_particles_synctest_pair(n_entities, check_distance, ticks, seed, max_prediction=None, ttl_lo=None,
-                                ttl_hi=None, flags=0, tune=None, spawn_rate=0, spawn_ttl=300, startup_burst=False):
+                                ttl_hi=None, flags=0, tune=None, spawn_rate=0, spawn_ttl=300, startup_burst=False,
+                                peek_check=False):
     """SyncTest on the GPU engine and on the oracle with identical inputs; returns comparison facts."""
     maxp = max_prediction or max(8, check_distance + 1)
     ttl_lo = ttl_lo if ttl_lo is not None else 300 + check_distance
@@ -88,11 +89,23 @@ def run_particles_synctest_pair(n_entities, check_distance, ticks, seed, max_pre
         all_o += app_o.last_checksums
     tick_launches = eng.launch_count() - launches0
     fused = eng.last_path_fused()
+    peek_equal = True
+    if peek_check:  # every live snapshot, every column: same bytes as the oracle's snapshot of that frame
+        n_rows = eng.row_count()
+        for f in eng.snapshot_frames():
+            for c in cols_e:
+                pe, po = eng.peek(f, c, 0, n_rows), orc.peek(f, c, 0, n_rows)
+                if (pe is None) != (po is None):
+                    peek_equal = False
+                    continue
+                m = po[1].astype(bool)
+                peek_equal = peek_equal and np.array_equal(pe[1].astype(bool), m) and np.array_equal(pe[0][m], po[0][m])
     res = {
         "checksums_equal": all_e == all_o and len(all_e) > 0,
         "n_checksums": len(all_e),
         "state_equal": eng.row_count() == orc.row_count() and compare_state(eng, orc, cols_e, eng.row_count()),
         "rows": (eng.row_count(), orc.row_count()),
+        "peek_equal": peek_equal,
         "mismatch_events": (len(mism_e), len(mism_o)),
         "fused": fused,
         "launches": tick_launches,

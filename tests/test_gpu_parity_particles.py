@@ -50,6 +50,25 @@ def test_fused_and_stepwise_agree_checksum_for_checksum():
     assert b["launches"] > 10 * a["launches"]
 
 
+@pytest.mark.parametrize("ticks", [2, 3, 5])
+def test_spawn_in_plain_save_advance_ticks_writes_whole_rows(ticks):
+    """Before the first rollback the ticks are [Save, Advance]: rows spawned there must be complete in the live
+    image (Transform::default() rotation / scale are passive planes)."""
+    r = run_particles_synctest_pair(100, 6, ticks, seed=3, ttl_lo=50, ttl_hi=60, spawn_rate=30, spawn_ttl=50)
+    assert r["fused"] and r["rows"][0] == r["rows"][1] > 100
+    assert r["checksums_equal"] and r["state_equal"]
+
+
+@pytest.mark.parametrize("flags", [0, capi.BGR_CFG_SKIP_UNCHANGED_PLANES])
+def test_skip_unchanged_planes_is_observably_identical(flags):
+    """BGR_CFG_SKIP_UNCHANGED_PLANES only elides redundant stores: checksums, live state, and the bytes peeked
+    out of every snapshot (including passive rotation/scale) equal the oracle's, with spawns bumping the
+    content version mid-run."""
+    r = run_particles_synctest_pair(2000, 5, 30, seed=8, ttl_lo=4, ttl_hi=60, flags=flags, spawn_rate=20, spawn_ttl=12,
+                                    peek_check=True)
+    assert r["fused"] and r["checksums_equal"] and r["state_equal"] and r["peek_equal"]
+
+
 @pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])
 def test_spawn_particles_inside_the_rollback_window(flags):
     """spawn_particles.run_if(spawn_pressed) with the rolled-back ParticleRng — rows are born
