@@ -50,10 +50,11 @@ def test_fused_and_stepwise_agree_checksum_for_checksum():
     assert b["launches"] > 10 * a["launches"]
 
 
-@pytest.mark.parametrize("ticks", [2, 3, 5])
+@pytest.mark.parametrize("ticks", [4, 5, 6])
 def test_spawn_in_plain_save_advance_ticks_writes_whole_rows(ticks):
-    """Before the first rollback the ticks are [Save, Advance]: rows spawned there must be complete in the live
-    image (Transform::default() rotation / scale are passive planes)."""
+    """Before the first rollback (check_distance 6) the ticks are [Save, Advance]; with input_delay 2 the spawn
+    key pressed on ticks 1-2 fires on frames 3-4.  Rows spawned there must be complete in the live image
+    (Transform::default() rotation / scale are passive planes)."""
     r = run_particles_synctest_pair(100, 6, ticks, seed=3, ttl_lo=50, ttl_hi=60, spawn_rate=30, spawn_ttl=50)
     assert r["fused"] and r["rows"][0] == r["rows"][1] > 100
     assert r["checksums_equal"] and r["state_equal"]
