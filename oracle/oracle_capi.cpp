@@ -7,6 +7,7 @@
 #include <memory>
 #include <string>
 
+#include "soa_baseline.hpp"
 #include "world.hpp"
 
 using namespace oracle;
@@ -210,6 +211,34 @@ ORC_API int orc_last_partial(World* w, bgr_partial* out) {
 // handle_requests; also returns the wall time spent inside (ns) for the CPU baseline
 ORC_API int orc_handle_requests(World* w, const bgr_session_info* sess, const bgr_request* reqs, uint32_t n,
                                 bgr_checksum* out, uint32_t cap, uint32_t* n_out, uint64_t* elapsed_ns) {
+    std::vector<bgr_checksum> cs;
+    auto t0 = std::chrono::steady_clock::now();
+    int rc = guarded([&] { w->handle_requests(*sess, reqs, n, cs); });
+    auto t1 = std::chrono::steady_clock::now();
+    if (elapsed_ns) *elapsed_ns = uint64_t(std::chrono::duration_cast<std::chrono::nanoseconds>(t1 - t0).count());
+    uint32_t k = 0;
+    for (auto& c : cs) { if (k < cap) out[k] = c; ++k; }
+    if (n_out) *n_out = k;
+    return rc;
+}
+
+// ---- optimised SoA CPU bar -------------------------------------------------------------
+ORC_API SoaWorld* orc_soa_new(uint32_t n, uint32_t depth, uint32_t fps, uint32_t threads) { return new SoaWorld(n, depth, fps, threads); }
+ORC_API void orc_soa_free(SoaWorld* w) { delete w; }
+ORC_API void orc_soa_set_columns(SoaWorld* w, const float* tf, const float* vel, const uint64_t* ttl) {
+    std::memcpy(w->live.tf.data(), tf, w->n * 40);
+    std::memcpy(w->live.vel.data(), vel, w->n * 12);
+    std::memcpy(w->live.ttl.data(), ttl, w->n * 8);
+    std::fill(w->live.alive.begin(), w->live.alive.end(), uint8_t(1));
+}
+ORC_API void orc_soa_get_columns(SoaWorld* w, float* tf, float* vel, uint64_t* ttl, uint8_t* alive) {
+    std::memcpy(tf, w->live.tf.data(), w->n * 40);
+    std::memcpy(vel, w->live.vel.data(), w->n * 12);
+    std::memcpy(ttl, w->live.ttl.data(), w->n * 8);
+    std::memcpy(alive, w->live.alive.data(), w->n);
+}
+ORC_API int orc_soa_handle_requests(SoaWorld* w, const bgr_session_info* sess, const bgr_request* reqs, uint32_t n,
+                                    bgr_checksum* out, uint32_t cap, uint32_t* n_out, uint64_t* elapsed_ns) {
     std::vector<bgr_checksum> cs;
     auto t0 = std::chrono::steady_clock::now();
     int rc = guarded([&] { w->handle_requests(*sess, reqs, n, cs); });

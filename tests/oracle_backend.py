@@ -84,6 +84,12 @@ def load_oracle() -> C.CDLL:
         "orc_load_world": (C.c_int, [vp]),
         "orc_advance_world": (C.c_int, [vp, vp, u32]),
         "orc_last_partial": (C.c_int, [vp, C.POINTER(capi.bgr_partial)]),
+        "orc_soa_new": (vp, [u32, u32, u32, u32]),
+        "orc_soa_free": (None, [vp]),
+        "orc_soa_set_columns": (None, [vp, vp, vp, vp]),
+        "orc_soa_get_columns": (None, [vp, vp, vp, vp, vp]),
+        "orc_soa_handle_requests": (C.c_int, [vp, C.POINTER(capi.bgr_session_info), C.POINTER(capi.bgr_request), u32,
+                                              C.POINTER(capi.bgr_checksum), u32, u32p, u64p]),
         "orc_handle_requests": (C.c_int, [vp, C.POINTER(capi.bgr_session_info), C.POINTER(capi.bgr_request), u32,
                                           C.POINTER(capi.bgr_checksum), u32, u32p, u64p]),
     }
@@ -241,3 +247,41 @@ class OracleWorld:
         self.last_elapsed_ns = ns.value
         self._check(st)
         return [(out[i].frame, (out[i].hi << 64) | out[i].lo) for i in range(n.value)]
+
+
+class SoaWorld:
+    """The optimised CPU SoA bar (oracle/soa_baseline.hpp): particles schema, all host cores."""
+
+    def __init__(self, tf, vel, ttl, depth, fps=60, threads=0):
+        self._lib = load_oracle()
+        self.n = tf.shape[0]
+        self.threads = threads or (os.cpu_count() or 1)
+        self._h = C.c_void_p(self._lib.orc_soa_new(self.n, depth, fps, self.threads))
+        tf = np.ascontiguousarray(tf, dtype=np.float32); vel = np.ascontiguousarray(vel, dtype=np.float32)
+        ttl = np.ascontiguousarray(ttl, dtype=np.uint64)
+        self._lib.orc_soa_set_columns(self._h, tf.ctypes.data, vel.ctypes.data, ttl.ctypes.data)
+        self.last_elapsed_ns = 0
+
+    def handle_requests(self, session_info, requests):
+        reqs = list(requests)
+        arr = capi.make_requests(reqs)
+        info = capi.make_session_info(session_info)
+        out = (capi.bgr_checksum * capi.BGR_MAX_REQUESTS)()
+        n, ns = C.c_uint32(), C.c_uint64()
+        st = self._lib.orc_soa_handle_requests(self._h, C.byref(info), arr, len(reqs), out, capi.BGR_MAX_REQUESTS,
+                                               C.byref(n), C.byref(ns))
+        self.last_elapsed_ns = ns.value
+        if st != 0:
+            raise OracleError(st, self._lib.orc_last_error().decode())
+        return [(out[i].frame, (out[i].hi << 64) | out[i].lo) for i in range(n.value)]
+
+    def columns(self):
+        tf = np.zeros((self.n, 10), np.float32); vel = np.zeros((self.n, 3), np.float32)
+        ttl = np.zeros(self.n, np.uint64); alive = np.zeros(self.n, np.uint8)
+        self._lib.orc_soa_get_columns(self._h, tf.ctypes.data, vel.ctypes.data, ttl.ctypes.data, alive.ctypes.data)
+        return tf, vel, ttl, alive
+
+    def close(self):
+        if self._h:
+            self._lib.orc_soa_free(self._h)
+            self._h = None
