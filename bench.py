@@ -160,6 +160,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     n, d, maxp = WORKLOADS[args.workload]
+    if args.entities:
+        n = args.entities
     K, W = args.steps, max(3, args.warmup)
     stream = torch.cuda.Stream(device=dev)
     sharded = world_size > 1
@@ -539,6 +541,7 @@ def main():
     ap.add_argument("--workload", default="stress_1m_d8", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-snapshot-bench", action="store_true")
+    ap.add_argument("--entities", type=int, default=0, help="override the workload's entity count (scaling studies)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
