@@ -359,17 +359,26 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                 // ---- checksum partials (component_checksum.rs:81-90) ----
                 uint64_t hx_t = 0, hx_v = 0;
                 uint32_t bad = 0;
+                // z == +0.0f for every row of the warp (a 2-D world): the tail lane of the 12-byte hash is a
+                // compile-time constant, one diffusion less per entity and column.  Warp-uniform test.
+                uint32_t tz_any = 0, vz_any = 0;
+#pragma unroll
+                for (int j = 0; j < VEC; ++j) { tz_any |= tr[2][j]; vz_any |= vl[2][j]; }
+                const bool tz_zero = CKT && __all_sync(0xffffffffu, tz_any == 0u);
+                const bool vz_zero = CKV && __all_sync(0xffffffffu, vz_any == 0u);
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
                     const uint64_t live = ((alive >> (8 * j)) & 1u) ? ~0ULL : 0ULL;
                     if (CKT) {
                         if (FINT) bad |= (f32_bits_nonfinite(tr[0][j]) | f32_bits_nonfinite(tr[1][j]) | f32_bits_nonfinite(tr[2][j])) & uint32_t(live);
-                        uint64_t c = sea_hash_12(uint64_t(tr[0][j]) | (uint64_t(tr[1][j]) << 32), tr[2][j]);
+                        const uint64_t lane_t = tz_zero ? kSeaTailZero : sea_diffuse(kSeaB ^ uint64_t(tr[2][j]));
+                        uint64_t c = sea_hash_12_lane(uint64_t(tr[0][j]) | (uint64_t(tr[1][j]) << 32), lane_t);
                         hx_t ^= sea_hash_entity(t0[j], c) & live;
                     }
                     if (CKV) {
                         if (FINV) bad |= (f32_bits_nonfinite(vl[0][j]) | f32_bits_nonfinite(vl[1][j]) | f32_bits_nonfinite(vl[2][j])) & uint32_t(live);
-                        uint64_t c = sea_hash_12(uint64_t(vl[0][j]) | (uint64_t(vl[1][j]) << 32), vl[2][j]);
+                        const uint64_t lane_v = vz_zero ? kSeaTailZero : sea_diffuse(kSeaB ^ uint64_t(vl[2][j]));
+                        uint64_t c = sea_hash_12_lane(uint64_t(vl[0][j]) | (uint64_t(vl[1][j]) << 32), lane_v);
                         hx_v ^= sea_hash_entity(t0[j], c) & live;
                     }
                 }

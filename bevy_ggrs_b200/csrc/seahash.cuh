@@ -12,9 +12,9 @@
 #include <cstdint>
 
 #if defined(__CUDACC__)
-#define BGR_HD __host__ __device__ __forceinline__
+#define BGR_HD __host__ __device__ __forceinline__ constexpr
 #else
-#define BGR_HD inline
+#define BGR_HD inline constexpr
 #endif
 
 namespace bgr {
@@ -47,6 +47,13 @@ BGR_HD uint64_t sea_hash_12(uint64_t w0, uint32_t tail) {
     uint64_t a = sea_diffuse(kSeaB ^ uint64_t(tail));  // tail goes into the new first lane
     return sea_diffuse(a ^ kSeaC ^ kSeaD ^ t ^ 12ULL);
 }
+// the tail lane when the last field is +0.0f (a 2-D game's z): a compile-time constant
+constexpr uint64_t kSeaTailZero = sea_diffuse(kSeaB);
+// same hash with the tail lane supplied by the caller (kSeaTailZero when the caller knows tail == 0)
+BGR_HD uint64_t sea_hash_12_lane(uint64_t w0, uint64_t tail_lane) {
+    uint64_t t = sea_diffuse(kSeaA ^ w0);
+    return sea_diffuse(tail_lane ^ kSeaC ^ kSeaD ^ t ^ 12ULL);
+}
 
 // first lane of the per-entity hash: depends only on the RollbackOrdered index, so it is
 // computed once per entity per launch and reused for every frame and every column
@@ -63,7 +70,12 @@ BGR_HD uint64_t sea_hash_2xu64(uint64_t a, uint64_t b) { return sea_hash_entity(
 
 // Generic stream over `n` bytes delivered by a callable byte(i) -> uint8_t (stepwise path only).
 template <class ByteAt>
-BGR_HD uint64_t sea_hash_stream(uint32_t n, ByteAt byte_at) {
+#if defined(__CUDACC__)
+__host__ __device__ __forceinline__
+#else
+inline
+#endif
+uint64_t sea_hash_stream(uint32_t n, ByteAt byte_at) {
     uint64_t a = kSeaA, b = kSeaB, c = kSeaC, d = kSeaD;
     uint32_t i = 0;
     for (; i + 8 <= n; i += 8) {

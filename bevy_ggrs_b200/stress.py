@@ -34,9 +34,11 @@ def register_particles(world, spawn_rate: int = 0, spawn_ttl: int = 300, rng_see
     return t, v, l
 
 
-def synth_particles(n: int, seed: int, ttl_lo: int, ttl_hi: int):
+def synth_particles(n: int, seed: int, ttl_lo: int, ttl_hi: int, z_fraction: float = 0.0):
     """Seeded synthetic population: translation x,y ~ U(-360,360), velocity x,y ~ U(-200,200)
-    (particles.rs:259,265), z = 0, identity rotation, unit scale, ttl ~ U{ttl_lo..ttl_hi}."""
+    (particles.rs:259,265), z = 0, identity rotation, unit scale, ttl ~ U{ttl_lo..ttl_hi}.
+    z_fraction > 0 gives that share of the rows a non-zero z translation and velocity (the example itself is
+    2-D; used by tests to exercise the general hash path next to the z == 0 fast path)."""
     rng = np.random.default_rng(seed)
     tf = np.zeros((n, 10), dtype=np.float32)
     tf[:, 0:2] = rng.uniform(-360.0, 360.0, size=(n, 2)).astype(np.float32)
@@ -45,6 +47,10 @@ def synth_particles(n: int, seed: int, ttl_lo: int, ttl_hi: int):
     vel = np.zeros((n, 3), dtype=np.float32)
     vel[:, 0:2] = rng.uniform(-200.0, 200.0, size=(n, 2)).astype(np.float32)
     ttl = rng.integers(ttl_lo, ttl_hi + 1, size=n, dtype=np.uint64)
+    if z_fraction > 0:
+        pick = rng.random(n) < z_fraction
+        tf[pick, 2] = rng.uniform(-50.0, 50.0, size=int(pick.sum())).astype(np.float32)
+        vel[pick, 2] = rng.uniform(-20.0, 20.0, size=int(pick.sum())).astype(np.float32)
     return tf, vel, ttl
 
 

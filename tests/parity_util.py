@@ -19,7 +19,7 @@ def input_system(app):
 
 
 def make_particles_app(backend, n_entities, seed, session, ttl_lo, ttl_hi, noop_inputs=False, spawn_rate=0,
-                       spawn_ttl=300, startup_burst=False):
+                       spawn_ttl=300, startup_burst=False, z_fraction=0.0):
     app = App(backend)
     app.add_plugins(GgrsPlugin())
     app.insert_resource(RollbackFrameRate(60))
@@ -43,7 +43,7 @@ def make_particles_app(backend, n_entities, seed, session, ttl_lo, ttl_hi, noop_
     mism = []
     app.add_observer(SyncTestMismatch, lambda ev: mism.append(ev))
     app._finish()
-    tf, vel, ttl = synth_particles(n_entities, seed, ttl_lo, ttl_hi)
+    tf, vel, ttl = synth_particles(n_entities, seed, ttl_lo, ttl_hi, z_fraction)
     populate(backend, cols, tf, vel, ttl)
     if startup_burst:
         backend.run_startup_system(capi.BGR_SYS_PARTICLES_SPAWN)  # add_systems(Startup, spawn_particles), particles.rs:232
@@ -66,7 +66,7 @@ def compare_state(eng, orc, cols, n):
 
 def run_particles_synctest_pair(n_entities, check_distance, ticks, seed, max_prediction=None, ttl_lo=None,
                                 ttl_hi=None, flags=0, tune=None, spawn_rate=0, spawn_ttl=300, startup_burst=False,
-                                peek_check=False):
+                                peek_check=False, z_fraction=0.0):
     """SyncTest on the GPU engine and on the oracle with identical inputs; returns comparison facts."""
     maxp = max_prediction or max(8, check_distance + 1)
     ttl_lo = ttl_lo if ttl_lo is not None else 300 + check_distance
@@ -76,10 +76,10 @@ def run_particles_synctest_pair(n_entities, check_distance, ticks, seed, max_pre
     orc = OracleWorld(fps=60)
     app_e, cols_e, mism_e = make_particles_app(eng, n_entities, seed, Session.SyncTest(
         SyncTestSession(2, check_distance, maxp, input_delay=2)), ttl_lo, ttl_hi, noop_inputs=True,
-        spawn_rate=spawn_rate, spawn_ttl=spawn_ttl, startup_burst=startup_burst)
+        spawn_rate=spawn_rate, spawn_ttl=spawn_ttl, startup_burst=startup_burst, z_fraction=z_fraction)
     app_o, cols_o, mism_o = make_particles_app(orc, n_entities, seed, Session.SyncTest(
         SyncTestSession(2, check_distance, maxp, input_delay=2)), ttl_lo, ttl_hi, noop_inputs=True,
-        spawn_rate=spawn_rate, spawn_ttl=spawn_ttl, startup_burst=startup_burst)
+        spawn_rate=spawn_rate, spawn_ttl=spawn_ttl, startup_burst=startup_burst, z_fraction=z_fraction)
     all_e, all_o = [], []
     launches0 = eng.launch_count()
     for _ in range(ticks):

@@ -142,3 +142,12 @@ def test_extra_passive_columns_of_odd_sizes_ride_along():
     pe, po = eng.peek(f, colsets[0][0], 0, n), orc.peek(f, colsets[0][0], 0, n)
     m = po[1].astype(bool)
     assert np.array_equal(pe[1].astype(bool), m) and np.array_equal(pe[0][m], po[0][m])
+
+
+@pytest.mark.parametrize("z_fraction", [1.0, 0.02, 0.5])
+@pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])
+def test_non_zero_z_takes_the_general_hash_path(z_fraction, flags):
+    """The fused kernel skips one diffusion when a whole warp has z == +0.0 (the example is 2-D); rows with a
+    non-zero z — all of them, a few (mixed warps), half — must hash exactly like the oracle."""
+    r = run_particles_synctest_pair(6000, 4, 14, seed=31, ttl_lo=3, ttl_hi=40, flags=flags, z_fraction=z_fraction)
+    assert r["checksums_equal"] and r["state_equal"]
