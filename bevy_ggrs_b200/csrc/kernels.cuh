@@ -243,11 +243,13 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         if (tid == 0) {
             for (uint32_t k = 0; k < kRing; ++k) { mbar_init(&s_full[k], 1); mbar_init(&s_empty[k], BLOCK / 32); }
             fence_mbar_init();
-            s_tile[1] = gridDim.x + atomicAdd(&p.ticket[1], 1u);  // the tile this block runs at it == 1
+            s_tile[0] = gridDim.x + atomicAdd(&p.ticket[1], 1u);  // the tile this block runs at it == 1 (ring entry j-1 = 0)
         }
         __syncthreads();
-        if (tid == 0) mbar_arrive(&s_full[1]);
+        if (tid == 0) mbar_arrive(&s_full[0]);
     }
+    // ring entry of the tile that iteration j (>= 1) runs: slot (j-1) % kRing, in its ((j-1) / kRing)-th use;
+    // iteration 0 runs tile blockIdx.x and never enters the ring
     uint32_t claimed = 0;        // thread 0: tile claimed for iteration it + 2 (valid while claim_live)
     bool claim_live = true;      // thread 0: the previous claim was a real tile, keep claiming
     uint32_t it = 0;
@@ -460,13 +462,13 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         }
         if (dynamic) {
             if (tid == 0 && claim_live) {  // publish the tile of iteration it + 2
-                const uint32_t slot = (it + 2) % kRing, use = (it + 2) / kRing;
+                const uint32_t slot = (it + 1) % kRing, use = (it + 1) / kRing;
                 if (use > 0) mbar_wait(&s_empty[slot], (use - 1) & 1u);  // every warp has read the previous occupant
                 s_tile[slot] = claimed;
                 mbar_arrive(&s_full[slot]);
                 claim_live = claimed < p.n_tiles;
             }
-            const uint32_t slot = (it + 1) % kRing, use = (it + 1) / kRing;
+            const uint32_t slot = it % kRing, use = it / kRing;  // entry of iteration it + 1
             mbar_wait(&s_full[slot], use & 1u);
             tile = s_tile[slot];
             __syncwarp();

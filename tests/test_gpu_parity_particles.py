@@ -151,3 +151,17 @@ def test_non_zero_z_takes_the_general_hash_path(z_fraction, flags):
     non-zero z — all of them, a few (mixed warps), half — must hash exactly like the oracle."""
     r = run_particles_synctest_pair(6000, 4, 14, seed=31, ttl_lo=3, ttl_hi=40, flags=flags, z_fraction=z_fraction)
     assert r["checksums_equal"] and r["state_equal"]
+
+
+@pytest.mark.parametrize("bps,dynamic", [("1", "1"), ("1", "0"), ("2", "1")])
+def test_many_tiles_per_block(monkeypatch, bps, dynamic):
+    """Blocks that run many tile iterations (one resident block per SM, 780 tiles): exercises the dynamic tile
+    ring (claims two ahead, slot reuse, empty/full mbarrier phases) and the static stride far past the first
+    wave.  A protocol error here hangs, so the run is bounded by pytest-timeout."""
+    monkeypatch.setenv("BGR_TUNE_BPS", bps)
+    monkeypatch.setenv("BGR_TUNE_DYNAMIC", dynamic)
+    r = run_particles_synctest_pair(400_000, 2, 6, seed=17, ttl_lo=2, ttl_hi=30)
+    assert r["fused"] and r["checksums_equal"] and r["state_equal"]
+
+
+test_many_tiles_per_block = pytest.mark.timeout(120)(test_many_tiles_per_block)
