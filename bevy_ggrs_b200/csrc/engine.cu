@@ -181,7 +181,7 @@ struct bgr_engine {
     int tune_vec = 2, tune_minb = 8, tune_bps = 0, tune_passive_tma = 1;
     int tune_tma = 1;          // stepwise Save/Load through the TMA-staged bulk-copy kernel
     uint32_t tma_stage_tiles = 0;  // tiles per TMA stage (0: schema too wide for 3 stages of shared memory)
-    int occ_cache[3][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+    int occ_cache[3][2][3] = {};
 
     uint8_t* image(uint32_t idx) const { return arena + size_t(idx) * image_bytes; }
     uint32_t image_off256(uint32_t idx) const { return uint32_t((size_t(idx) * image_bytes) >> 8); }
@@ -411,13 +411,16 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
     std::memcpy(pp.ops, pg.ops, sizeof(Op) * pg.n_ops);
     const int v = e->tune_vec;
     const bool st = e->bundle_static_ck;
-    const bool hi = e->tune_minb > 1;
+    const int mb = e->tune_minb >= 8 ? 2 : (e->tune_minb >= 2 ? 1 : 0);  // launch-bounds tier: 1024 / 768 / unconstrained threads per SM
 #define BGR_LAUNCH(VEC, VI)                                                                                \
     if (v == VEC) {                                                                                        \
         constexpr int kHi = (1024 / int(kTileRows / VEC)) > 32 ? 32 : (1024 / int(kTileRows / VEC));        \
-        if (st && hi) return launch_particles<VEC, true, kHi>(e, pp, VI, 1, 1);                            \
+        constexpr int kMid = (768 / int(kTileRows / VEC)) < 1 ? 1 : (768 / int(kTileRows / VEC));           \
+        if (st && mb == 2) return launch_particles<VEC, true, kHi>(e, pp, VI, 1, 2);                       \
+        if (st && mb == 1) return launch_particles<VEC, true, kMid>(e, pp, VI, 1, 1);                      \
         if (st) return launch_particles<VEC, true, 1>(e, pp, VI, 1, 0);                                    \
-        if (hi) return launch_particles<VEC, false, kHi>(e, pp, VI, 0, 1);                                 \
+        if (mb == 2) return launch_particles<VEC, false, kHi>(e, pp, VI, 0, 2);                            \
+        if (mb == 1) return launch_particles<VEC, false, kMid>(e, pp, VI, 0, 1);                           \
         return launch_particles<VEC, false, 1>(e, pp, VI, 0, 0);                                           \
     }
     BGR_LAUNCH(1, 0)

@@ -232,9 +232,11 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     __syncthreads();
 
     const uint32_t i0 = tid * VEC;  // first row of this thread inside the tile
-    // Dynamic tile hand-off WITHOUT a block barrier: thread 0 claims tiles two iterations ahead from a global
-    // counter and publishes them through a 4-slot ring guarded by full/empty mbarriers, so a fast warp never
-    // waits for a slow one (a per-tile __syncthreads cost 13 % of all warp time in the round-1 profile).
+    // Dynamic tile hand-off WITHOUT a block barrier: at the top of a tile thread 0 claims the block's NEXT tile
+    // from a global counter (late binding: one tile ahead, so the tail stays balanced) and publishes it a little
+    // later — once the atomic has returned, hidden behind the tile's loads — through a 4-slot ring guarded by
+    // full/empty mbarriers.  A fast warp never waits for a slow one (a per-tile __syncthreads cost 13 % of all
+    // warp time in the round-1 profile).
     constexpr uint32_t kRing = 4;
     __shared__ uint32_t s_tile[kRing];
     __shared__ __align__(8) uint64_t s_full[kRing], s_empty[kRing];
@@ -243,18 +245,15 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         if (tid == 0) {
             for (uint32_t k = 0; k < kRing; ++k) { mbar_init(&s_full[k], 1); mbar_init(&s_empty[k], BLOCK / 32); }
             fence_mbar_init();
-            s_tile[0] = gridDim.x + atomicAdd(&p.ticket[1], 1u);  // the tile this block runs at it == 1 (ring entry j-1 = 0)
         }
         __syncthreads();
-        if (tid == 0) mbar_arrive(&s_full[0]);
     }
     // ring entry of the tile that iteration j (>= 1) runs: slot (j-1) % kRing, in its ((j-1) / kRing)-th use;
     // iteration 0 runs tile blockIdx.x and never enters the ring
-    uint32_t claimed = 0;        // thread 0: tile claimed for iteration it + 2 (valid while claim_live)
-    bool claim_live = true;      // thread 0: the previous claim was a real tile, keep claiming
+    uint32_t claimed = 0;        // thread 0: tile claimed for iteration it + 1
     uint32_t it = 0;
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; ++it) {
-        if (dynamic && tid == 0 && claim_live) claimed = gridDim.x + atomicAdd(&p.ticket[1], 1u);  // consumed at the bottom
+        if (dynamic && tid == 0) claimed = gridDim.x + atomicAdd(&p.ticket[1], 1u);  // published after the loads below
         const size_t tile_off = size_t(tile) * p.tile_bytes;
         const uint32_t row0 = tile * kTileRows + i0;
         const size_t woff = tile_off + size_t(i0) * 4u;  // + plane offset (+ image offset) = address of this thread's words
@@ -311,6 +310,13 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
 #pragma unroll
         for (int j = 0; j < VEC; ++j) t0[j] = sea_order_lane(p.order_base + row0 + j);
 
+        if (dynamic && tid == 0) {  // publish the tile of iteration it + 1 (ring entry `it`)
+            const uint32_t slot = it % kRing, use = it / kRing;
+            if (use > 0) mbar_wait(&s_empty[slot], (use - 1) & 1u);  // every warp has read the previous occupant
+            s_tile[slot] = claimed;
+            mbar_arrive(&s_full[slot]);
+        }
+
         uint32_t pend[6] = {0, 0, 0, 0, 0, 0};
         uint32_t pend_row = 0;
         bool pend_valid = false;
@@ -366,8 +372,11 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                 uint32_t tz_any = 0, vz_any = 0;
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) { tz_any |= tr[2][j]; vz_any |= vl[2][j]; }
-                const bool tz_zero = CKT && __all_sync(0xffffffffu, tz_any == 0u);
-                const bool vz_zero = CKV && __all_sync(0xffffffffu, vz_any == 0u);
+#ifndef BGR_ZERO_TAIL
+#define BGR_ZERO_TAIL 1
+#endif
+                const bool tz_zero = BGR_ZERO_TAIL && CKT && __all_sync(0xffffffffu, tz_any == 0u);
+                const bool vz_zero = BGR_ZERO_TAIL && CKV && __all_sync(0xffffffffu, vz_any == 0u);
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
                     const uint64_t live = ((alive >> (8 * j)) & 1u) ? ~0ULL : 0ULL;
@@ -461,13 +470,6 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
             }
         }
         if (dynamic) {
-            if (tid == 0 && claim_live) {  // publish the tile of iteration it + 2
-                const uint32_t slot = (it + 1) % kRing, use = (it + 1) / kRing;
-                if (use > 0) mbar_wait(&s_empty[slot], (use - 1) & 1u);  // every warp has read the previous occupant
-                s_tile[slot] = claimed;
-                mbar_arrive(&s_full[slot]);
-                claim_live = claimed < p.n_tiles;
-            }
             const uint32_t slot = it % kRing, use = it / kRing;  // entry of iteration it + 1
             mbar_wait(&s_full[slot], use & 1u);
             tile = s_tile[slot];
