@@ -168,8 +168,9 @@ struct bgr_engine {
     uint64_t launches = 0;
     bool last_fused = false;
     unsigned long long seq = 0;   // sequence number of the last submit (completion flag value)
-    int tune_poll = 1;
-    int tune_dynamic = 1;         // dynamic tile scheduling in the fused kernel (measured +5% over a static stride)            // collect() spins on the host-mapped flag before falling back to the event
+    int tune_poll = 1;            // collect() spins on the host-mapped flag before falling back to the event
+    int tune_pdl = 1;             // programmatic dependent launch between consecutive fused kernels
+    int tune_dynamic = 1;         // dynamic tile scheduling in the fused kernel (measured +5% over a static stride)
 
     // compiled bundle: particles (update_particles + despawn_particles)
     bool bundle_particles = false;
@@ -178,7 +179,7 @@ struct bgr_engine {
     std::vector<PassiveRun> runs;
     uint32_t passive_bytes = 0;
     bool bundle_static_ck = false;  // both columns checksummed with the finite assertion: fully specialised kernel
-    int tune_vec = 2, tune_minb = 8, tune_bps = 0, tune_passive_tma = 1;
+    int tune_vec = 2, tune_minb = 2, tune_bps = 0, tune_passive_tma = 1;
     int tune_tma = 1;          // stepwise Save/Load through the TMA-staged bulk-copy kernel
     uint32_t tma_stage_tiles = 0;  // tiles per TMA stage (0: schema too wide for 3 stages of shared memory)
     int occ_cache[3][2][3] = {};
@@ -360,7 +361,13 @@ int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int
     int bps = e->occ_cache[vi][si][mi];
     if (e->tune_bps > 0) bps = std::min(e->tune_bps, bps);
     uint32_t grid = std::max(1u, std::min(pp.n_tiles, uint32_t(e->num_sms * bps)));
-    kern<<<grid, BLOCK, smem, e->stream>>>(pp);
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(BLOCK); lc.dynamicSmemBytes = smem; lc.stream = e->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = e->tune_pdl ? 1 : 0;
+    lc.attrs = attr; lc.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&lc, kern, pp));
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
     return BGR_OK;
@@ -805,12 +812,13 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
         e->own_stream = true;
     }
     e->tune_vec = env_int("BGR_TUNE_VEC", 2);
-    e->tune_minb = env_int("BGR_TUNE_MINB", 8);
+    e->tune_minb = env_int("BGR_TUNE_MINB", 2);
     e->tune_bps = env_int("BGR_TUNE_BPS", 0);
     e->tune_tma = env_int("BGR_TUNE_TMA", 1);
     e->tune_passive_tma = env_int("BGR_TUNE_PASSIVE_TMA", 1);
     e->tune_poll = env_int("BGR_TUNE_POLL", 1);
     e->tune_dynamic = env_int("BGR_TUNE_DYNAMIC", 1);
+    e->tune_pdl = env_int("BGR_TUNE_PDL", 1);
     if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 2;
     e->st.confirmed = 0;
     *out = e;

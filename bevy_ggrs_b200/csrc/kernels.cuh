@@ -222,6 +222,9 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     __shared__ unsigned int s_last;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    // Programmatic dependent launch: let the NEXT request vector's kernel be launched and its blocks scheduled
+    // into SM slots as this grid drains (hides launch latency and block ramp-up between back-to-back ticks) ...
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (uint32_t i = tid; i < p.n_saves * kAccStride * 2; i += BLOCK) s_acc[i] = 0u;
     const bool use_tma = (p.flags & PF_PASSIVE_TMA) && p.n_runs > 0;
     if (tid == 0 && use_tma) {
@@ -230,6 +233,9 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         fence_mbar_init();
     }
     __syncthreads();
+
+    // ... while this grid touches no global memory before the previous grid has completed and flushed
+    asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const uint32_t i0 = tid * VEC;  // first row of this thread inside the tile
     // Dynamic tile hand-off WITHOUT a block barrier: at the top of a tile thread 0 claims the block's NEXT tile

@@ -1,16 +1,12 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/ab_*.json
-timeout 200 python -m pytest tests/test_gpu_parity_particles.py -m gpu -x -q 2>&1 | tail -3
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 run() { name=$1; shift; env "$@" timeout 60 python bench.py --steps 1000 --warmup 5 --no-cpu-baseline --no-snapshot-bench > gpurun_out/ab_$name.json 2>gpurun_out/ab_$name.err; }
 for rep in 1 2; do
-run v2_m1_dyn_$rep BGR_TUNE_MINB=1
-run v2_m2_dyn_$rep BGR_TUNE_MINB=2
-run v2_m8_dyn_$rep BGR_TUNE_MINB=8
+run pdl1_$rep A=1
+run pdl0_$rep BGR_TUNE_PDL=0
 done
-run v2_m1_static BGR_TUNE_MINB=1 BGR_TUNE_DYNAMIC=0
-run v2_m2_static BGR_TUNE_MINB=2 BGR_TUNE_DYNAMIC=0
-run v4_m1_dyn BGR_TUNE_VEC=4 BGR_TUNE_MINB=1
-run v4_m2_dyn BGR_TUNE_VEC=4 BGR_TUNE_MINB=2
+run pdl1_100k BGR_X=1
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/ab_*.json')):
@@ -20,3 +16,6 @@ for f in sorted(glob.glob('gpurun_out/ab_*.json')):
     except Exception as e:
         print(f, "FAILED", open(f.replace('.json','.err')).read()[-200:])
 PY
+for pdl in 1 0; do BGR_TUNE_PDL=$pdl timeout 60 python bench.py --workload stress_100k_d8 --steps 2000 --warmup 5 --no-cpu-baseline --no-snapshot-bench 2>/dev/null | python -c "
+import json,sys
+d=json.loads([l for l in sys.stdin if l.startswith('{')][0]); print('100k pdl=$pdl ms=%.4f e2e=%.0f'%(d['ms_per_step'],d['e2e']['value']))"; done
