@@ -169,7 +169,7 @@ struct bgr_engine {
     bool last_fused = false;
     unsigned long long seq = 0;   // sequence number of the last submit (completion flag value)
     int tune_poll = 1;            // collect() spins on the host-mapped flag before falling back to the event
-    int tune_pdl = 1;             // programmatic dependent launch between consecutive fused kernels
+    int tune_pdl = 0;             // programmatic dependent launch between consecutive fused kernels (measured: +0.8 % at 1M, -14 % at 100k -> off)
     int tune_dynamic = 1;         // dynamic tile scheduling in the fused kernel (measured +5% over a static stride)
 
     // compiled bundle: particles (update_particles + despawn_particles)
@@ -818,7 +818,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_passive_tma = env_int("BGR_TUNE_PASSIVE_TMA", 1);
     e->tune_poll = env_int("BGR_TUNE_POLL", 1);
     e->tune_dynamic = env_int("BGR_TUNE_DYNAMIC", 1);
-    e->tune_pdl = env_int("BGR_TUNE_PDL", 1);
+    e->tune_pdl = env_int("BGR_TUNE_PDL", 0);
     if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 2;
     e->st.confirmed = 0;
     *out = e;

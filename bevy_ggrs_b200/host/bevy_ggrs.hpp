@@ -65,6 +65,12 @@ struct System {
     std::vector<uint32_t> params;
 };
 
+// A GgrsSchedule system that only touches host-side resources (box_game.rs:146-148 increase_frame_system).
+// Resources are a few bytes and not data-parallel: they stay on the host, this layer rolls them back per frame
+// (resource_snapshot.rs:65-93) and XORs their checksum parts into the engine's checksum (checksum.rs:88-99).
+class App;
+struct ResourceSystem { std::function<void(App&)> fn; };
+
 // what a `fn(&T) -> u64` hasher becomes across the C ABI: seahash of a byte range of the element
 struct ByteRangeHasher { uint32_t offset, len; bool assert_finite; };
 inline ByteRangeHasher hash_bytes(uint32_t offset, uint32_t len, bool assert_finite = false) { return {offset, len, assert_finite}; }
@@ -88,6 +94,7 @@ public:
     App& add_systems(ReadInputs, std::function<void(App&)> f) { read_inputs_.push_back(std::move(f)); return *this; }
     App& add_systems(Startup, std::function<void(App&)> f) { startup_.push_back(std::move(f)); return *this; }
     App& add_systems(GgrsSchedule, System s) { systems_.push_back(std::move(s)); return *this; }
+    App& add_systems(GgrsSchedule, ResourceSystem s) { res_systems_.push_back(std::move(s.fn)); return *this; }
     App& add_observer(std::function<void(const SyncTestMismatch&)> f) { observers_.push_back(std::move(f)); return *this; }
 
     // ---- RollbackApp (rollback_app.rs:31-248) ----
@@ -95,6 +102,23 @@ public:
     template <class T> App& rollback_component_with_clone() { return register_component<T>(BGR_STRATEGY_CLONE); }
     template <class T> App& checksum_component(ByteRangeHasher h) { checksums_.push_back({col<T>(), h}); return *this; }
     template <class T> App& checksum_component_with_hash() { return checksum_component<T>(hash_bytes(0, uint32_t(sizeof(T)))); }
+
+    // rollback_resource_with_copy / _with_clone (rollback_app.rs:171-176, 192-197) and
+    // checksum_resource_with_hash (rollback_app.rs:213-218) for POD resources, host-side
+    template <class R> App& rollback_resource_with_copy(const R& initial) {
+        static_assert(std::is_trivially_copyable<R>::value, "POD resources only");
+        std::vector<uint8_t> b(sizeof(R));
+        std::memcpy(b.data(), &initial, sizeof(R));
+        resources_[std::type_index(typeid(R))] = std::move(b);
+        return *this;
+    }
+    template <class R> App& rollback_resource_with_clone(const R& initial) { return rollback_resource_with_copy<R>(initial); }
+    template <class R> App& checksum_resource_with_hash() { res_checksummed_.push_back(std::type_index(typeid(R))); return *this; }
+    template <class R> R& resource() {
+        auto it = resources_.find(std::type_index(typeid(R)));
+        if (it == resources_.end()) throw Panic(BGR_ERR_MISSING_RESOURCE, std::string("Requested resource does not exist: ") + typeid(R).name());
+        return *reinterpret_cast<R*>(it->second.data());
+    }
 
     template <class T> uint32_t col() const {
         auto it = columns_.find(std::type_index(typeid(T)));
@@ -203,11 +227,45 @@ private:
         uint32_t n = 0;
         check(bgr_handle_requests(engine_, &info, reqs.data(), uint32_t(reqs.size()), last_checksums_.data(), BGR_MAX_REQUESTS, &n));
         last_checksums_.resize(n);
+        if (!resources_.empty()) handle_resource_requests(requests);
         for (auto& cs : last_checksums_)  // cell.save(frame, None, checksum) (:231-236)
             sess.save_cell(cs.frame, (static_cast<unsigned __int128>(cs.hi) << 64) | cs.lo);
     }
 
+    // host-side half of handle_requests for resources: the same request vector replayed on a few bytes
+    void handle_resource_requests(const std::vector<ggrs::GgrsRequest>& requests) {
+        size_t k = 0;
+        for (const auto& r : requests) {
+            if (r.kind == ggrs::GgrsRequest::SaveGameState) {
+                res_store_[res_frame_] = resources_;
+                uint64_t part = 0;
+                for (auto& t : res_checksummed_) { auto& b = resources_.at(t); part ^= bgr_seahash(b.data(), b.size()); }
+                if (k < last_checksums_.size()) last_checksums_[k].lo ^= part;
+                ++k;
+            } else if (r.kind == ggrs::GgrsRequest::LoadGameState) {
+                res_frame_ = r.frame;
+                resources_ = res_store_.at(r.frame);
+            } else {
+                res_frame_ += 1;
+                for (auto& f : res_systems_) f(*this);
+            }
+        }
+        int32_t frames[128]; uint32_t nf = 0;
+        check(bgr_snapshot_frames(engine_, frames, 128, &nf));
+        for (auto it = res_store_.begin(); it != res_store_.end();) {
+            bool alive = false;
+            for (uint32_t i = 0; i < nf && i < 128; ++i) alive = alive || frames[i] == it->first;
+            it = alive ? std::next(it) : res_store_.erase(it);
+        }
+    }
+
     struct PendingCol { std::type_index type; std::string name; uint32_t bytes, strategy; };
+    using ResourceMap = std::map<std::type_index, std::vector<uint8_t>>;
+    ResourceMap resources_;
+    std::vector<std::type_index> res_checksummed_;
+    std::vector<std::function<void(App&)>> res_systems_;
+    std::map<ggrs::Frame, ResourceMap> res_store_;
+    ggrs::Frame res_frame_ = 0;
     bgr_config cfg_{};
     bgr_engine* engine_ = nullptr;
     std::vector<PendingCol> pending_cols_;

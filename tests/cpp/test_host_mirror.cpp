@@ -10,6 +10,7 @@
 #include <string>
 
 #include "../../bevy_ggrs_b200/host/bevy_ggrs.hpp"
+#include "../../oracle/world.hpp"  // the checker: tests may link the oracle (never the product)
 
 using namespace bevy_ggrs;
 
@@ -155,6 +156,90 @@ static void particles_stress_synctest() {  // examples/stress_tests/particles.rs
     EXPECT(std::fabs((v[k].v[1] - v2[0].v[1]) - 100.0f) < 0.01f);
 }
 
+struct FrameCount { uint32_t frame; };  // box_game.rs:49-53
+
+// BASELINE config C1: box_game SyncTest, 2 players, check_distance 8 (max_prediction 9), input_delay 2
+// (examples/box_game/box_game_synctest.rs) — engine through the C++ mirror vs the oracle in the same process.
+static void box_game_synctest_c1() {
+    std::printf("box_game_synctest_c1\n");
+    const uint8_t seq[8] = {1, 8, 5, 0, 2, 10, 4, 9};
+    int tick_e = 0;
+    App app(4, 9);
+    app.insert_resource(Session::SyncTest(ggrs::SyncTestSession(2, 8, 9, 2)))
+        .add_plugins(GgrsPlugin<GgrsConfig<uint8_t>>{})
+        .add_systems(ReadInputs{}, [&](App& a) {
+            LocalInputs li;
+            for (auto h : a.local_players().handles) li.inputs[h] = seq[(tick_e + 3 * int(h)) % 8];
+            a.insert_resource(li);
+        })
+        .rollback_resource_with_copy<FrameCount>(FrameCount{0})
+        .rollback_component_with_copy<Velocity>()
+        .rollback_component_with_clone<Transform>()
+        .checksum_resource_with_hash<FrameCount>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_BOX_MOVE, {1, 0}, {}});
+    app.add_systems(GgrsSchedule{}, ResourceSystem{[](App& a) { a.resource<FrameCount>().frame += 1; }});  // increase_frame_system
+    bool mismatch = false;
+    app.add_observer([&](const SyncTestMismatch&) { mismatch = true; });
+    std::vector<Transform> t0(2);
+    for (int h = 0; h < 2; ++h) {
+        float rot = float(h) / 2.0f * 2.0f * 3.14159265358979323846f, r = 5.0f / 4.0f;
+        t0[h] = Transform{{r * std::cos(rot), 0.1f, r * std::sin(rot)}, {0, 0, 0, 1}, {1, 1, 1}};
+    }
+    app.write<Transform>(app.spawn(2), t0);
+
+    // the oracle, driven with the same request vectors
+    oracle::World w;
+    uint32_t ov = w.add_column("Velocity", 12), ot = w.add_column("Transform", 40);
+    uint32_t zero = 0;
+    uint32_t fc = w.add_resource("FrameCount", &zero, 4, true);
+    w.systems.push_back({BGR_SYS_BOX_MOVE, {ot, ov}, {}});
+    w.systems.push_back({oracle::ORC_SYS_RESOURCE_U32_ADD, {}, {fc}});
+    w.spawn(2);
+    std::memcpy(w.data[ot].data(), t0.data(), 80);
+    ggrs::SyncTestSession osess(2, 8, 9, 2);
+    bool all_equal = true;
+    size_t n_cs = 0;
+    for (int i = 0; i < 100; ++i) {
+        app.step();
+        for (size_t h = 0; h < 2; ++h) osess.add_local_input(h, seq[(tick_e + 3 * int(h)) % 8]);
+        ++tick_e;
+        std::vector<ggrs::GgrsRequest> reqs; ggrs::MismatchedChecksum err;
+        if (!osess.advance_frame(reqs, err)) { mismatch = true; break; }
+        std::vector<bgr_request> br(reqs.size());
+        for (size_t k = 0; k < reqs.size(); ++k) {
+            std::memset(&br[k], 0, sizeof(bgr_request));
+            br[k].kind = uint32_t(reqs[k].kind); br[k].frame = reqs[k].frame; br[k].n_players = uint32_t(reqs[k].inputs.size());
+            for (size_t p = 0; p < reqs[k].inputs.size(); ++p) br[k].inputs[p] = reqs[k].inputs[p].first;
+        }
+        bgr_session_info info{BGR_SESSION_SYNCTEST, 9, 8, 0};
+        std::vector<bgr_checksum> ocs;
+        w.handle_requests(info, br.data(), uint32_t(br.size()), ocs);
+        for (auto& c : ocs) osess.save_cell(c.frame, (static_cast<unsigned __int128>(c.hi) << 64) | c.lo);
+        const auto& ecs = app.last_checksums();
+        all_equal = all_equal && ecs.size() == ocs.size();
+        for (size_t k = 0; k < ocs.size() && k < ecs.size(); ++k, ++n_cs)
+            all_equal = all_equal && ecs[k].lo == ocs[k].lo && ecs[k].frame == ocs[k].frame;
+    }
+    EXPECT(!mismatch);
+    EXPECT(all_equal && n_cs > 400);  // FrameCount part ^ entity part: bit-identical
+    EXPECT(app.resource<FrameCount>().frame == 100);
+    auto te = app.read<Transform>(0, 2);
+    auto ve = app.read<Velocity>(0, 2);
+    bool within = true, moved = false;
+    for (int h = 0; h < 2; ++h) {
+        size_t row = size_t(w.find_row(uint64_t(h)));
+        const float* to = reinterpret_cast<const float*>(&w.data[ot][row * 40]);
+        const float* vo = reinterpret_cast<const float*>(&w.data[ov][row * 12]);
+        for (int k = 0; k < 3; ++k) {
+            within = within && std::fabs(te[h].translation[k] - to[k]) <= 1e-5f * std::max(1.0f, std::fabs(to[k]));
+            within = within && std::fabs(ve[h].v[k] - vo[k]) <= 1e-5f * std::max(1.0f, std::fabs(vo[k]));
+            moved = moved || ve[h].v[k] != 0.0f;
+        }
+    }
+    EXPECT(within);  // powf: the north_star's stated f32 tolerance
+    EXPECT(moved);
+}
+
 int main(int argc, char** argv) {
     if (argc > 1 && std::string(argv[1]) == "--no-gpu") {
         // the library must refuse loudly (no CPU fallback) when no device is usable
@@ -176,6 +261,7 @@ int main(int argc, char** argv) {
         synctest_prunes_confirmed_snapshots();
         rollback_missing_frame_panics();
         particles_stress_synctest();
+        box_game_synctest_c1();
     } catch (const std::exception& e) {
         std::printf("unexpected exception: %s\n", e.what());
         return 2;
