@@ -132,6 +132,7 @@ class App:
         self.ticks = 0
         # host-side resources (rollback_resource_with_copy / checksum_resource_with_hash)
         self.resources: Dict[str, bytearray] = {}
+        self._res_registered: List[str] = []
         self._res_checksummed: List[str] = []
         self._res_systems: List[Callable] = []
         self._res_store: Dict[int, Dict[str, bytes]] = {}
@@ -188,8 +189,12 @@ class App:
     def checksum_component_with_hash(self, column: int) -> "App":
         return self.checksum_component(column, 0, self.world.elem_bytes[column])
 
-    def rollback_resource_with_copy(self, type_name: str, initial: bytes) -> "App":  # rollback_app.rs:171-176
-        self.resources[type_name] = bytearray(initial)
+    def rollback_resource_with_copy(self, type_name: str, initial: Optional[bytes] = None) -> "App":  # rollback_app.rs:171-176
+        """``initial=None`` registers a resource that is absent for now: the snapshot stores ``None`` for it
+        (GgrsResourceSnapshots = GgrsSnapshots<R, Option<As>>, mod.rs:87) and a Load re-inserts / removes it."""
+        self._res_registered.append(type_name)
+        if initial is not None:
+            self.resources[type_name] = bytearray(initial)
         return self
 
     rollback_resource_with_clone = rollback_resource_with_copy
@@ -266,7 +271,7 @@ class App:
     def handle_requests(self, requests: Sequence[Request]) -> None:
         inner = self._session.inner
         checksums = self.world.handle_requests(inner.info(), requests)
-        if self.resources:
+        if self._res_registered:
             checksums = self._handle_resource_requests(requests, checksums)
         # cell.save(frame, None, checksum) (:236)
         for frame, cs in checksums:
@@ -281,23 +286,30 @@ class App:
         lib = capi.load_library()
         out, k = [], 0
         for r in requests:
-            if r.kind == SAVE:
-                self._res_store[self._res_frame] = {n: bytes(v) for n, v in self.resources.items()}
+            if r.kind == SAVE:  # resource_snapshot.rs:65-73: Some(clone) or None
+                self._res_store[self._res_frame] = {n: (bytes(self.resources[n]) if n in self.resources else None)
+                                                    for n in self._res_registered}
                 part = 0
-                for name in self._res_checksummed:
+                for name in self._res_checksummed:  # resource_checksum.rs:63-82 (the resource must exist)
                     b = bytes(self.resources[name])
                     part ^= lib.bgr_seahash(C.create_string_buffer(b, len(b)), len(b))
                 frame, cs = checksums[k]
                 out.append((frame, cs ^ part))
                 k += 1
-            elif r.kind == LOAD:
+            elif r.kind == LOAD:  # resource_snapshot.rs:77-93: update / insert / remove
                 self._res_frame = r.frame
                 for n, v in self._res_store[r.frame].items():
-                    self.resources[n] = bytearray(v)
+                    if v is None:
+                        self.resources.pop(n, None)
+                    else:
+                        self.resources[n] = bytearray(v)
             else:
                 self._res_frame += 1
                 for fn in self._res_systems:
-                    fn(self.resources)
+                    if fn.__code__.co_argcount >= 2:
+                        fn(self.resources, self._res_frame)   # (resources, RollbackFrameCount)
+                    else:
+                        fn(self.resources)
         alive = set(self.world.snapshot_frames())
         self._res_store = {f: v for f, v in self._res_store.items() if f in alive}
         return out

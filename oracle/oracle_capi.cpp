@@ -72,6 +72,11 @@ ORC_API void orc_ordered_free(RollbackOrdered* o) { delete o; }
 ORC_API void orc_ordered_push(RollbackOrdered* o, uint64_t id) { o->push(id); }
 ORC_API int orc_ordered_order(RollbackOrdered* o, uint64_t id, uint64_t* out) { return guarded([&] { *out = o->order_of(id); }); }
 ORC_API uint64_t orc_ordered_len(RollbackOrdered* o) { return o->len(); }
+ORC_API uint32_t orc_ordered_iter_sorted(RollbackOrdered* o, uint64_t* out, uint32_t cap) {
+    uint32_t n = 0;
+    for (uint64_t id : o->sorted) { if (n < cap) out[n] = id; ++n; }
+    return n;
+}
 
 // ---- World ------------------------------------------------------------------------------
 ORC_API World* orc_world_new(uint32_t fps, uint64_t order_base, uint32_t save_threads) {

@@ -59,6 +59,7 @@ def load_oracle() -> C.CDLL:
         "orc_ordered_push": (None, [vp, u64]),
         "orc_ordered_order": (C.c_int, [vp, u64, u64p]),
         "orc_ordered_len": (u64, [vp]),
+        "orc_ordered_iter_sorted": (u32, [vp, u64p, u32]),
         "orc_world_new": (vp, [u32, u64, u32]),
         "orc_world_free": (None, [vp]),
         "orc_rollback_component": (C.c_int, [vp, C.c_char_p, u32, u32p]),
