@@ -511,10 +511,13 @@ def run_reference(args):
         return
     n, d, maxp = WORKLOADS[args.workload]
     K, W = args.steps, args.warmup
-    # bound the whole run to a few minutes: ~2.8 s per 1M-entity tick on 8 cores
-    budget_s = 150.0
-    est = 3.0 * (K + W) + 6.0
-    e = n if est <= budget_s else max(50_000, int(n * budget_s / est) // 1000 * 1000)
+    # bound the whole run to a few minutes: the port needs ~2.6 s per 1M-entity rollback tick with 8 threads and
+    # about linear time in the entity count (super-linear in reality — hash maps fall out of cache — so a smaller
+    # sample flatters the CPU, never the GPU); d+1 plain ticks fill the ring before the first rollback tick
+    budget_s = 120.0
+    per_tick_1m = 2.6 * (n / 1_000_000)
+    est = per_tick_1m * (K + W + d + 1)
+    e = n if est <= budget_s else max(10_000, int(n * budget_s / est) // 1000 * 1000)
     r = run_cpu_sample(n, d, maxp, rollback_ticks=K, entities=e, warm_ticks=W)
     line = {
         "impl": "reference",
