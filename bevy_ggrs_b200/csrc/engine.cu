@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <array>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -92,10 +93,10 @@ constexpr uint32_t kMaxSpawnVals = 1u << 16;  // particles spawned by one reques
 
 // Every host-side resource handle_requests / the schedules mutate.  A request vector is compiled
 // against a copy and committed only if the whole vector is valid.
-struct HostState {
+struct HostState {  // trivially copyable: copying it per call must not allocate
     SlotRing ring;
-    std::vector<uint32_t> slot_rows;        // RollbackOrdered::len() captured by each snapshot (mod.rs:339)
-    std::vector<uint64_t> slot_elapsed_ns;  // Time<GgrsTime> captured by each snapshot (time.rs:100)
+    std::array<uint32_t, SlotRing::kMaxSlots> slot_rows{};        // RollbackOrdered::len() captured by each snapshot (mod.rs:339)
+    std::array<uint64_t, SlotRing::kMaxSlots> slot_elapsed_ns{};  // Time<GgrsTime> captured by each snapshot (time.rs:100)
     int32_t frame_count = 0;                // RollbackFrameCount (mod.rs:66-67)
     int32_t confirmed = 0;                  // ConfirmedFrameCount (mod.rs:76-77), init_resource -> 0
     bool has_maxpred = false;               // MaxPredictionWindow inserted? (lib.rs:116-117)
@@ -104,10 +105,10 @@ struct HostState {
     uint32_t n_rows = 0;                    // RollbackOrdered::len()
     uint32_t call_count = 0;                // un-rolled-back counter of BGR_SYS_U32_STORE_CALL_COUNT
     ParticleRng rng;                        // ParticleRng resource (particles.rs:128)
-    std::vector<ParticleRng> slot_rng;      // its per-snapshot clones
+    std::array<ParticleRng, SlotRing::kMaxSlots> slot_rng{};  // its per-snapshot clones
     // content versions of the passive planes (BGR_CFG_SKIP_UNCHANGED_PLANES): equal ids <=> identical bytes
     uint64_t live_passive_ver = 1, ver_counter = 1;
-    std::vector<uint64_t> slot_passive_ver;  // 0 = never written
+    std::array<uint64_t, SlotRing::kMaxSlots> slot_passive_ver{};  // 0 = never written
 };
 
 struct Pending {
@@ -600,7 +601,7 @@ int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs,
     if (rc != BGR_OK) return rc;
     CUDA_TRY(cudaEventRecord(e->ev[buf], e->stream));
     e->last_fused = fused;
-    e->st = std::move(s);
+    e->st = s;
     Pending pd;
     pd.buf = buf; pd.n_saves = pg.n_saves; pd.seq = e->seq;
     std::memcpy(pd.frames, pg.save_frames, sizeof(int32_t) * pg.n_saves);
@@ -959,10 +960,9 @@ BGR_API int bgr_build(bgr_engine* e) {
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
     }
     e->st.ring.reset(e->cfg.max_depth);
-    e->st.slot_rows.assign(e->cfg.max_depth, 0);
-    e->st.slot_elapsed_ns.assign(e->cfg.max_depth, 0);
-    e->st.slot_rng.assign(e->cfg.max_depth, ParticleRng());
-    e->st.slot_passive_ver.assign(e->cfg.max_depth, 0);
+    e->st.slot_rows.fill(0);
+    e->st.slot_elapsed_ns.fill(0);
+    e->st.slot_passive_ver.fill(0);
     if (e->spawn_sys >= 0)
         for (int i = 0; i < bgr_engine::kBufs; ++i) {
             CUDA_TRY(cudaHostAlloc(&e->h_spawn[i], sizeof(float2) * kMaxSpawnVals, cudaHostAllocMapped));

@@ -14,29 +14,33 @@
 // the same frame into each of them, every LoadWorld rolls each back to the same frame), so one
 // ring serves every registered column.
 #pragma once
+#include <array>
 #include <cstdint>
 #include <string>
 #include <vector>
 
 namespace bgr {
 
+// Fixed capacity (kMaxSlots), trivially copyable: handle_requests validates a request vector against a COPY of
+// the host state, so copying the ring must not allocate on the hot path.
 class SlotRing {
 public:
     static constexpr uint32_t kNoSlot = 0xFFFFFFFFu;
+    static constexpr uint32_t kMaxSlots = 64;
 
     explicit SlotRing(uint32_t n_slots = 0) { reset(n_slots); }
 
     void reset(uint32_t n_slots) {
-        n_slots_ = n_slots;
-        entries_.clear();
-        free_.clear();
-        for (uint32_t s = n_slots; s-- > 0;) free_.push_back(s);
+        n_slots_ = n_slots > kMaxSlots ? kMaxSlots : n_slots;
+        entries_.n = 0;
+        free_.n = 0;
+        for (uint32_t s = n_slots_; s-- > 0;) free_.push_back(s);
         depth_ = 60;  // DEFAULT_FPS until sync_depth runs (mod.rs:112)
     }
 
     uint32_t depth() const { return depth_; }
     void set_depth(uint32_t d) { depth_ = d; }  // mod.rs:120-135 (no eviction until the next push)
-    uint32_t len() const { return uint32_t(entries_.size()); }
+    uint32_t len() const { return entries_.size(); }
     uint32_t n_slots() const { return n_slots_; }
 
     // Returns the slot that now holds `frame`, or kNoSlot if more than n_slots snapshots would
@@ -83,7 +87,7 @@ public:
     }
 
     bool peek(int32_t frame, uint32_t* slot) const {
-        for (size_t i = entries_.size(); i-- > 0;)  // newest first, like the reference's iter()
+        for (uint32_t i = entries_.size(); i-- > 0;)  // newest first, like the reference's iter()
             if (entries_[i].frame == frame) { *slot = entries_[i].slot; return true; }
         return false;
     }
@@ -91,7 +95,7 @@ public:
     // newest first
     void frames(std::vector<int32_t>* out) const {
         out->clear();
-        for (size_t i = entries_.size(); i-- > 0;) out->push_back(entries_[i].frame);
+        for (uint32_t i = entries_.size(); i-- > 0;) out->push_back(entries_[i].frame);
     }
 
 private:
@@ -106,11 +110,28 @@ private:
         bool after_wrapped = incoming >= stored && wrapped;
         return !(after || after_wrapped);
     }
+    // tiny inline vector: no heap, trivially copyable
+    template <class T>
+    struct Small {
+        std::array<T, kMaxSlots> a;
+        uint32_t n = 0;
+        bool empty() const { return n == 0; }
+        uint32_t size() const { return n; }
+        T& back() { return a[n - 1]; }
+        const T& back() const { return a[n - 1]; }
+        T& front() { return a[0]; }
+        const T& front() const { return a[0]; }
+        T& operator[](uint32_t i) { return a[i]; }
+        const T& operator[](uint32_t i) const { return a[i]; }
+        void push_back(const T& v) { a[n++] = v; }
+        void pop_back() { --n; }
+        void pop_front() { for (uint32_t i = 1; i < n; ++i) a[i - 1] = a[i]; --n; }
+    };
     void release_back() { free_.push_back(entries_.back().slot); entries_.pop_back(); }
-    void release_front() { free_.push_back(entries_.front().slot); entries_.erase(entries_.begin()); }
+    void release_front() { free_.push_back(entries_.front().slot); entries_.pop_front(); }
 
-    std::vector<Entry> entries_;  // oldest first; depth is small (<= 64), vector ops are O(depth)
-    std::vector<uint32_t> free_;
+    Small<Entry> entries_;  // oldest first; depth is small (<= 64), O(depth) per operation
+    Small<uint32_t> free_;
     uint32_t n_slots_ = 0;
     uint32_t depth_ = 60;
 };
