@@ -7,6 +7,7 @@
 // generic kernel per request ("stepwise" path).  No CPU compute path exists: without a GPU every
 // entry point that touches state returns BGR_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>  // header-only; a no-op unless a profiler is attached
 
 #include <algorithm>
 #include <array>
@@ -584,7 +585,14 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
     return BGR_OK;
 }
 
+// the reference's tracing span (schedule_systems.rs:171 `info_span!("ggrs", name = "HandleRequests")`) as an NVTX range
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+
 int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs, uint32_t n) {
+    NvtxRange span("HandleRequests");
     if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
     if (!e->built) return fail(BGR_ERR_STATE, "bgr_build has not been called");
     if (e->pending.size() >= size_t(bgr_engine::kBufs)) return fail(BGR_ERR_STATE, "too many un-collected submits");

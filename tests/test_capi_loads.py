@@ -63,3 +63,20 @@ def test_no_gpu_fails_loudly_no_cpu_fallback():
         Engine(max_entities=16)
     assert ei.value.status == capi.BGR_ERR_CUDA
     assert "no CPU fallback" in str(ei.value)
+
+
+def test_rust_ffi_source_declares_every_engine_symbol():
+    """rust_shim/ is source only (no rustc here), but it must not rot: every engine entry point of the header
+    (the bgr_ring_* host-test hooks aside) has an `extern "C"` declaration and the #[repr(C)] structs keep the
+    field order of the C structs."""
+    hdr = open(os.path.join(ROOT, "include", "bevy_ggrs_b200.h")).read()
+    rs = open(os.path.join(ROOT, "rust_shim", "bevy_ggrs_b200_sys", "src", "lib.rs")).read()
+    declared = set(re.findall(r"BGR_API\s+[\w\s\*]+?\b(bgr_\w+)\s*\(", hdr))
+    have = set(re.findall(r"pub fn (bgr_\w+)", rs))
+    assert {d for d in declared if not d.startswith("bgr_ring_")} <= have
+    for struct, fields in (("bgr_request", ["kind", "frame", "n_players", "inputs", "status"]),
+                           ("bgr_config", ["abi_version", "device", "max_entities", "max_depth", "fps", "flags", "order_base", "stream"]),
+                           ("bgr_checksum", ["frame", "has_checksum", "lo", "hi"])):
+        body = rs[rs.index("pub struct " + struct):]
+        body = body[:body.index("}")]
+        assert re.findall(r"pub (\w+):", body) == fields
