@@ -198,12 +198,16 @@ def run_ours(args):
         else:
             history.extend(eng.collect())
 
+    # un-collected submits kept queued on the GPU: 2 hide the host loop; the sharded loop keeps 6 so that the
+    # batched all_gather (every ~32 ticks) never drains the queue
+    depth = 6 if sharded else 2
+
     def run_pipelined(tick_list):
         inflight = 0
         for arr, nreq, _, info, _ in tick_list:
             eng.submit_prepared(info, arr, nreq)
             inflight += 1
-            if inflight > 2:
+            if inflight > depth:
                 collect_one()
                 inflight -= 1
         while inflight:

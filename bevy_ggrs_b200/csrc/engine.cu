@@ -154,15 +154,15 @@ struct bgr_engine {
 
     HostState st;
 
-    static constexpr int kBufs = 4;
+    static constexpr int kBufs = 8;  // result / spawn buffers = max un-collected submits
     unsigned long long* d_accum = nullptr;
     unsigned int* d_ticket = nullptr;
-    float2* h_spawn[kBufs] = {nullptr, nullptr, nullptr, nullptr};  // host-mapped (vx, vy) of spawned particles
-    float2* d_spawn[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    float2* h_spawn[kBufs] = {};  // host-mapped (vx, vy) of spawned particles
+    float2* d_spawn[kBufs] = {};
     int spawn_sys = -1;             // index of BGR_SYS_PARTICLES_SPAWN in `systems`, or -1
-    unsigned long long* h_out[kBufs] = {nullptr, nullptr, nullptr, nullptr};
-    unsigned long long* d_out[kBufs] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    unsigned long long* h_out[kBufs] = {};
+    unsigned long long* d_out[kBufs] = {};
+    cudaEvent_t ev[kBufs] = {};
     std::deque<Pending> pending;
     uint32_t next_buf = 0;
     std::vector<bgr_partial> last_partials;

@@ -229,7 +229,7 @@ BGR_API int bgr_handle_requests(bgr_engine* e, const bgr_session_info* session,
                                 const bgr_request* requests, uint32_t n_requests,
                                 bgr_checksum* checksums_out, uint32_t checksums_cap, uint32_t* n_checksums_out);
 /* Asynchronous pair: submit enqueues on the engine stream and returns; collect waits and
- * returns the checksums of the oldest un-collected submit.  At most 2 submits in flight. */
+ * returns the checksums of the oldest un-collected submit.  At most 8 submits may be un-collected. */
 BGR_API int bgr_submit_requests(bgr_engine* e, const bgr_session_info* session,
                                 const bgr_request* requests, uint32_t n_requests);
 BGR_API int bgr_collect(bgr_engine* e, bgr_checksum* checksums_out, uint32_t checksums_cap,
