@@ -114,6 +114,7 @@ struct HostState {  // trivially copyable: copying it per call must not allocate
 
 struct Pending {
     uint32_t buf = 0;
+    uint32_t chains = 1;            // result blocks to wait for
     unsigned long long seq = 0;
     uint32_t n_saves = 0;
     int32_t frames[kMaxSaves];
@@ -155,6 +156,19 @@ struct bgr_engine {
     HostState st;
 
     static constexpr int kBufs = 8;  // result / spawn buffers = max un-collected submits
+    static constexpr int kMaxChains = 8;
+    // Chains: the entity range is cut into n_chains contiguous tile ranges, each with its own stream, accumulators
+    // and result block.  Entities are independent, so chain A's kernel of tick i+1 only depends on chain A's kernel
+    // of tick i: with back-to-back submits the ramp / tail of one chain's kernel overlaps the other chain's kernel
+    // (the same entity-range sharding as across GPUs, inside one GPU; partials are XOR-folded on the host).
+    int n_chains = 1;
+    cudaStream_t chain_stream[kMaxChains] = {};
+    cudaEvent_t chain_ev[kMaxChains] = {};
+    cudaEvent_t main_ev = nullptr;
+    bool main_dirty = false;        // the main stream has un-synchronised work the chains must wait for
+    uint32_t last_total_tiles = 0, last_chains = 0;  // tile partition of the previous chained launch
+    unsigned long long* d_accum_c[kMaxChains] = {};
+    unsigned int* d_ticket_c[kMaxChains] = {};
     unsigned long long* d_accum = nullptr;
     unsigned int* d_ticket = nullptr;
     float2* h_spawn[kBufs] = {};  // host-mapped (vx, vy) of spawned particles
@@ -350,7 +364,7 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
 // launch: fused bundle kernel
 // ---------------------------------------------------------------------------------------------
 template <int VEC, bool STATIC_CK, int MINB>
-int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int mi) {
+int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int mi, cudaStream_t stream) {
     auto kern = k_particles_program<VEC, STATIC_CK, MINB>;
     constexpr int BLOCK = kTileRows / VEC;
     const size_t smem = (pp.flags & PF_PASSIVE_TMA) ? size_t(2) * pp.passive_bytes : 0;
@@ -362,9 +376,9 @@ int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int
     }
     int bps = e->occ_cache[vi][si][mi];
     if (e->tune_bps > 0) bps = std::min(e->tune_bps, bps);
-    uint32_t grid = std::max(1u, std::min(pp.n_tiles, uint32_t(e->num_sms * bps)));
+    uint32_t grid = std::max(1u, std::min(pp.n_tiles - pp.tile_begin, uint32_t(e->num_sms * bps)));
     cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(grid); lc.blockDim = dim3(BLOCK); lc.dynamicSmemBytes = smem; lc.stream = e->stream;
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(BLOCK); lc.dynamicSmemBytes = smem; lc.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = e->tune_pdl ? 1 : 0;
@@ -375,17 +389,16 @@ int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int
     return BGR_OK;
 }
 
-int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
+int launch_fused_variant(bgr_engine* e, const ProgramParams& pp, cudaStream_t stream);
+
+int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_out) {
     ProgramParams pp;
     std::memset(&pp, 0, sizeof pp);
     pp.seq = e->seq;
     pp.arena = e->arena;
     pp.order_base = e->cfg.order_base;
-    pp.accum = e->d_accum;
-    pp.out = e->d_out[buf];
-    pp.ticket = e->d_ticket;
     pp.words = e->words; pp.tile_bytes = e->tile_bytes;
-    pp.n_tiles = std::max(1u, e->tiles_for(pg.max_rows));  // at least one tile so the result block is published
+    const uint32_t total_tiles = std::max(1u, e->tiles_for(pg.max_rows));  // at least one tile so a result block is published
     pp.n_ops = pg.n_ops; pp.n_saves = pg.n_saves;
     pp.live_rows = pg.live_rows;
     pp.flags = 0;
@@ -418,6 +431,38 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
         pp.passive_template[i] = (uint32_t(e->passive[i]) >= ct.first_plane && tw >= 6 && tw <= 9) ? 0x3f800000u : 0u;
     }
     std::memcpy(pp.ops, pg.ops, sizeof(Op) * pg.n_ops);
+
+    // one launch per chain: contiguous tile ranges, own stream / accumulators / result block
+    const uint32_t chains = std::max(1u, std::min(uint32_t(e->n_chains), total_tiles));
+    *chains_out = chains;
+    // Chain c of this launch follows chain c of the previous one in stream order, which is all the ordering the data
+    // needs while both cover the same tiles.  A changed partition (rows spawned, first launch), stepwise work, or a
+    // caller-owned stream (whose earlier work we cannot see) makes every chain wait for everything before it.
+    if (chains != e->last_chains || total_tiles != e->last_total_tiles || !e->own_stream) e->main_dirty = true;
+    e->last_chains = chains; e->last_total_tiles = total_tiles;
+    if (chains > 1 && e->main_dirty) {
+        CUDA_TRY(cudaEventRecord(e->main_ev, e->stream));
+        for (uint32_t c = 0; c < chains; ++c) CUDA_TRY(cudaStreamWaitEvent(e->chain_stream[c], e->main_ev, 0));
+        e->main_dirty = false;
+    }
+    for (uint32_t c = 0; c < chains; ++c) {
+        pp.tile_begin = uint32_t(uint64_t(total_tiles) * c / chains);
+        pp.n_tiles = uint32_t(uint64_t(total_tiles) * (c + 1) / chains);
+        pp.accum = e->d_accum_c[c];
+        pp.ticket = e->d_ticket_c[c];
+        pp.out = e->d_out[buf] + size_t(c) * kResultStride;
+        cudaStream_t stream = chains > 1 ? e->chain_stream[c] : e->stream;
+        int rc = launch_fused_variant(e, pp, stream);
+        if (rc != BGR_OK) return rc;
+        if (chains > 1) {  // everything later on the main stream (and external timing events) is ordered after the chains
+            CUDA_TRY(cudaEventRecord(e->chain_ev[c], stream));
+            CUDA_TRY(cudaStreamWaitEvent(e->stream, e->chain_ev[c], 0));
+        }
+    }
+    return BGR_OK;
+}
+
+int launch_fused_variant(bgr_engine* e, const ProgramParams& pp, cudaStream_t stream) {
     const int v = e->tune_vec;
     const bool st = e->bundle_static_ck;
     const int mb = e->tune_minb >= 8 ? 2 : (e->tune_minb >= 2 ? 1 : 0);  // launch-bounds tier: 1024 / 768 / unconstrained threads per SM
@@ -425,12 +470,12 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf) {
     if (v == VEC) {                                                                                        \
         constexpr int kHi = (1024 / int(kTileRows / VEC)) > 32 ? 32 : (1024 / int(kTileRows / VEC));        \
         constexpr int kMid = (768 / int(kTileRows / VEC)) < 1 ? 1 : (768 / int(kTileRows / VEC));           \
-        if (st && mb == 2) return launch_particles<VEC, true, kHi>(e, pp, VI, 1, 2);                       \
-        if (st && mb == 1) return launch_particles<VEC, true, kMid>(e, pp, VI, 1, 1);                      \
-        if (st) return launch_particles<VEC, true, 1>(e, pp, VI, 1, 0);                                    \
-        if (mb == 2) return launch_particles<VEC, false, kHi>(e, pp, VI, 0, 2);                            \
-        if (mb == 1) return launch_particles<VEC, false, kMid>(e, pp, VI, 0, 1);                           \
-        return launch_particles<VEC, false, 1>(e, pp, VI, 0, 0);                                           \
+        if (st && mb == 2) return launch_particles<VEC, true, kHi>(e, pp, VI, 1, 2, stream);                       \
+        if (st && mb == 1) return launch_particles<VEC, true, kMid>(e, pp, VI, 1, 1, stream);                      \
+        if (st) return launch_particles<VEC, true, 1>(e, pp, VI, 1, 0, stream);                                    \
+        if (mb == 2) return launch_particles<VEC, false, kHi>(e, pp, VI, 0, 2, stream);                            \
+        if (mb == 1) return launch_particles<VEC, false, kMid>(e, pp, VI, 0, 1, stream);                           \
+        return launch_particles<VEC, false, 1>(e, pp, VI, 0, 0, stream);                                           \
     }
     BGR_LAUNCH(1, 0)
     BGR_LAUNCH(4, 2)
@@ -474,6 +519,7 @@ int launch_tma(bgr_engine* e, const uint8_t* src, uint8_t* dst, uint32_t n_rows_
 // launch: stepwise path (generic schemas / systems)
 // ---------------------------------------------------------------------------------------------
 int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
+    e->main_dirty = true;
     uint32_t live_rows = pg.live_rows;
     uint8_t* live = e->image(0);
     for (uint32_t i = 0; i < pg.n_ops; ++i) {
@@ -605,13 +651,14 @@ int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs,
     if (!pg.spawn_vals.empty()) std::memcpy(e->h_spawn[buf], pg.spawn_vals.data(), pg.spawn_vals.size() * sizeof(float2));
     e->seq += 1;
     bool fused = e->bundle_particles && !(e->cfg.flags & BGR_CFG_FORCE_STEPWISE);
-    rc = fused ? run_fused(e, pg, buf) : run_stepwise(e, pg, buf);
+    uint32_t chains = 1;
+    rc = fused ? run_fused(e, pg, buf, &chains) : run_stepwise(e, pg, buf);
     if (rc != BGR_OK) return rc;
     CUDA_TRY(cudaEventRecord(e->ev[buf], e->stream));
     e->last_fused = fused;
     e->st = s;
     Pending pd;
-    pd.buf = buf; pd.n_saves = pg.n_saves; pd.seq = e->seq;
+    pd.buf = buf; pd.n_saves = pg.n_saves; pd.seq = e->seq; pd.chains = chains;
     std::memcpy(pd.frames, pg.save_frames, sizeof(int32_t) * pg.n_saves);
     std::memcpy(pd.totals, pg.save_totals, sizeof(uint32_t) * pg.n_saves);
     e->pending.push_back(pd);
@@ -636,8 +683,9 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
     if (e->pending.empty()) return fail(BGR_ERR_STATE, "nothing to collect");
     Pending pd = e->pending.front();
     e->pending.pop_front();
-    {   // completion: the kernel's last block writes its sequence number after the results (system fence)
-        const volatile unsigned long long* flag = &e->h_out[pd.buf][kSeqIndex];
+    for (uint32_t c = 0; c < pd.chains; ++c) {
+        // completion: each kernel's last block writes its sequence number after the results (system fence)
+        const volatile unsigned long long* flag = &e->h_out[pd.buf][size_t(c) * kResultStride + kSeqIndex];
         bool done = false;
         if (e->tune_poll) {
             for (int spin = 0; spin < 200000; ++spin) {
@@ -645,9 +693,20 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
                 __builtin_ia32_pause();
             }
         }
-        if (!done) CUDA_TRY(cudaEventSynchronize(e->ev[pd.buf]));
+        if (!done) { CUDA_TRY(cudaEventSynchronize(e->ev[pd.buf])); break; }  // the event is ordered after every chain
     }
-    const unsigned long long* r = e->h_out[pd.buf];
+    // fold the chains' result blocks: XOR the column words, sum the live-row counts, OR the flags
+    unsigned long long folded[kMaxSaves * kAccStride];
+    for (uint32_t i = 0; i < pd.n_saves * kAccStride; ++i) {
+        unsigned long long v = 0;
+        const uint32_t w = i % kAccStride;
+        for (uint32_t c = 0; c < pd.chains; ++c) {
+            const unsigned long long x = e->h_out[pd.buf][size_t(c) * kResultStride + i];
+            if (w == 6) v += x; else if (w == 7) v |= x; else v ^= x;
+        }
+        folded[i] = v;
+    }
+    const unsigned long long* r = folded;
     e->last_partials.clear();
     bool nonfinite = false;
     for (uint32_t k = 0; k < pd.n_saves; ++k) {
@@ -828,6 +887,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_poll = env_int("BGR_TUNE_POLL", 1);
     e->tune_dynamic = env_int("BGR_TUNE_DYNAMIC", 1);
     e->tune_pdl = env_int("BGR_TUNE_PDL", 0);
+    e->n_chains = std::max(1, std::min(int(bgr_engine::kMaxChains), env_int("BGR_TUNE_CHAINS", 1)));
     if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 2;
     e->st.confirmed = 0;
     *out = e;
@@ -848,6 +908,11 @@ BGR_API void bgr_engine_destroy(bgr_engine* e) {
     if (e->d_stage) cudaFree(e->d_stage);
     if (e->d_accum) cudaFree(e->d_accum);
     if (e->d_ticket) cudaFree(e->d_ticket);
+    for (int c = 0; c < bgr_engine::kMaxChains; ++c) {
+        if (e->chain_stream[c]) { cudaStreamSynchronize(e->chain_stream[c]); cudaStreamDestroy(e->chain_stream[c]); }
+        if (e->chain_ev[c]) cudaEventDestroy(e->chain_ev[c]);
+    }
+    if (e->main_ev) cudaEventDestroy(e->main_ev);
     if (e->own_stream && e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -957,13 +1022,27 @@ BGR_API int bgr_build(bgr_engine* e) {
     CUDA_TRY(cudaMemsetAsync(e->arena, 0, total, e->stream));
     CUDA_TRY(cudaMalloc(&e->d_kill, e->epad));
     CUDA_TRY(cudaMemsetAsync(e->d_kill, 0, e->epad, e->stream));
-    CUDA_TRY(cudaMalloc(&e->d_accum, sizeof(unsigned long long) * kMaxSaves * kAccStride));
-    CUDA_TRY(cudaMemsetAsync(e->d_accum, 0, sizeof(unsigned long long) * kMaxSaves * kAccStride, e->stream));
-    CUDA_TRY(cudaMalloc(&e->d_ticket, 4 * sizeof(unsigned int)));
-    CUDA_TRY(cudaMemsetAsync(e->d_ticket, 0, 4 * sizeof(unsigned int), e->stream));
+    const size_t acc_bytes = sizeof(unsigned long long) * kMaxSaves * kAccStride;
+    CUDA_TRY(cudaMalloc(&e->d_accum, acc_bytes * bgr_engine::kMaxChains));
+    CUDA_TRY(cudaMemsetAsync(e->d_accum, 0, acc_bytes * bgr_engine::kMaxChains, e->stream));
+    CUDA_TRY(cudaMalloc(&e->d_ticket, 4 * sizeof(unsigned int) * bgr_engine::kMaxChains));
+    CUDA_TRY(cudaMemsetAsync(e->d_ticket, 0, 4 * sizeof(unsigned int) * bgr_engine::kMaxChains, e->stream));
+    for (int c = 0; c < bgr_engine::kMaxChains; ++c) {
+        e->d_accum_c[c] = e->d_accum + size_t(c) * kMaxSaves * kAccStride;
+        e->d_ticket_c[c] = e->d_ticket + 4 * c;
+    }
+    if (e->n_chains > 1) {
+        for (int c = 0; c < e->n_chains; ++c) {
+            CUDA_TRY(cudaStreamCreateWithFlags(&e->chain_stream[c], cudaStreamNonBlocking));
+            CUDA_TRY(cudaEventCreateWithFlags(&e->chain_ev[c], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaEventCreateWithFlags(&e->main_ev, cudaEventDisableTiming));
+        e->main_dirty = true;  // the memsets above
+    }
     for (int i = 0; i < bgr_engine::kBufs; ++i) {
-        CUDA_TRY(cudaHostAlloc(&e->h_out[i], sizeof(unsigned long long) * (kMaxSaves * kAccStride + 8), cudaHostAllocMapped));
-        std::memset(e->h_out[i], 0, sizeof(unsigned long long) * (kMaxSaves * kAccStride + 8));
+        const size_t out_bytes = sizeof(unsigned long long) * kResultStride * bgr_engine::kMaxChains;
+        CUDA_TRY(cudaHostAlloc(&e->h_out[i], out_bytes, cudaHostAllocMapped));
+        std::memset(e->h_out[i], 0, out_bytes);
         CUDA_TRY(cudaHostGetDevicePointer(&e->d_out[i], e->h_out[i], 0));
         CUDA_TRY(cudaEventCreateWithFlags(&e->ev[i], cudaEventDisableTiming));
     }

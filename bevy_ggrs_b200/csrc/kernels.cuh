@@ -41,6 +41,7 @@ constexpr int kMaxPassive = 64;   // word planes that no compiled system touches
 constexpr int kMaxRuns = 8;       // runs of adjacent passive planes (TMA path)
 constexpr int kAccStride = 8;     // u64 per save: [0..5] column xors, [6] active rows, [7] flags
 constexpr int kSeqIndex = kMaxSaves * kAccStride;  // result block word that receives the launch sequence number last
+constexpr int kResultStride = kSeqIndex + 8;         // u64 words per result block (one block per chain per buffer)
 
 __host__ __device__ inline uint32_t tile_bytes_of(uint32_t words) { return kTileRows * (4u * words + 1u); }
 __host__ __device__ inline size_t word_offset(uint32_t words, uint32_t row, uint32_t plane) {
@@ -89,7 +90,8 @@ struct ProgramParams {
     unsigned int* ticket;       // [0] block-completion ticket, [1] dynamic tile counter
     const float2* spawn_vals;   // (vx, vy) of every particle spawned by this program (host-mapped), particles.rs:265
     unsigned long long seq;     // written to out[kSeqIndex] after the results (completion flag the host polls)
-    uint32_t words, tile_bytes, n_tiles, n_ops, n_saves;
+    uint32_t words, tile_bytes, n_ops, n_saves;
+    uint32_t tile_begin, n_tiles;  // this launch covers tiles [tile_begin, n_tiles) (one chain of the entity range)
     uint32_t live_rows, flags;
     uint32_t t_off, v_off, l_off, alive_off;  // byte offsets inside a tile of Transform / Velocity / Ttl word 0 / alive plane
     uint32_t ck_t_slot, ck_v_slot;            // accumulator column of each checksummed type
@@ -258,8 +260,8 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     // iteration 0 runs tile blockIdx.x and never enters the ring
     uint32_t claimed = 0;        // thread 0: tile claimed for iteration it + 1
     uint32_t it = 0;
-    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; ++it) {
-        if (dynamic && tid == 0) claimed = gridDim.x + atomicAdd(&p.ticket[1], 1u);  // published after the loads below
+    for (uint32_t tile = p.tile_begin + blockIdx.x; tile < p.n_tiles; ++it) {
+        if (dynamic && tid == 0) claimed = p.tile_begin + gridDim.x + atomicAdd(&p.ticket[1], 1u);  // published after the loads below
         const size_t tile_off = size_t(tile) * p.tile_bytes;
         const uint32_t row0 = tile * kTileRows + i0;
         const size_t woff = tile_off + size_t(i0) * 4u;  // + plane offset (+ image offset) = address of this thread's words
