@@ -171,7 +171,8 @@ def run_ours(args):
     slot_bytes = eng.slot_bytes()
 
     fill = max(d, maxp) + 2           # ticks until the request vector has its steady-state shape
-    ticks = pregenerate_ticks(fill + W + K + K, d, maxp)
+    K2 = min(K, 500) if world_size == 1 else 0   # ticks of the host-mirror leg (N = 1 only)
+    ticks = pregenerate_ticks(fill + W + K + K + K2, d, maxp)
     history = []
 
     def fold_all(partials_list):
@@ -275,6 +276,30 @@ def run_ours(args):
             e2e_s = float(t.item())
         h2d = sum(C.sizeof(capi.bgr_request) * t[1] + C.sizeof(capi.bgr_session_info) for t in e2e_ticks) / K
         d2h = sum(64 * len(t[4]) + 8 for t in e2e_ticks) / K  # one 8 x u64 result row per SaveGameState + the completion word, pinned host memory
+        # ---------------- e2e with a host mirror: every tick also downloads Transform.translation ----------------
+        # What a host-resident ECS needs back per tick to draw the particles (INTEGRATION.md "mirror"): 12 B/entity
+        # packed on the GPU, copied D2H on a copy stream into page-locked memory while the next tick runs.
+        mirror = None
+        if K2:
+            m_ticks = ticks[fill + W + K + K:]
+            bufs = [eng.host_alloc(n, 12), eng.host_alloc(n, 12)]
+            pending = None
+            barrier()
+            t0 = time.perf_counter()
+            for i, (arr, nreq, _, info, _) in enumerate(m_ticks):
+                eng.submit_prepared(info, arr, nreq)
+                tk = eng.download_begin(0, 0, 12, 0, n, bufs[i & 1])
+                history.extend(eng.collect())
+                if pending is not None:
+                    eng.download_wait(pending)   # the previous tick's mirror is now readable on the host
+                pending = tk
+            eng.download_wait(pending)
+            m_s = time.perf_counter() - t0
+            mirror = {"value": sum(t[2] for t in m_ticks) / m_s, "unit": "rollback frames/s", "ticks": K2,
+                      "d2h_bytes_per_step": 12 * n + sum(64 * len(t[4]) + 8 for t in m_ticks) / K2,
+                      "d2h_gbs": 12 * n * K2 / m_s / 1e9,
+                      "note": "e2e + bgr_download_begin/wait of Transform.translation (12 B/entity) every tick, "
+                              "double-buffered pinned host memory; PCIe-bound when 12 B x entities / tick exceeds the link"}
 
     consistent = check_synctest_consistency(history)
     fused = eng.last_path_fused()
@@ -333,6 +358,8 @@ def run_ours(args):
             line["cpu_baseline"] = cpu
         if cpu_soa:
             line["cpu_baseline_optimised_soa"] = cpu_soa
+        if mirror:
+            line["e2e_host_mirror"] = mirror
         if snap:
             line["snapshot_save_restore"] = snap
         if skip:

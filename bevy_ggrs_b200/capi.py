@@ -91,6 +91,10 @@ PROTOTYPES = {
     "bgr_write_component": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]),
     "bgr_read_component": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]),
     "bgr_read_alive": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "bgr_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "bgr_host_free": (C.c_int, [C.c_void_p]),
+    "bgr_download_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, u32p]),
+    "bgr_download_wait": (C.c_int, [C.c_void_p, C.c_uint32]),
     "bgr_rollback_frame_count": (C.c_int, [C.c_void_p, i32p]),
     "bgr_set_rollback_frame_count": (C.c_int, [C.c_void_p, C.c_int32]),
     "bgr_confirmed_frame_count": (C.c_int, [C.c_void_p, i32p]),

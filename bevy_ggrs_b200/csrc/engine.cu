@@ -152,6 +152,11 @@ struct bgr_engine {
     uint8_t* d_kill = nullptr;
     uint8_t* d_stage = nullptr;  // device staging for ECS column <-> image transposition
     size_t stage_cap = 0;
+    // asynchronous mirror downloads: packed on the main stream, copied D2H on copy_stream
+    struct Download { uint8_t* d_buf = nullptr; size_t cap = 0; cudaEvent_t packed = nullptr, done = nullptr; bool busy = false; };
+    Download dl[BGR_MAX_DOWNLOADS];
+    cudaStream_t copy_stream = nullptr;
+    uint32_t next_dl = 0;
 
     HostState st;
 
@@ -800,6 +805,61 @@ int read_alive_image(bgr_engine* e, uint32_t image_idx, uint32_t first, uint32_t
     return BGR_OK;
 }
 
+int download_begin(bgr_engine* e, uint32_t column, uint32_t off, uint32_t len, uint32_t first, uint32_t count, void* host,
+                   uint32_t* ticket_out) {
+    if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
+    if (!host || !ticket_out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    if (column >= e->cols.size()) return fail(BGR_ERR_INVALID_ARGUMENT, "unknown column");
+    const Column& c = e->cols[column];
+    if ((off & 3u) || (len & 3u) || len == 0 || uint64_t(off) + len > uint64_t(c.words) * 4u)
+        return fail(BGR_ERR_INVALID_ARGUMENT, "field range must be 4-byte aligned and inside the element");
+    if (uint64_t(first) + count > e->st.n_rows) return fail(BGR_ERR_CAPACITY, "row range exceeds the spawned rows");
+    uint32_t slot = BGR_MAX_DOWNLOADS;
+    for (uint32_t k = 0; k < BGR_MAX_DOWNLOADS; ++k) {
+        const uint32_t i = (e->next_dl + k) % BGR_MAX_DOWNLOADS;
+        if (!e->dl[i].busy) { slot = i; break; }
+    }
+    if (slot == BGR_MAX_DOWNLOADS) return fail(BGR_ERR_STATE, "too many downloads in flight (BGR_MAX_DOWNLOADS)");
+    bgr_engine::Download& d = e->dl[slot];
+    const size_t bytes = size_t(count) * len;
+    if (!e->copy_stream) CUDA_TRY(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    if (!d.packed) {
+        CUDA_TRY(cudaEventCreateWithFlags(&d.packed, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.done, cudaEventDisableTiming));
+    }
+    if (bytes > d.cap) {  // grows to the largest request and stays (the slot is idle: its last copy was waited for)
+        if (d.d_buf) CUDA_TRY(cudaFree(d.d_buf));
+        d.d_buf = nullptr; d.cap = 0;
+        CUDA_TRY(cudaMalloc(&d.d_buf, bytes));
+        d.cap = bytes;
+    }
+    if (count) {
+        const uint32_t n_words = len / 4u;
+        const uint32_t grid = e->grid_for(uint32_t(std::min<size_t>(size_t(count) * n_words, 0x7fffffffu)), 256);
+        k_gather_fields<<<grid, 256, 0, e->stream>>>(e->image(0), e->words, c.first_plane + off / 4u, n_words, first, count,
+                                                      reinterpret_cast<uint32_t*>(d.d_buf));
+        e->launches += 1;
+        CUDA_TRY(cudaGetLastError());
+        e->main_dirty = true;  // later chain launches overwrite the live image this kernel reads
+        CUDA_TRY(cudaEventRecord(d.packed, e->stream));
+        CUDA_TRY(cudaStreamWaitEvent(e->copy_stream, d.packed, 0));
+        CUDA_TRY(cudaMemcpyAsync(host, d.d_buf, bytes, cudaMemcpyDeviceToHost, e->copy_stream));
+    }
+    CUDA_TRY(cudaEventRecord(d.done, e->copy_stream));
+    d.busy = true;
+    e->next_dl = (slot + 1) % BGR_MAX_DOWNLOADS;
+    *ticket_out = slot;
+    return BGR_OK;
+}
+
+int download_wait(bgr_engine* e, uint32_t ticket) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    if (ticket >= BGR_MAX_DOWNLOADS || !e->dl[ticket].busy) return fail(BGR_ERR_STATE, "no such download in flight");
+    CUDA_TRY(cudaEventSynchronize(e->dl[ticket].done));
+    e->dl[ticket].busy = false;
+    return BGR_OK;
+}
+
 void detect_bundles(bgr_engine* e) {
     e->bundle_particles = false;
     e->passive.clear();
@@ -908,6 +968,12 @@ BGR_API void bgr_engine_destroy(bgr_engine* e) {
     if (e->d_stage) cudaFree(e->d_stage);
     if (e->d_accum) cudaFree(e->d_accum);
     if (e->d_ticket) cudaFree(e->d_ticket);
+    if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+    for (auto& d : e->dl) {
+        if (d.d_buf) cudaFree(d.d_buf);
+        if (d.packed) cudaEventDestroy(d.packed);
+        if (d.done) cudaEventDestroy(d.done);
+    }
     for (int c = 0; c < bgr_engine::kMaxChains; ++c) {
         if (e->chain_stream[c]) { cudaStreamSynchronize(e->chain_stream[c]); cudaStreamDestroy(e->chain_stream[c]); }
         if (e->chain_ev[c]) cudaEventDestroy(e->chain_ev[c]);
@@ -1153,6 +1219,22 @@ BGR_API int bgr_read_component(bgr_engine* e, uint32_t column, uint32_t first_ro
     if (!host_dst && count) return fail(BGR_ERR_INVALID_ARGUMENT, "null host buffer");
     return transfer_column(e, 0, column, first_row, count, host_dst, stride, false);
 }
+
+BGR_API int bgr_host_alloc(size_t bytes, void** out) {
+    if (!out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    CUDA_TRY(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable));
+    return BGR_OK;
+}
+BGR_API int bgr_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return BGR_OK;
+}
+BGR_API int bgr_download_begin(bgr_engine* e, uint32_t column, uint32_t byte_offset, uint32_t byte_len, uint32_t first_row,
+                               uint32_t count, void* host_dst, uint32_t* ticket_out) {
+    return download_begin(e, column, byte_offset, byte_len, first_row, count, host_dst, ticket_out);
+}
+BGR_API int bgr_download_wait(bgr_engine* e, uint32_t ticket) { return download_wait(e, ticket); }
 
 BGR_API int bgr_read_alive(bgr_engine* e, uint32_t first_row, uint32_t count, uint8_t* host_dst) {
     if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");

@@ -617,6 +617,17 @@ __global__ void __launch_bounds__(256) k_gather_column(const uint8_t* __restrict
         for (uint32_t b = 0; b < nb; ++b) d[b] = uint8_t(v >> (8 * b));
     }
 }
+// words [first_word, first_word + n_words) of a column for rows [first_row, first_row+count), packed densely: consecutive
+// threads write consecutive words of the output (coalesced stores; the plane reads are n_words interleaved streams)
+__global__ void __launch_bounds__(256) k_gather_fields(const uint8_t* __restrict__ img, uint32_t words, uint32_t first_word,
+                                                       uint32_t n_words, uint32_t first_row, uint32_t count,
+                                                       uint32_t* __restrict__ out) {
+    const size_t n = size_t(count) * n_words;
+    for (size_t t = size_t(blockIdx.x) * blockDim.x + threadIdx.x; t < n; t += size_t(gridDim.x) * blockDim.x) {
+        const uint32_t i = uint32_t(t / n_words), w = uint32_t(t % n_words);
+        out[t] = *reinterpret_cast<const uint32_t*>(img + word_offset(words, first_row + i, first_word + w));
+    }
+}
 // alive bytes of rows [first, first+count): gather to a dense array / set to a value
 __global__ void __launch_bounds__(256) k_gather_alive(const uint8_t* __restrict__ img, uint32_t words, uint32_t first_row,
                                                       uint32_t count, uint32_t n_rows, uint8_t* out) {

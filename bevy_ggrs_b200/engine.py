@@ -26,6 +26,7 @@ class Engine:
         self._h = handle
         self.elem_bytes: List[int] = []
         self.max_entities = max_entities
+        self._pinned: List[C.c_void_p] = []
 
     # ---- plumbing ----
     def _check(self, status: int) -> None:
@@ -34,8 +35,11 @@ class Engine:
 
     def close(self) -> None:
         if self._h is not None:
-            self._lib.bgr_engine_destroy(self._h)
+            self._lib.bgr_engine_destroy(self._h)  # waits for every download in flight
             self._h = None
+            for p in self._pinned:
+                self._lib.bgr_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -98,6 +102,25 @@ class Engine:
         out = np.zeros(count, dtype=np.uint8)
         self._check(self._lib.bgr_read_alive(self._h, first_row, count, out.ctypes.data))
         return out
+
+    # ---- asynchronous mirror download (bgr_download_begin / bgr_download_wait) ----
+    def host_alloc(self, count: int, byte_len: int) -> np.ndarray:
+        """Page-locked (count, byte_len) u8 array for download_begin; freed with the engine."""
+        p = C.c_void_p()
+        self._check(self._lib.bgr_host_alloc(count * byte_len, C.byref(p)))
+        self._pinned.append(p)
+        buf = (C.c_uint8 * max(1, count * byte_len)).from_address(p.value)
+        return np.frombuffer(buf, dtype=np.uint8, count=count * byte_len).reshape(count, byte_len)
+
+    def download_begin(self, col: int, byte_offset: int, byte_len: int, first_row: int, count: int, dst: np.ndarray) -> int:
+        assert dst.dtype == np.uint8 and dst.flags.c_contiguous and dst.size >= count * byte_len
+        t = C.c_uint32()
+        self._check(self._lib.bgr_download_begin(self._h, col, byte_offset, byte_len, first_row, count, dst.ctypes.data,
+                                                 C.byref(t)))
+        return t.value
+
+    def download_wait(self, ticket: int) -> None:
+        self._check(self._lib.bgr_download_wait(self._h, ticket))
 
     # ---- frame resources ----
     def rollback_frame_count(self) -> int:

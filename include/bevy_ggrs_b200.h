@@ -200,6 +200,25 @@ BGR_API int bgr_read_component(bgr_engine* e, uint32_t column, uint32_t first_ro
                                void* host_dst, uint32_t stride);
 BGR_API int bgr_read_alive(bgr_engine* e, uint32_t first_row, uint32_t count, uint8_t* host_dst);
 
+/* ---- asynchronous mirror download: what the ECS side reads back every tick -----------------
+ * In the reference the world lives in host memory and everything after GgrsSchedule (rendering via Transform,
+ * examples/stress_tests/particles.rs:191-196; game logic outside the rollback schedule) reads it there.  With the
+ * world in HBM the shim mirrors only the fields those readers need: bytes [byte_offset, byte_offset+byte_len) of
+ * every element of `column` for rows [first_row, first_row+count), packed densely (byte_len bytes per row) into
+ * `host_dst`.  byte_offset and byte_len must be multiples of 4.
+ *
+ * bgr_download_begin is ordered after every request vector submitted so far (it sees the live world those leave
+ * behind), returns without waiting for the GPU, and does not delay later submits: the fields are packed into a device
+ * staging buffer on the engine's stream and cross PCIe on a separate copy stream.  `host_dst` should come from
+ * bgr_host_alloc (page-locked); it must not be read before bgr_download_wait(ticket) returns.  At most
+ * BGR_MAX_DOWNLOADS may be in flight. */
+#define BGR_MAX_DOWNLOADS 4
+BGR_API int bgr_host_alloc(size_t bytes, void** out);
+BGR_API int bgr_host_free(void* p);
+BGR_API int bgr_download_begin(bgr_engine* e, uint32_t column, uint32_t byte_offset, uint32_t byte_len,
+                               uint32_t first_row, uint32_t count, void* host_dst, uint32_t* ticket_out);
+BGR_API int bgr_download_wait(bgr_engine* e, uint32_t ticket);
+
 /* ---- frame resources (src/snapshot/mod.rs:66-77, lib.rs:116-117) ------------------------ */
 BGR_API int bgr_rollback_frame_count(bgr_engine* e, int32_t* out);
 BGR_API int bgr_set_rollback_frame_count(bgr_engine* e, int32_t frame);

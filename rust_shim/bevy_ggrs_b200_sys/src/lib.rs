@@ -106,6 +106,10 @@ extern "C" {
     pub fn bgr_write_component(e: *mut bgr_engine, column: u32, first_row: u32, count: u32, host_src: *const c_void, stride: u32) -> c_int;
     pub fn bgr_read_component(e: *mut bgr_engine, column: u32, first_row: u32, count: u32, host_dst: *mut c_void, stride: u32) -> c_int;
     pub fn bgr_read_alive(e: *mut bgr_engine, first_row: u32, count: u32, host_dst: *mut u8) -> c_int;
+    pub fn bgr_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
+    pub fn bgr_host_free(p: *mut c_void) -> c_int;
+    pub fn bgr_download_begin(e: *mut bgr_engine, column: u32, byte_offset: u32, byte_len: u32, first_row: u32, count: u32, host_dst: *mut c_void, ticket_out: *mut u32) -> c_int;
+    pub fn bgr_download_wait(e: *mut bgr_engine, ticket: u32) -> c_int;
     pub fn bgr_rollback_frame_count(e: *mut bgr_engine, out: *mut i32) -> c_int;
     pub fn bgr_set_rollback_frame_count(e: *mut bgr_engine, frame: i32) -> c_int;
     pub fn bgr_confirmed_frame_count(e: *mut bgr_engine, out: *mut i32) -> c_int;

@@ -157,3 +157,48 @@ def test_p2p_trace_matches_oracle_request_for_request():
     assert np.array_equal(eng.read_alive(0, 5000).astype(bool), alive)
     for c in cols:
         assert np.array_equal(eng.read_component(c, 0, 5000)[alive], orc.read_component(c, 0, 5000)[alive])
+
+
+@pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])
+def test_async_download_sees_the_world_at_begin_and_overlaps_later_ticks(flags):
+    """bgr_download_begin is ordered after the submits before it and is not disturbed by the submits after it: the
+    mirrored Transform.translation / Velocity / Ttl bytes equal the oracle's world at that tick, bit for bit."""
+    n = 3000  # ragged: 5 full tiles + a partial one
+    eng, orc, cols = _pair(n, flags=flags, seed=9, ttl=(3, 40))
+    t, v, l = cols
+    tick = lambda f: [Request(SAVE, f), Request(ADVANCE, f, [0, 0])]
+    host = {name: eng.host_alloc(n, nb) for name, nb in (("tr", 12), ("vel", 12), ("ttl", 8), ("rot", 16))}
+    for f in range(3):
+        eng.submit_requests(NOSESS, tick(f))
+        orc.handle_requests(NOSESS, tick(f))
+    tickets = [eng.download_begin(t, 0, 12, 0, n, host["tr"]), eng.download_begin(v, 0, 12, 0, n, host["vel"]),
+               eng.download_begin(l, 0, 8, 0, n, host["ttl"]), eng.download_begin(t, 12, 16, 0, n, host["rot"])]
+    with pytest.raises(BgrError) as ei:  # BGR_MAX_DOWNLOADS in flight
+        eng.download_begin(t, 0, 12, 0, n, host["tr"])
+    assert ei.value.status == capi.BGR_ERR_STATE
+    tr, alive = orc.read_component_alive(t, 0, n)  # dead rows' stale bytes are not observable: compare the live ones
+    alive = alive.astype(bool)
+    assert 0 < alive.sum() < n
+    want = {"tr": tr[:, :12].copy(), "vel": orc.read_component(v, 0, n).copy(),
+            "ttl": orc.read_component(l, 0, n).copy(), "rot": tr[:, 12:28].copy()}
+    for f in range(3, 6):  # later ticks run while the copies are in flight and must not leak into them
+        eng.submit_requests(NOSESS, tick(f))
+        orc.handle_requests(NOSESS, tick(f))
+    for k in tickets:
+        eng.download_wait(k)
+    for name in want:
+        assert np.array_equal(host[name][alive], want[name][alive]), name
+    for _ in range(6):
+        eng.collect()
+    # a sub-range, after the in-flight slots were released
+    k = eng.download_begin(t, 4, 8, 513, 1000, host["ttl"])
+    eng.download_wait(k)
+    sub, sub_alive = orc.read_component_alive(t, 513, 1000)
+    assert np.array_equal(host["ttl"][:1000][sub_alive.astype(bool)], sub[:, 4:12][sub_alive.astype(bool)])
+    with pytest.raises(BgrError):
+        eng.download_wait(k)  # already waited for
+    with pytest.raises(BgrError):
+        eng.download_begin(t, 2, 8, 0, 10, host["ttl"])  # unaligned field range
+    with pytest.raises(BgrError):
+        eng.download_begin(t, 0, 12, n - 5, 10, host["tr"])  # beyond the spawned rows
+    eng.close()
