@@ -21,6 +21,8 @@ BGR_OK, BGR_ERR_INVALID_ARGUMENT, BGR_ERR_STATE, BGR_ERR_CUDA, BGR_ERR_NO_SNAPSH
     BGR_ERR_MISSING_RESOURCE, BGR_ERR_NON_FINITE, BGR_ERR_CAPACITY, BGR_ERR_UNSUPPORTED = range(9)
 # bgr_strategy
 BGR_STRATEGY_COPY, BGR_STRATEGY_CLONE = 0, 1
+BGR_STRATEGY_OPTIONAL = 0x100
+BGR_MAX_OPTIONAL_COLUMNS = 7
 # bgr_hash_kind
 BGR_HASH_NONE, BGR_HASH_BYTES = 0, 1
 BGR_HASH_FLAG_ASSERT_FINITE_F32 = 1
@@ -91,6 +93,9 @@ PROTOTYPES = {
     "bgr_write_component": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]),
     "bgr_read_component": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32]),
     "bgr_read_alive": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "bgr_remove_component": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32]),
+    "bgr_insert_component": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "bgr_has_component": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "bgr_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "bgr_host_free": (C.c_int, [C.c_void_p]),
     "bgr_download_begin": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p, u32p]),

@@ -43,6 +43,7 @@ struct Column {
     uint32_t elem_bytes = 0, words = 0, first_plane = 0, strategy = 0;
     uint32_t hash_kind = BGR_HASH_NONE, hash_off = 0, hash_len = 0, hash_flags = 0;
     int ck_slot = -1;  // index among checksummed columns (registration order)
+    uint32_t absent = 0;  // optional column: its absent bit in the per-row mask byte (kernels.cuh row_matches)
 };
 
 struct SystemReg {
@@ -510,6 +511,7 @@ int launch_tma(bgr_engine* e, const uint8_t* src, uint8_t* dst, uint32_t n_rows_
                 HashSpec& h = tp.hash[tp.n_hash++];
                 h.first_plane = c.first_plane; h.off = c.hash_off; h.len = c.hash_len;
                 h.finite = c.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32; h.slot = uint32_t(c.ck_slot);
+                h.absent = c.absent;
             }
     uint32_t n_chunks = (tp.n_tiles + tp.stage_tiles - 1) / tp.stage_tiles;
     uint32_t grid = std::max(1u, std::min(n_chunks, uint32_t(e->num_sms)));
@@ -543,13 +545,13 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
                 k_checksum_column<<<e->grid_for(std::max(1u, op.n_rows), 256), 256, 0, e->stream>>>(
                     live, e->words, c.first_plane, c.hash_off, c.hash_len,
                     c.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32, op.n_rows, e->cfg.order_base, acc,
-                    uint32_t(c.ck_slot), counted ? 0u : 1u, 1u);
+                    uint32_t(c.ck_slot), counted ? 0u : 1u, 1u, c.absent);
                 counted = true;
                 e->launches += 1;
             }
             if (!counted) {
                 k_checksum_column<<<e->grid_for(std::max(1u, op.n_rows), 256), 256, 0, e->stream>>>(
-                    live, e->words, 0, 0, 0, 0, op.n_rows, e->cfg.order_base, acc, 0, 1u, 0u);
+                    live, e->words, 0, 0, 0, 0, op.n_rows, e->cfg.order_base, acc, 0, 1u, 0u, 0u);
                 e->launches += 1;
             }
             if (!(op.flags & OPF_NO_STORE) && op.n_rows > 0) {
@@ -581,31 +583,33 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
             uint32_t grid = e->grid_for(std::max(1u, n), 256);
             for (const SystemReg& sy : e->systems) {
                 if (n == 0) break;
+                uint32_t need = 0;  // the query matches entities that have every bound column
+                for (uint32_t c : sy.cols) need |= e->cols[c].absent;
                 switch (sy.id) {
                 case BGR_SYS_PARTICLES_UPDATE:
                     k_sys_particles_update<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane,
-                                                                          e->cols[sy.cols[1]].first_plane, n, op.dt_bits);
+                                                                          e->cols[sy.cols[1]].first_plane, n, op.dt_bits, need);
                     break;
                 case BGR_SYS_PARTICLES_DESPAWN:
-                    k_sys_particles_despawn<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane, n, e->d_kill);
+                    k_sys_particles_despawn<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane, n, e->d_kill, need);
                     any_despawn = true;
                     break;
                 case BGR_SYS_U32_ADD:
-                    k_sys_u32_add<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1]);
+                    k_sys_u32_add<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1], need);
                     break;
                 case BGR_SYS_U32_SATSUB_DESPAWN:
-                    k_sys_u32_satsub_despawn<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1], e->d_kill);
+                    k_sys_u32_satsub_despawn<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, sy.params[1], e->d_kill, need);
                     any_despawn = true;
                     break;
                 case BGR_SYS_U32_STORE_CALL_COUNT:
-                    k_sys_u32_store<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, counter++);
+                    k_sys_u32_store<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane + sy.params[0] / 4, n, counter++, need);
                     break;
                 case BGR_SYS_PARTICLES_SPAWN:
                     continue;  // Commands: applied after the schedule (below)
                 case BGR_SYS_BOX_MOVE: {
                     uint32_t packed = uint32_t(op.inputs[0]) | (uint32_t(op.inputs[1]) << 8) | (uint32_t(op.inputs[2]) << 16) | (uint32_t(op.inputs[3]) << 24);
                     k_sys_box_move<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane, e->cols[sy.cols[1]].first_plane,
-                                                                 n, op.dt_bits, packed, (op.flags >> 8) & 0xFu, e->cfg.order_base);
+                                                                 n, op.dt_bits, packed, (op.flags >> 8) & 0xFu, e->cfg.order_base, need);
                     break;
                 }
                 default: return fail(BGR_ERR_UNSUPPORTED, "system has no GPU implementation yet");
@@ -790,14 +794,15 @@ int transfer_column(bgr_engine* e, uint32_t image_idx, uint32_t column, uint32_t
     return BGR_OK;
 }
 
-int read_alive_image(bgr_engine* e, uint32_t image_idx, uint32_t first, uint32_t count, uint32_t n_rows, uint8_t* dst) {
+int read_alive_image(bgr_engine* e, uint32_t image_idx, uint32_t first, uint32_t count, uint32_t n_rows, uint8_t* dst,
+                     uint32_t need = 0) {
     if (count == 0) return BGR_OK;
     int rc = drain(e);
     if (rc != BGR_OK) return rc;
     if (uint64_t(first) + count > e->cfg.max_entities) return fail(BGR_ERR_CAPACITY, "row range exceeds max_entities");
     rc = ensure_stage(e, count);
     if (rc != BGR_OK) return rc;
-    k_gather_alive<<<e->grid_for(count, 256), 256, 0, e->stream>>>(e->image(image_idx), e->words, first, count, n_rows, e->d_stage);
+    k_gather_alive<<<e->grid_for(count, 256), 256, 0, e->stream>>>(e->image(image_idx), e->words, first, count, n_rows, e->d_stage, need);
     e->launches += 1;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(dst, e->d_stage, count, cudaMemcpyDeviceToHost, e->stream));
@@ -863,6 +868,8 @@ int download_wait(bgr_engine* e, uint32_t ticket) {
 void detect_bundles(bgr_engine* e) {
     e->bundle_particles = false;
     e->passive.clear();
+    for (const Column& c : e->cols)
+        if (c.absent) return;  // per-entity presence is only implemented by the generic (stepwise) kernels
     const SystemReg* up = nullptr; const SystemReg* de = nullptr; const SystemReg* sp = nullptr;
     for (auto& s : e->systems) {
         if (s.id == BGR_SYS_PARTICLES_UPDATE && !up) up = &s;
@@ -988,9 +995,17 @@ BGR_API int bgr_rollback_component(bgr_engine* e, const char* type_name, uint32_
     if (!e || !column_out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
     if (e->built) return fail(BGR_ERR_STATE, "components must be registered before bgr_build");
     if (elem_bytes == 0 || elem_bytes > 1024) return fail(BGR_ERR_INVALID_ARGUMENT, "elem_bytes must be in 1..1024");
+    const bool optional = strategy & BGR_STRATEGY_OPTIONAL;
+    strategy &= ~BGR_STRATEGY_OPTIONAL;
     if (strategy != BGR_STRATEGY_COPY && strategy != BGR_STRATEGY_CLONE)
         return fail(BGR_ERR_UNSUPPORTED, "only Copy/Clone strategies of POD types are supported (ReflectStrategy is out of scope)");
     Column c;
+    if (optional) {
+        uint32_t n_opt = 0;
+        for (const Column& o : e->cols) n_opt += o.absent ? 1u : 0u;
+        if (n_opt >= BGR_MAX_OPTIONAL_COLUMNS) return fail(BGR_ERR_CAPACITY, "more than BGR_MAX_OPTIONAL_COLUMNS optional columns");
+        c.absent = 2u << n_opt;
+    }
     c.name = type_name ? type_name : "";
     c.elem_bytes = elem_bytes;
     c.words = (elem_bytes + 3) / 4;
@@ -1220,6 +1235,41 @@ BGR_API int bgr_read_component(bgr_engine* e, uint32_t column, uint32_t first_ro
     return transfer_column(e, 0, column, first_row, count, host_dst, stride, false);
 }
 
+static int presence_args(bgr_engine* e, uint32_t column, uint32_t row) {
+    if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
+    if (column >= e->cols.size()) return fail(BGR_ERR_INVALID_ARGUMENT, "unknown column");
+    if (!e->cols[column].absent) return fail(BGR_ERR_INVALID_ARGUMENT, "column was not registered with BGR_STRATEGY_OPTIONAL");
+    if (row >= e->st.n_rows) return fail(BGR_ERR_INVALID_ARGUMENT, "row out of range");
+    return drain(e);
+}
+BGR_API int bgr_remove_component(bgr_engine* e, uint32_t column, uint32_t row) {
+    int rc = presence_args(e, column, row);
+    if (rc != BGR_OK) return rc;
+    k_set_absent<<<1, 1, 0, e->stream>>>(e->image(0), e->words, row, e->cols[column].absent, 1u);
+    e->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    e->st.live_passive_ver = ++e->st.ver_counter;
+    return BGR_OK;
+}
+BGR_API int bgr_insert_component(bgr_engine* e, uint32_t column, uint32_t row, const void* value) {
+    if (!value) return fail(BGR_ERR_INVALID_ARGUMENT, "null value");
+    int rc = presence_args(e, column, row);
+    if (rc != BGR_OK) return rc;
+    rc = transfer_column(e, 0, column, row, 1, const_cast<void*>(value), e->cols[column].elem_bytes, true);
+    if (rc != BGR_OK) return rc;
+    k_set_absent<<<1, 1, 0, e->stream>>>(e->image(0), e->words, row, e->cols[column].absent, 0u);
+    e->launches += 1;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return BGR_OK;
+}
+BGR_API int bgr_has_component(bgr_engine* e, uint32_t column, uint32_t first_row, uint32_t count, uint8_t* host_dst) {
+    if (!e || !e->built || !host_dst) return fail(BGR_ERR_STATE, "engine not built");
+    if (column >= e->cols.size()) return fail(BGR_ERR_INVALID_ARGUMENT, "unknown column");
+    return read_alive_image(e, 0, first_row, count, e->st.n_rows, host_dst, e->cols[column].absent);
+}
+
 BGR_API int bgr_host_alloc(size_t bytes, void** out) {
     if (!out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
     *out = nullptr;
@@ -1287,7 +1337,8 @@ BGR_API int bgr_peek(bgr_engine* e, int32_t frame, uint32_t column, uint32_t fir
     *found = 1;
     int rc = transfer_column(e, slot + 1, column, first_row, count, host_dst, stride, false);
     if (rc != BGR_OK) return rc;
-    if (alive_dst) return read_alive_image(e, slot + 1, first_row, count, e->st.slot_rows[slot], alive_dst);
+    // alive_dst[i] = the snapshot of `frame` holds this column for row first_row+i (the row existed and had the component)
+    if (alive_dst) return read_alive_image(e, slot + 1, first_row, count, e->st.slot_rows[slot], alive_dst, e->cols[column].absent);
     return BGR_OK;
 }
 

@@ -47,6 +47,11 @@ __host__ __device__ inline uint32_t tile_bytes_of(uint32_t words) { return kTile
 __host__ __device__ inline size_t word_offset(uint32_t words, uint32_t row, uint32_t plane) {
     return size_t(row / kTileRows) * tile_bytes_of(words) + size_t(plane) * kPlaneBytes + size_t(row % kTileRows) * 4u;
 }
+// The byte per row behind the word planes: bit 0 = the entity exists (Rollback marker alive); bit 1+k = optional
+// column k is ABSENT from this entity (component_snapshot.rs:106-115: a column registered with
+// BGR_STRATEGY_OPTIONAL can be removed from / inserted into single entities).  Spawning writes 1: alive, everything
+// present.  A row takes part in a query over columns whose absent bits are `need` iff (m & (1 | need)) == 1.
+__host__ __device__ inline bool row_matches(uint32_t m, uint32_t need) { return (m & (1u | need)) == 1u; }
 __host__ __device__ inline size_t alive_offset(uint32_t words, uint32_t row) {
     return size_t(row / kTileRows) * tile_bytes_of(words) + size_t(words) * kPlaneBytes + size_t(row % kTileRows);
 }
@@ -549,14 +554,16 @@ __global__ void __launch_bounds__(256) k_checksum_column(const uint8_t* __restri
                                                          uint32_t first_plane, uint32_t off, uint32_t len,
                                                          uint32_t finite_flag, uint32_t n_rows,
                                                          unsigned long long order_base, unsigned long long* acc,
-                                                         uint32_t col_slot, uint32_t count_alive, uint32_t hash_column) {
+                                                         uint32_t col_slot, uint32_t count_alive, uint32_t hash_column,
+                                                         uint32_t absent) {
     const uint32_t lane = threadIdx.x & 31u;
     uint64_t hx = 0;
     uint32_t cnt = 0, bad = 0;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r - lane < n_rows; r += gridDim.x * blockDim.x) {
-        if (r < n_rows && img[alive_offset(words, r)]) {
+        const uint32_t m = r < n_rows ? img[alive_offset(words, r)] : 0u;
+        if (m & 1u) {
             ++cnt;
-            if (hash_column) {
+            if (hash_column && !(m & absent)) {
                 const uint8_t* base = img + word_offset(words, r, first_plane);
                 auto byte_at = [&](uint32_t i) -> uint8_t {
                     uint32_t b = off + i;
@@ -629,10 +636,16 @@ __global__ void __launch_bounds__(256) k_gather_fields(const uint8_t* __restrict
     }
 }
 // alive bytes of rows [first, first+count): gather to a dense array / set to a value
+// out[i] = 1 iff the row exists and none of the `need` absent bits is set (need = 0: the alive flag itself)
 __global__ void __launch_bounds__(256) k_gather_alive(const uint8_t* __restrict__ img, uint32_t words, uint32_t first_row,
-                                                      uint32_t count, uint32_t n_rows, uint8_t* out) {
+                                                      uint32_t count, uint32_t n_rows, uint8_t* out, uint32_t need) {
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x)
-        out[i] = (first_row + i < n_rows) ? img[alive_offset(words, first_row + i)] : uint8_t(0);
+        out[i] = (first_row + i < n_rows && row_matches(img[alive_offset(words, first_row + i)], need)) ? uint8_t(1) : uint8_t(0);
+}
+// Commands::entity(e).remove::<T>() / .insert(T): set / clear one absent bit of a live row
+__global__ void k_set_absent(uint8_t* img, uint32_t words, uint32_t row, uint32_t bit, uint32_t absent) {
+    uint8_t* m = img + alive_offset(words, row);
+    if (*m & 1u) *m = absent ? uint8_t(*m | bit) : uint8_t(*m & ~bit);
 }
 // `commands.spawn((..., Rollback))`: zeroed components, alive = 1
 __global__ void __launch_bounds__(256) k_spawn_rows(uint8_t* img, uint32_t words, uint32_t first_row, uint32_t count) {
@@ -647,10 +660,10 @@ __global__ void k_set_alive(uint8_t* img, uint32_t words, uint32_t row, uint8_t 
 
 // ---- GgrsSchedule systems on the live image (stepwise path) ----
 __global__ void __launch_bounds__(256) k_sys_particles_update(uint8_t* img, uint32_t words, uint32_t t_plane,
-                                                              uint32_t v_plane, uint32_t n_rows, uint32_t dt_bits) {
+                                                              uint32_t v_plane, uint32_t n_rows, uint32_t dt_bits, uint32_t need) {
     const float dt = __uint_as_float(dt_bits);
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
-        if (!img[alive_offset(words, r)]) continue;
+        if (!row_matches(img[alive_offset(words, r)], need)) continue;
         uint32_t* t = reinterpret_cast<uint32_t*>(img + word_offset(words, r, t_plane));
         uint32_t* v = reinterpret_cast<uint32_t*>(img + word_offset(words, r, v_plane));
         uint32_t tx = t[0], ty = t[kTileRows], tz = t[2 * kTileRows], vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
@@ -662,9 +675,9 @@ __global__ void __launch_bounds__(256) k_sys_particles_update(uint8_t* img, uint
 // `kill` receives the despawns; they are applied after every system of the schedule has run
 // (Commands are deferred to the end of GgrsSchedule).
 __global__ void __launch_bounds__(256) k_sys_particles_despawn(uint8_t* img, uint32_t words, uint32_t l_plane,
-                                                               uint32_t n_rows, uint8_t* kill) {
+                                                               uint32_t n_rows, uint8_t* kill, uint32_t need) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
-        if (!img[alive_offset(words, r)]) continue;
+        if (!row_matches(img[alive_offset(words, r)], need)) continue;
         uint32_t* l = reinterpret_cast<uint32_t*>(img + word_offset(words, r, l_plane));
         uint64_t ttl = (uint64_t(l[kTileRows]) << 32) | l[0];
         ttl -= 1;
@@ -674,16 +687,16 @@ __global__ void __launch_bounds__(256) k_sys_particles_despawn(uint8_t* img, uin
 }
 
 // x.0 += k   (tests/component_rollback.rs:25-29)
-__global__ void __launch_bounds__(256) k_sys_u32_add(uint8_t* img, uint32_t words, uint32_t plane, uint32_t n_rows, uint32_t k) {
+__global__ void __launch_bounds__(256) k_sys_u32_add(uint8_t* img, uint32_t words, uint32_t plane, uint32_t n_rows, uint32_t k, uint32_t need) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
-        if (img[alive_offset(words, r)]) *reinterpret_cast<uint32_t*>(img + word_offset(words, r, plane)) += k;
+        if (row_matches(img[alive_offset(words, r)], need)) *reinterpret_cast<uint32_t*>(img + word_offset(words, r, plane)) += k;
 }
 
 // h = h.saturating_sub(k); despawn at 0   (tests/synctest.rs:38-45)
 __global__ void __launch_bounds__(256) k_sys_u32_satsub_despawn(uint8_t* img, uint32_t words, uint32_t plane,
-                                                                uint32_t n_rows, uint32_t k, uint8_t* kill) {
+                                                                uint32_t n_rows, uint32_t k, uint8_t* kill, uint32_t need) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
-        if (!img[alive_offset(words, r)]) continue;
+        if (!row_matches(img[alive_offset(words, r)], need)) continue;
         uint32_t* x = reinterpret_cast<uint32_t*>(img + word_offset(words, r, plane));
         uint32_t v = *x;
         v = v > k ? v - k : 0u;
@@ -693,9 +706,9 @@ __global__ void __launch_bounds__(256) k_sys_u32_satsub_despawn(uint8_t* img, ui
 }
 
 // c.0 = count  (the deliberately non-deterministic system of tests/synctest.rs:92-97)
-__global__ void __launch_bounds__(256) k_sys_u32_store(uint8_t* img, uint32_t words, uint32_t plane, uint32_t n_rows, uint32_t value) {
+__global__ void __launch_bounds__(256) k_sys_u32_store(uint8_t* img, uint32_t words, uint32_t plane, uint32_t n_rows, uint32_t value, uint32_t need) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
-        if (img[alive_offset(words, r)]) *reinterpret_cast<uint32_t*>(img + word_offset(words, r, plane)) = value;
+        if (row_matches(img[alive_offset(words, r)], need)) *reinterpret_cast<uint32_t*>(img + word_offset(words, r, plane)) = value;
 }
 
 // spawn_particles (particles.rs:258-270) on the live image: rows [first, first+count) become
@@ -722,11 +735,12 @@ __global__ void __launch_bounds__(256) k_sys_particles_spawn(uint8_t* img, uint3
 // `FRICTION.powf(dt)` is libm on the CPU and CUDA powf here: this is the one system of the path whose f32
 // results are only guaranteed within a tolerance (|d| <= 1e-5 * max(1, |x|), tested), not bit-exact.
 __global__ void k_sys_box_move(uint8_t* img, uint32_t words, uint32_t t_plane, uint32_t v_plane, uint32_t n_rows,
-                               uint32_t dt_bits, uint32_t inputs_packed, uint32_t n_players, unsigned long long order_base) {
+                               uint32_t dt_bits, uint32_t inputs_packed, uint32_t n_players, unsigned long long order_base,
+                               uint32_t need) {
     const float dt = __uint_as_float(dt_bits);
     const float ACCELERATION = 18.0f, MAX_SPEED = 3.0f, FRICTION = 0.0018f, PLANE_SIZE = 5.0f, CUBE_SIZE = 0.2f;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
-        if (!img[alive_offset(words, r)]) continue;
+        if (!row_matches(img[alive_offset(words, r)], need)) continue;
         float* t = reinterpret_cast<float*>(img + word_offset(words, r, t_plane));
         float* v = reinterpret_cast<float*>(img + word_offset(words, r, v_plane));
         float tx = t[0], ty = t[kTileRows], tz = t[2 * kTileRows];

@@ -27,6 +27,7 @@ constexpr int kMaxHashCols = 6;
 
 struct HashSpec {
     uint32_t first_plane, off, len, finite, slot;
+    uint32_t absent;  // absent bit of an optional column (0: the column is on every live row)
 };
 
 struct TmaCopyParams {
@@ -98,13 +99,15 @@ __global__ void __launch_bounds__(kTmaBlock, 1) k_image_tma(const __grid_constan
             for (uint32_t r = tid; r < rows; r += kTmaBlock) {
                 const uint8_t* tile = st + size_t(r / kTileRows) * p.tile_bytes;
                 const uint32_t i = r % kTileRows;
-                if (!tile[size_t(p.words) * kPlaneBytes + i]) continue;
+                const uint32_t m = tile[size_t(p.words) * kPlaneBytes + i];
+                if (!(m & 1u)) continue;
                 ++n_alive;
                 const uint64_t t0 = sea_order_lane(p.order_base + row_base + r);
 #pragma unroll
                 for (int c = 0; c < kMaxHashCols; ++c) {
                     if (c < p.n_hash) {
                         const HashSpec hs = p.hash[c];
+                        if (m & hs.absent) continue;  // Query<(&RollbackId, &T)> does not match this entity
                         const uint32_t* col = reinterpret_cast<const uint32_t*>(tile + size_t(hs.first_plane) * kPlaneBytes) + i;
                         uint64_t custom;
                         if (hs.off == 0 && hs.len == 12) {  // 3 x u32 `to_bits` fields (particles.rs:107-120, 207-222)

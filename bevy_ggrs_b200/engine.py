@@ -103,6 +103,20 @@ class Engine:
         self._check(self._lib.bgr_read_alive(self._h, first_row, count, out.ctypes.data))
         return out
 
+    # ---- per-entity presence of BGR_STRATEGY_OPTIONAL columns ----
+    def remove_component(self, col: int, row: int) -> None:
+        self._check(self._lib.bgr_remove_component(self._h, col, row))
+
+    def insert_component(self, col: int, row: int, value) -> None:
+        a = np.ascontiguousarray(value).view(np.uint8).reshape(-1)
+        assert a.size == self.elem_bytes[col]
+        self._check(self._lib.bgr_insert_component(self._h, col, row, a.ctypes.data))
+
+    def has_component(self, col: int, first_row: int, count: int) -> np.ndarray:
+        out = np.zeros(count, dtype=np.uint8)
+        self._check(self._lib.bgr_has_component(self._h, col, first_row, count, out.ctypes.data))
+        return out
+
     # ---- asynchronous mirror download (bgr_download_begin / bgr_download_wait) ----
     def host_alloc(self, count: int, byte_len: int) -> np.ndarray:
         """Page-locked (count, byte_len) u8 array for download_begin; freed with the engine."""

@@ -100,6 +100,10 @@ public:
     // ---- RollbackApp (rollback_app.rs:31-248) ----
     template <class T> App& rollback_component_with_copy() { return register_component<T>(BGR_STRATEGY_COPY); }
     template <class T> App& rollback_component_with_clone() { return register_component<T>(BGR_STRATEGY_CLONE); }
+    // a component single entities may lose / regain inside the window: Option<&mut T> in ComponentSnapshotPlugin::load
+    // (component_snapshot.rs:99-115); see remove<T>() / insert<T>() below
+    template <class T> App& rollback_optional_component_with_copy() { return register_component<T>(BGR_STRATEGY_COPY | BGR_STRATEGY_OPTIONAL); }
+    template <class T> App& rollback_optional_component_with_clone() { return register_component<T>(BGR_STRATEGY_CLONE | BGR_STRATEGY_OPTIONAL); }
     template <class T> App& checksum_component(ByteRangeHasher h) { checksums_.push_back({col<T>(), h}); return *this; }
     template <class T> App& checksum_component_with_hash() { return checksum_component<T>(hash_bytes(0, uint32_t(sizeof(T)))); }
 
@@ -138,6 +142,22 @@ public:
         check(bgr_read_component(engine_, col<T>(), first_row, count, v.data(), uint32_t(sizeof(T))));
         return v;
     }
+    // commands.entity(row).remove::<T>() / .insert(value) / Query<Has<T>> for optional components
+    template <class T> void remove(uint32_t row) { finish(); check(bgr_remove_component(engine_, col<T>(), row)); }
+    template <class T> void insert(uint32_t row, const T& value) { finish(); check(bgr_insert_component(engine_, col<T>(), row, &value)); }
+    template <class T> std::vector<uint8_t> has(uint32_t first_row, uint32_t count) {
+        std::vector<uint8_t> v(count);
+        check(bgr_has_component(engine_, col<T>(), first_row, count, v.data()));
+        return v;
+    }
+    // asynchronous host mirror of bytes [offset, offset+len) of every T in rows [first_row, first_row+count):
+    // `dst` from bgr_host_alloc; readable after download_wait(ticket)
+    template <class T> uint32_t download_begin(uint32_t offset, uint32_t len, uint32_t first_row, uint32_t count, void* dst) {
+        uint32_t ticket = 0;
+        check(bgr_download_begin(engine_, col<T>(), offset, len, first_row, count, dst, &ticket));
+        return ticket;
+    }
+    void download_wait(uint32_t ticket) { check(bgr_download_wait(engine_, ticket)); }
     // GgrsComponentSnapshots<T>::peek(frame) (mod.rs:233-240)
     template <class T> std::optional<std::vector<T>> peek(ggrs::Frame frame, uint32_t first_row, uint32_t count) {
         std::vector<T> v(count);

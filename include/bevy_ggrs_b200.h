@@ -61,6 +61,12 @@ typedef enum bgr_status {
 /* Strategy<T> (src/snapshot/strategy.rs:22-83).  Copy and Clone of a POD are both a bitwise
  * copy; ReflectStrategy is out of scope (boxed dynamic reflection). */
 typedef enum bgr_strategy { BGR_STRATEGY_COPY = 0, BGR_STRATEGY_CLONE = 1 } bgr_strategy;
+/* OR into `strategy`: single entities may lose / regain this component inside the rollback window
+ * (`Option<&mut S::Target>` in ComponentSnapshotPlugin::load, src/snapshot/component_snapshot.rs:99-115).  Save stores
+ * the component only for the entities that have it, Load updates / removes / inserts / leaves alone accordingly, the
+ * checksum and the GgrsSchedule systems only see entities that have it.  At most BGR_MAX_OPTIONAL_COLUMNS columns. */
+#define BGR_STRATEGY_OPTIONAL 0x100u
+#define BGR_MAX_OPTIONAL_COLUMNS 7
 
 /* How `checksum_component::<T>(hasher)` hashes one element (rollback_app.rs:227-232,
  * component_checksum.rs:44-48).  BGR_HASH_BYTES = seahash over elem[offset .. offset+len):
@@ -199,6 +205,13 @@ BGR_API int bgr_write_component(bgr_engine* e, uint32_t column, uint32_t first_r
 BGR_API int bgr_read_component(bgr_engine* e, uint32_t column, uint32_t first_row, uint32_t count,
                                void* host_dst, uint32_t stride);
 BGR_API int bgr_read_alive(bgr_engine* e, uint32_t first_row, uint32_t count, uint8_t* host_dst);
+
+/* ---- per-entity component presence (columns registered with BGR_STRATEGY_OPTIONAL) ----------
+ * bgr_remove_component = `commands.entity(e).remove::<T>()`, bgr_insert_component = `.insert(value)` applied to the live
+ * world between request vectors (value: elem_bytes bytes); bgr_has_component writes 1 per row that is alive and has it. */
+BGR_API int bgr_remove_component(bgr_engine* e, uint32_t column, uint32_t row);
+BGR_API int bgr_insert_component(bgr_engine* e, uint32_t column, uint32_t row, const void* value);
+BGR_API int bgr_has_component(bgr_engine* e, uint32_t column, uint32_t first_row, uint32_t count, uint8_t* host_dst);
 
 /* ---- asynchronous mirror download: what the ECS side reads back every tick -----------------
  * In the reference the world lives in host memory and everything after GgrsSchedule (rendering via Transform,

@@ -151,6 +151,24 @@ ORC_API int orc_read_component(World* w, uint32_t col, uint32_t first, uint32_t 
         }
     });
 }
+// commands.entity(e).remove::<C>() / .insert(value) on the entity whose RollbackOrdered index is `order`
+// (the other side of the Option<&mut S::Target> match in component_snapshot.rs:106-115)
+static size_t row_of_order(World* w, uint64_t order) {
+    for (size_t r = 0; r < w->rows(); ++r)
+        if (w->rollback_ordered.order_of(w->rollback_id[r]) == order) return r;
+    throw std::runtime_error("no live entity with that RollbackOrdered index");
+}
+ORC_API int orc_remove_component(World* w, uint32_t col, uint64_t order) {
+    return guarded([&] { w->has.at(col).at(row_of_order(w, order)) = 0; });
+}
+ORC_API int orc_insert_component(World* w, uint32_t col, uint64_t order, const void* value) {
+    return guarded([&] {
+        size_t r = row_of_order(w, order);
+        uint32_t eb = w->columns.at(col).elem_bytes;
+        std::memcpy(&w->data[col][r * size_t(eb)], value, eb);
+        w->has[col][r] = 1;
+    });
+}
 // peek(frame) of GgrsComponentSnapshots<C> (mod.rs:233-240): returns 0 if no snapshot for the frame
 ORC_API int orc_peek(World* w, int32_t frame, uint32_t col, uint32_t first, uint32_t count, void* dst, uint32_t stride, uint8_t* alive_out) {
     FlatTable* t = w->comp_snaps.at(col).peek(frame);

@@ -14,6 +14,8 @@ pub const BGR_ERR_NON_FINITE: c_int = 6;
 
 pub const BGR_STRATEGY_COPY: u32 = 0;
 pub const BGR_STRATEGY_CLONE: u32 = 1;
+pub const BGR_STRATEGY_OPTIONAL: u32 = 0x100;
+pub const BGR_MAX_OPTIONAL_COLUMNS: u32 = 7;
 pub const BGR_HASH_BYTES: u32 = 1;
 pub const BGR_HASH_FLAG_ASSERT_FINITE_F32: u32 = 1;
 
@@ -106,6 +108,9 @@ extern "C" {
     pub fn bgr_write_component(e: *mut bgr_engine, column: u32, first_row: u32, count: u32, host_src: *const c_void, stride: u32) -> c_int;
     pub fn bgr_read_component(e: *mut bgr_engine, column: u32, first_row: u32, count: u32, host_dst: *mut c_void, stride: u32) -> c_int;
     pub fn bgr_read_alive(e: *mut bgr_engine, first_row: u32, count: u32, host_dst: *mut u8) -> c_int;
+    pub fn bgr_remove_component(e: *mut bgr_engine, column: u32, row: u32) -> c_int;
+    pub fn bgr_insert_component(e: *mut bgr_engine, column: u32, row: u32, value: *const c_void) -> c_int;
+    pub fn bgr_has_component(e: *mut bgr_engine, column: u32, first_row: u32, count: u32, host_dst: *mut u8) -> c_int;
     pub fn bgr_host_alloc(bytes: usize, out: *mut *mut c_void) -> c_int;
     pub fn bgr_host_free(p: *mut c_void) -> c_int;
     pub fn bgr_download_begin(e: *mut bgr_engine, column: u32, byte_offset: u32, byte_len: u32, first_row: u32, count: u32, host_dst: *mut c_void, ticket_out: *mut u32) -> c_int;

@@ -156,6 +156,42 @@ static void particles_stress_synctest() {  // examples/stress_tests/particles.rs
     EXPECT(std::fabs((v[k].v[1] - v2[0].v[1]) - 100.0f) < 0.01f);
 }
 
+// Option<&mut T> in ComponentSnapshotPlugin::load (component_snapshot.rs:99-115): a component removed by code outside
+// GgrsSchedule is re-inserted by the next rollback, one inserted there is removed again; plus the async host mirror.
+static void optional_component_is_reinserted_and_removed_by_rollback() {
+    std::printf("optional_component_is_reinserted_and_removed_by_rollback\n");
+    App app(16, 8);
+    base_synctest_app(app, 3);
+    app.rollback_optional_component_with_copy<Score>().checksum_component_with_hash<Score>();
+    app.rollback_optional_component_with_copy<Health>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_U32_ADD, {0}, {0, 1}});
+    app.add_systems(Startup{}, [](App& a) { a.spawn(2); a.remove<Health>(1); });
+    bool mismatch = false;
+    app.add_observer([&](const SyncTestMismatch&) { mismatch = true; });
+    for (int i = 0; i < 10; ++i) app.update();
+    EXPECT(app.has<Score>(0, 2) == (std::vector<uint8_t>{1, 1}));
+    EXPECT(app.has<Health>(0, 2) == (std::vector<uint8_t>{1, 0}));
+    app.remove<Score>(0);                 // (None, Some) at the next Load -> insert
+    app.insert<Health>(1, Health{77});    // (Some, None) at the next Load -> remove
+    EXPECT(app.has<Score>(0, 2) == (std::vector<uint8_t>{0, 1}));
+    EXPECT(app.has<Health>(0, 2) == (std::vector<uint8_t>{1, 1}));
+    app.update();
+    EXPECT(app.has<Score>(0, 2) == (std::vector<uint8_t>{1, 1}));
+    EXPECT(app.has<Health>(0, 2) == (std::vector<uint8_t>{1, 0}));
+    auto sc = app.read<Score>(0, 2);
+    EXPECT(sc[0].v == uint32_t(app.rollback_frame_count()) && sc[1].v == sc[0].v);  // resimulated from the snapshot
+    EXPECT(!mismatch);
+    // asynchronous mirror of Score for both rows
+    void* pinned = nullptr;
+    EXPECT(bgr_host_alloc(8, &pinned) == BGR_OK);
+    uint32_t tk = app.download_begin<Score>(0, 4, 0, 2, pinned);
+    app.update();                         // the next tick runs while the copy is in flight
+    app.download_wait(tk);
+    const uint32_t* m = static_cast<const uint32_t*>(pinned);
+    EXPECT(m[0] == sc[0].v && m[1] == sc[1].v);
+    bgr_host_free(pinned);
+}
+
 struct FrameCount { uint32_t frame; };  // box_game.rs:49-53
 
 // BASELINE config C1: box_game SyncTest, 2 players, check_distance 8 (max_prediction 9), input_delay 2
@@ -261,6 +297,7 @@ int main(int argc, char** argv) {
         synctest_prunes_confirmed_snapshots();
         rollback_missing_frame_panics();
         particles_stress_synctest();
+        optional_component_is_reinserted_and_removed_by_rollback();
         box_game_synctest_c1();
     } catch (const std::exception& e) {
         std::printf("unexpected exception: %s\n", e.what());

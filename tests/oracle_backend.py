@@ -73,6 +73,8 @@ def load_oracle() -> C.CDLL:
         "orc_active_count": (u64, [vp]),
         "orc_write_component": (C.c_int, [vp, u32, u32, u32, vp, u32]),
         "orc_read_component": (C.c_int, [vp, u32, u32, u32, vp, u32, vp]),
+        "orc_remove_component": (C.c_int, [vp, u32, u64]),
+        "orc_insert_component": (C.c_int, [vp, u32, u64, vp]),
         "orc_peek": (C.c_int, [vp, i32, u32, u32, u32, vp, u32, vp]),
         "orc_snapshot_frames": (C.c_int, [vp, C.POINTER(i32), u32]),
         "orc_read_resource": (C.c_int, [vp, u32, vp]),
@@ -178,6 +180,17 @@ class OracleWorld:
         eb = self.elem_bytes[col]
         a = np.ascontiguousarray(values).view(np.uint8).reshape(-1, eb)
         self._check(self._lib.orc_write_component(self._h, col, first_row, a.shape[0], a.ctypes.data, eb))
+
+    def remove_component(self, col, row):
+        self._check(self._lib.orc_remove_component(self._h, col, row))
+
+    def insert_component(self, col, row, value):
+        a = np.ascontiguousarray(value).view(np.uint8).reshape(-1)
+        assert a.size == self.elem_bytes[col]
+        self._check(self._lib.orc_insert_component(self._h, col, row, a.ctypes.data))
+
+    def has_component(self, col, first_row, count):
+        return self.read_component_alive(col, first_row, count)[1]
 
     def read_component_alive(self, col, first_row, count):
         eb = self.elem_bytes[col]

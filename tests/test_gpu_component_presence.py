@@ -1,0 +1,123 @@
+"""Per-entity component presence (BGR_STRATEGY_OPTIONAL) against the oracle: the four-way match of
+ComponentSnapshotPlugin::load (component_snapshot.rs:99-115), save / checksum / system queries that only see entities
+having the component, across tile boundaries and through a SyncTest-shaped run."""
+import numpy as np
+import pytest
+
+from bevy_ggrs_b200 import capi
+from bevy_ggrs_b200.capi import BgrError
+from bevy_ggrs_b200.engine import Engine
+from bevy_ggrs_b200.session import ADVANCE, LOAD, SAVE, Request
+from oracle_backend import OracleWorld
+
+pytestmark = pytest.mark.gpu
+NOSESS = (capi.BGR_SESSION_NONE, 0, 0, 0)
+OPT = capi.BGR_STRATEGY_OPTIONAL
+
+
+def _pair(n, depth=8):
+    """Score (optional, checksummed, +1 per frame), Health (optional, satsub-despawn), Tag (always present, checksummed)."""
+    worlds, cols = [], None
+    for w in (Engine(max_entities=n + 8, max_depth=depth), OracleWorld()):
+        score = w.rollback_component("Score", 4, capi.BGR_STRATEGY_COPY | OPT)
+        health = w.rollback_component("Health", 4, capi.BGR_STRATEGY_CLONE | OPT)
+        tag = w.rollback_component("Tag", 12, capi.BGR_STRATEGY_COPY)
+        w.checksum_component(score, 0, 4)
+        w.checksum_component(tag, 0, 12)
+        w.checksum_component(health, 0, 4)
+        w.add_system(capi.BGR_SYS_U32_ADD, [score], [0, 1])
+        w.add_system(capi.BGR_SYS_U32_SATSUB_DESPAWN, [health], [0, 1])
+        w.build()
+        w.spawn(n)
+        rng = np.random.default_rng(5)
+        w.write_component(score, 0, rng.integers(0, 1000, n, dtype=np.uint32))
+        w.write_component(health, 0, rng.integers(3, 40, n, dtype=np.uint32))
+        w.write_component(tag, 0, rng.integers(0, 2**32, (n, 3), dtype=np.uint32))
+        worlds.append(w)
+        cols = (score, health, tag)
+    return worlds[0], worlds[1], cols
+
+
+def _same(eng, orc, cols, n):
+    alive_e = eng.read_alive(0, n).astype(bool)
+    for c in cols:
+        vo, ho = orc.read_component_alive(c, 0, n)
+        he = eng.has_component(c, 0, n).astype(bool)
+        assert np.array_equal(he, ho.astype(bool)), f"presence of column {c}"
+        assert np.array_equal(eng.read_component(c, 0, n)[he], vo[he]), f"values of column {c}"
+    assert np.array_equal(alive_e, orc.read_alive(0, n).astype(bool))
+
+
+def test_optional_columns_take_the_generic_path_and_match_the_oracle():
+    n = 1300  # three tiles, the last one partial
+    eng, orc, cols = _pair(n)
+    score, health, tag = cols
+    both = lambda f, *a: [getattr(w, f)(*a) for w in (eng, orc)]
+    rows = [0, 1, 511, 512, 513, 1023, 1024, 1299]
+    for r in rows[::2]:
+        both("remove_component", score, r)
+    both("remove_component", health, 512)
+    a, b = both("handle_requests", NOSESS, [Request(SAVE, 0), Request(ADVANCE, 0, [0]), Request(SAVE, 1), Request(ADVANCE, 0, [0])])
+    assert a == b and len(a) == 2
+    assert not eng.last_path_fused()
+    _same(eng, orc, cols, n)
+    # change presence after the snapshots: every arm of the four-way match is hit by the Load below
+    for r in rows[1::2]:
+        both("remove_component", score, r)                       # (None, Some) -> insert
+    for r in rows[::2][:2]:
+        both("insert_component", score, r, np.uint32(4242))      # (Some, None) -> remove
+    both("insert_component", health, 512, np.uint32(7))
+    _same(eng, orc, cols, n)
+    a, b = both("handle_requests", NOSESS, [Request(LOAD, 1), Request(ADVANCE, 0, [0]), Request(SAVE, 2)])
+    assert a == b
+    _same(eng, orc, cols, n)
+    # peek: the snapshot of frame 0 holds Score exactly for the rows that had it then
+    vals, had = eng.peek(0, score, 0, n)
+    vo, ho = orc.peek(0, score, 0, n)
+    assert np.array_equal(had.astype(bool), ho.astype(bool)) and 0 < ho.sum() < n
+    assert np.array_equal(vals[ho.astype(bool)], vo[ho.astype(bool)])
+
+
+def test_synctest_shaped_run_with_presence_changes_between_ticks():
+    """Load(f-d), d x (Advance, Save) every tick, with removals / insertions applied between ticks (a system outside
+    GgrsSchedule): rollbacks undo them for the resimulated frames exactly as in the oracle; entities also die (Health)."""
+    n, d = 700, 4
+    SESS = (capi.BGR_SESSION_SYNCTEST, 8, d, 0)  # max_prediction 8: the ring keeps 8 frames, confirmed = frame - d
+    eng, orc, cols = _pair(n)
+    score, health, tag = cols
+    both = lambda f, *a: [getattr(w, f)(*a) for w in (eng, orc)]
+    rng = np.random.default_rng(11)
+    frame = 0
+    for tick in range(14):
+        reqs = []
+        if tick >= d:
+            reqs.append(Request(LOAD, frame - d))
+            for k in range(d):
+                reqs += [Request(ADVANCE, 0, [0]), Request(SAVE, frame - d + k + 1)] if k < d - 1 else [Request(ADVANCE, 0, [0])]
+        reqs += [Request(SAVE, frame), Request(ADVANCE, 0, [0])]
+        a, b = both("handle_requests", SESS, reqs)
+        assert a == b, f"tick {tick}"
+        frame += 1
+        alive = orc.read_alive(0, n).astype(bool)
+        for r in rng.choice(np.flatnonzero(alive), 5, replace=False):
+            col = (score, health)[int(rng.integers(2))]
+            if orc.has_component(col, int(r), 1)[0]:
+                both("remove_component", col, int(r))
+            else:
+                both("insert_component", col, int(r), np.uint32(rng.integers(5, 50)))
+        _same(eng, orc, cols, n)
+    assert 0 < orc.read_alive(0, n).sum() < n  # Health ran out for some entities inside the run
+
+
+def test_presence_api_errors():
+    eng, orc, (score, health, tag) = _pair(10)
+    with pytest.raises(BgrError):
+        eng.remove_component(tag, 0)          # not registered optional
+    with pytest.raises(BgrError):
+        eng.remove_component(score, 10_000)   # row out of range
+    e2 = Engine(max_entities=4, max_depth=2)
+    for i in range(capi.BGR_MAX_OPTIONAL_COLUMNS):
+        e2.rollback_component(f"C{i}", 4, OPT)
+    with pytest.raises(BgrError) as ei:
+        e2.rollback_component("C8", 4, OPT)
+    assert ei.value.status == capi.BGR_ERR_CAPACITY
