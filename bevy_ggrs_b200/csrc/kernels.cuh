@@ -83,6 +83,7 @@ enum ProgFlags : uint32_t {
     PF_PASSIVE_TMA = 8u,         // at most one LOAD and it is ops[0]: passive planes move by TMA bulk copies
     PF_CK_T = 16u, PF_CK_V = 32u, PF_FIN_T = 64u, PF_FIN_V = 128u,  // which bundle columns are checksummed / assert finite
     PF_DYNAMIC_TILES = 256u,     // tiles handed out by an atomic counter instead of a static stride
+    PF_PREFETCH_NEXT = 512u,     // warp 0 pulls the next tile's active planes into L2 while this tile computes
 };
 
 struct PassiveRun { uint32_t off, bytes; };  // inside a tile; adjacent passive planes form one run
@@ -328,6 +329,22 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
             if (use > 0) mbar_wait(&s_empty[slot], (use - 1) & 1u);  // every warp has read the previous occupant
             s_tile[slot] = claimed;
             mbar_arrive(&s_full[slot]);
+        }
+        if (dynamic && (p.flags & PF_PREFETCH_NEXT) && tid < 32) {
+            // the next tile's first touch is a dependent DRAM read at the top of the tile (20 % of all stall samples in
+            // the round-1 profile): pull its active planes (8 word planes + alive = 132 lines) into L2 now
+            const uint32_t nxt = __shfl_sync(0xffffffffu, claimed, 0);
+            if (nxt < p.n_tiles) {
+                const uint8_t* img = p.arena + ((p.flags & PF_READ_LIVE) ? size_t(0) : (size_t(p.ops[0].image_off256) << 8)) + size_t(nxt) * p.tile_bytes;
+                for (uint32_t l = lane; l < 8u * (kPlaneBytes / 128u) + kTileRows / 128u; l += 32u) {
+                    const uint32_t plane = l / (kPlaneBytes / 128u), line = l % (kPlaneBytes / 128u);
+                    const size_t off = plane < 3 ? p.t_off + size_t(plane) * kPlaneBytes
+                                     : plane < 6 ? p.v_off + size_t(plane - 3) * kPlaneBytes
+                                     : plane < 8 ? p.l_off + size_t(plane - 6) * kPlaneBytes
+                                                 : size_t(p.alive_off);
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(img + off + size_t(line) * 128u));
+                }
+            }
         }
 
         uint32_t pend[6] = {0, 0, 0, 0, 0, 0};

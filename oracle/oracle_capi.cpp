@@ -151,6 +151,16 @@ ORC_API int orc_read_component(World* w, uint32_t col, uint32_t first, uint32_t 
         }
     });
 }
+// alive_out[i] = 1 iff an entity with RollbackOrdered index first+i exists (whatever components it has)
+ORC_API int orc_read_alive(World* w, uint32_t first, uint32_t count, uint8_t* alive_out) {
+    return guarded([&] {
+        std::memset(alive_out, 0, count);
+        for (size_t r = 0; r < w->rows(); ++r) {
+            uint64_t ord = w->rollback_ordered.order_of(w->rollback_id[r]);
+            if (ord >= first && ord < uint64_t(first) + count) alive_out[ord - first] = 1;
+        }
+    });
+}
 // commands.entity(e).remove::<C>() / .insert(value) on the entity whose RollbackOrdered index is `order`
 // (the other side of the Option<&mut S::Target> match in component_snapshot.rs:106-115)
 static size_t row_of_order(World* w, uint64_t order) {

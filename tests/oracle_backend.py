@@ -73,6 +73,7 @@ def load_oracle() -> C.CDLL:
         "orc_active_count": (u64, [vp]),
         "orc_write_component": (C.c_int, [vp, u32, u32, u32, vp, u32]),
         "orc_read_component": (C.c_int, [vp, u32, u32, u32, vp, u32, vp]),
+        "orc_read_alive": (C.c_int, [vp, u32, u32, vp]),
         "orc_remove_component": (C.c_int, [vp, u32, u64]),
         "orc_insert_component": (C.c_int, [vp, u32, u64, vp]),
         "orc_peek": (C.c_int, [vp, i32, u32, u32, u32, vp, u32, vp]),
@@ -203,7 +204,9 @@ class OracleWorld:
         return self.read_component_alive(col, first_row, count)[0]
 
     def read_alive(self, first_row, count):
-        return self.read_component_alive(0, first_row, count)[1]
+        alive = np.zeros(count, dtype=np.uint8)
+        self._check(self._lib.orc_read_alive(self._h, first_row, count, alive.ctypes.data))
+        return alive
 
     def rollback_frame_count(self):
         return self._lib.orc_rollback_frame_count(self._h)
