@@ -309,6 +309,12 @@ def run_ours(args):
     # per tick: read 1 image (slot or live) + write one slot per Save + write the live image
     alg_bytes = sum(len(t[4]) + 2 for t in timed) / K * slot_bytes
     achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+    # SURVEY §8(d)'s other accounting, for reference: what the reference's UNFUSED schedule would move for the same
+    # requests (every Save and Load = read + write of an image, every Advance = 64 B/entity); it exceeds the HBM
+    # peak because the fused kernel never moves those bytes
+    n_loads = sum(1 for t in timed for i in range(t[1]) if t[0][i].kind == capi.BGR_REQ_LOAD)
+    unfused_bytes = (sum(2 * len(t[4]) for t in timed) + 2 * n_loads) / K * slot_bytes + 64.0 * n * adv_per_tick
+    achieved_unfused = unfused_bytes / (ms_per_step * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -351,7 +357,10 @@ def run_ours(args):
                             "component columns live in HBM by design and never cross"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "k_particles_program",
-                         "algorithmic_bytes_per_launch": alg_bytes},
+                         "algorithmic_bytes_per_launch": alg_bytes,
+                         "unfused_accounting": {"bytes_per_step": unfused_bytes, "effective_gbs": achieved_unfused,
+                                                "note": "bytes the reference's one-schedule-per-request path would move "
+                                                        "(2S per Save/Load + 64 B per Advance per entity); not a roofline claim"}},
             "synctest_consistent": consistent,
         }
         if cpu:

@@ -191,6 +191,7 @@ struct bgr_engine {
     bool last_fused = false;
     unsigned long long seq = 0;   // sequence number of the last submit (completion flag value)
     int tune_poll = 1;            // collect() spins on the host-mapped flag before falling back to the event
+    int tune_grid = 0;            // experiment: cap the fused kernel's grid (0 = SMs x resident blocks)
     int tune_prefetch = 1;        // L2 prefetch of the next tile's active planes
     int tune_pdl = 0;             // programmatic dependent launch between consecutive fused kernels (measured: +0.8 % at 1M, -14 % at 100k -> off)
     int tune_dynamic = 1;         // dynamic tile scheduling in the fused kernel (measured +5% over a static stride)
@@ -384,6 +385,7 @@ int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int
     int bps = e->occ_cache[vi][si][mi];
     if (e->tune_bps > 0) bps = std::min(e->tune_bps, bps);
     uint32_t grid = std::max(1u, std::min(pp.n_tiles - pp.tile_begin, uint32_t(e->num_sms * bps)));
+    if (e->tune_grid > 0) grid = std::min(grid, uint32_t(e->tune_grid));
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(BLOCK); lc.dynamicSmemBytes = smem; lc.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -957,6 +959,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_dynamic = env_int("BGR_TUNE_DYNAMIC", 1);
     e->tune_pdl = env_int("BGR_TUNE_PDL", 0);
     e->tune_prefetch = env_int("BGR_TUNE_PREFETCH", 1);
+    e->tune_grid = env_int("BGR_TUNE_GRID", 0);
     e->n_chains = std::max(1, std::min(int(bgr_engine::kMaxChains), env_int("BGR_TUNE_CHAINS", 1)));
     if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 2;
     e->st.confirmed = 0;

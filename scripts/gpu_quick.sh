@@ -1,19 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/pf_*.json
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
-run() { name=$1; wl=$2; steps=$3; shift 3; env "$@" timeout 120 python bench.py --workload $wl --steps $steps --warmup 5 --no-cpu-baseline --no-snapshot-bench > gpurun_out/pf_$name.json 2>gpurun_out/pf_$name.err; }
-for rep in 1 2; do
-run 1m_p1_$rep stress_1m_d8 1000 BGR_TUNE_PREFETCH=1
-run 1m_p0_$rep stress_1m_d8 1000 BGR_TUNE_PREFETCH=0
+timeout 600 python -m pytest tests/test_gpu_parity_particles.py -m gpu -x -q 2>&1 | tail -3
+run() { name=$1; n=$2; steps=$3; shift 3; env "$@" timeout 120 python bench.py --entities $n --steps $steps --warmup 5 --no-cpu-baseline --no-snapshot-bench > gpurun_out/pf_$name.json 2>gpurun_out/pf_$name.err; }
+for n in 50000 100000 200000 400000; do
+for v in 1 2 4; do run n${n}_v$v $n 2000 BGR_TUNE_VEC=$v; done
 done
-run 1m_p1_c4 stress_1m_d8 1000 BGR_TUNE_PREFETCH=1 BGR_TUNE_CHAINS=4
-run 1m_p1_m8 stress_1m_d8 1000 BGR_TUNE_PREFETCH=1 BGR_TUNE_MINB=8
-run d16_p1 stress_1m_d16 500 BGR_TUNE_PREFETCH=1
-run d16_p0 stress_1m_d16 500 BGR_TUNE_PREFETCH=0
-run p2p_p1 p2p_1m_maxpred8 500 BGR_TUNE_PREFETCH=1
-run p2p_p0 p2p_1m_maxpred8 500 BGR_TUNE_PREFETCH=0
-run 10m_p1 stress_10m_d32 40 BGR_TUNE_PREFETCH=1
-run 10m_p0 stress_10m_d32 40 BGR_TUNE_PREFETCH=0
+run n100000_v1_m1 100000 2000 BGR_TUNE_VEC=1 BGR_TUNE_MINB=1
 python - <<'PY'
 import json,glob
 for f in sorted(glob.glob('gpurun_out/pf_*.json')):

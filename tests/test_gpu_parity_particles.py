@@ -165,3 +165,17 @@ def test_many_tiles_per_block(monkeypatch, bps, dynamic):
 
 
 test_many_tiles_per_block = pytest.mark.timeout(120)(test_many_tiles_per_block)
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("chains", ["2", "3"])
+def test_chains_split_the_tile_range_without_observable_change(monkeypatch, chains):
+    """BGR_TUNE_CHAINS: the tile range is split over several streams, each with its own accumulators and result
+    block.  Spawns change the partition mid-run (every chain must then wait for all of the previous tick), peeks and
+    column reads interleave main-stream work: checksums, live state and snapshot contents still equal the oracle's."""
+    monkeypatch.setenv("BGR_TUNE_CHAINS", chains)
+    r = run_particles_synctest_pair(3000, 5, 30, seed=8, ttl_lo=4, ttl_hi=60, spawn_rate=200, spawn_ttl=12, peek_check=True)
+    assert r["fused"] and r["checksums_equal"] and r["state_equal"] and r["peek_equal"]
+    assert r["rows"][0] == r["rows"][1] > 3000
+    r = run_particles_synctest_pair(200_000, 3, 8, seed=4, ttl_lo=2, ttl_hi=30)
+    assert r["fused"] and r["checksums_equal"] and r["state_equal"]
