@@ -4,7 +4,8 @@ import numpy as np
 import pytest
 
 from bevy_ggrs_b200 import capi
-from parity_util import run_particles_synctest_pair
+from bevy_ggrs_b200.engine import Engine
+from parity_util import compare_state, run_particles_synctest_pair
 
 pytestmark = pytest.mark.gpu
 
@@ -179,3 +180,50 @@ def test_chains_split_the_tile_range_without_observable_change(monkeypatch, chai
     assert r["rows"][0] == r["rows"][1] > 3000
     r = run_particles_synctest_pair(200_000, 3, 8, seed=4, ttl_lo=2, ttl_hi=30)
     assert r["fused"] and r["checksums_equal"] and r["state_equal"]
+
+
+@pytest.mark.parametrize("group,flags", [(3, 0), (4, 0), (2, capi.BGR_CFG_FORCE_STEPWISE)])
+def test_catch_up_ticks_in_one_request_vector_match_tick_by_tick(group, flags):
+    """run_ggrs_schedules runs several GGRS ticks back to back when a frame was long (schedule_systems.rs:60-82).
+    Handing their request vectors to bgr_handle_requests as ONE vector (several LoadGameState inside) is one fused
+    launch and is observably identical to the oracle executing them one tick at a time: checksums, live state,
+    snapshot contents; particles die and are spawned inside the window."""
+    from bevy_ggrs_b200.session import SAVE, SyncTestSession
+    from bevy_ggrs_b200.stress import populate, register_particles, synth_particles
+    from oracle_backend import OracleWorld
+    n, d, maxp, n_ticks = 2500, 4, 8, 24
+    eng, orc = Engine(max_entities=n + 60 * n_ticks, max_depth=maxp, flags=flags), OracleWorld()
+    cols = None
+    for w in (eng, orc):
+        cols = register_particles(w, spawn_rate=40, spawn_ttl=7)
+        w.build()
+        populate(w, cols, *synth_particles(n, 21, 3, 40))
+    sess = SyncTestSession(2, d, maxp, input_delay=2)
+    vectors = []
+    for t in range(n_ticks):
+        sess.add_local_input(0, (1 << 4) if t % 5 in (1, 2) else 0)   # INPUT_SPAWN
+        sess.add_local_input(1, (1 << 5) if t % 3 == 0 else 0)        # INPUT_NOOP
+        reqs = sess.advance_frame()
+        for r in reqs:
+            if r.kind == SAVE:
+                sess.save_cell(r.frame, 0)   # checksums are compared below, not by the stand-in session
+        vectors.append(reqs)
+    got, want = [], []
+    launches0 = eng.launch_count()
+    for g in range(0, n_ticks, group):
+        merged = [r for v in vectors[g:g + group] for r in v]
+        got += eng.handle_requests(sess.info(), merged)
+        for v in vectors[g:g + group]:
+            want += orc.handle_requests(sess.info(), v)
+    assert got == want and len(got) > n_ticks
+    if not flags:
+        assert eng.last_path_fused() and eng.launch_count() - launches0 == n_ticks // group
+    rows = eng.row_count()
+    assert rows == orc.row_count() > n
+    assert compare_state(eng, orc, cols, rows)
+    assert eng.snapshot_frames() == orc.snapshot_frames()
+    for f in eng.snapshot_frames():
+        for c in cols:
+            pe, po = eng.peek(f, c, 0, rows), orc.peek(f, c, 0, rows)
+            m = po[1].astype(bool)
+            assert np.array_equal(pe[1].astype(bool), m) and np.array_equal(pe[0][m], po[0][m])
