@@ -173,6 +173,7 @@ def run_ours(args):
     fill = max(d, maxp) + 2           # ticks until the request vector has its steady-state shape
     K2 = min(K, 500) if world_size == 1 else 0   # ticks of the host-mirror leg (N = 1 only)
     BT = int(os.environ.get("BENCH_BATCH_TICKS", "4")) if world_size == 1 and d > 0 else 0   # catch-up leg: ticks per request vector
+    BT = min(BT, capi.BGR_MAX_REQUESTS // (2 * d + 2)) if d > 0 else 0                          # ... that fit one call
     K3 = (min(K, 400) // BT) * BT if BT > 1 else 0
     ticks = pregenerate_ticks(fill + W + K + K + K2 + K3, d, maxp)
     history = []

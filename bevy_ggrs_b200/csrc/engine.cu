@@ -191,6 +191,11 @@ struct bgr_engine {
     bool last_fused = false;
     unsigned long long seq = 0;   // sequence number of the last submit (completion flag value)
     int tune_poll = 1;            // collect() spins on the host-mapped flag before falling back to the event
+    int tune_tiledep = 1;         // consecutive fused launches overlap: per-tile dependencies instead of grid-level (PF_TILE_WAIT)
+    unsigned int* d_tile_done = nullptr;  // [tiles] see ProgramParams::tile_done
+    unsigned int* d_tile_cnt = nullptr;
+    bool tiledep_chain = false;   // the last operation enqueued on the main stream was a PF_TILE_SIGNAL launch
+    uint32_t tiledep_seq = 0, tiledep_tiles = 0;
     int tune_grid = 0;            // experiment: cap the fused kernel's grid (0 = SMs x resident blocks)
     int tune_prefetch = 1;        // L2 prefetch of the next tile's active planes
     int tune_pdl = 0;             // programmatic dependent launch between consecutive fused kernels (measured: +0.8 % at 1M, -14 % at 100k -> off)
@@ -390,7 +395,7 @@ int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int
     lc.gridDim = dim3(grid); lc.blockDim = dim3(BLOCK); lc.dynamicSmemBytes = smem; lc.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = e->tune_pdl ? 1 : 0;
+    attr[0].val.programmaticStreamSerializationAllowed = (e->tune_pdl || (pp.flags & PF_TILE_WAIT)) ? 1 : 0;
     lc.attrs = attr; lc.numAttrs = 1;
     CUDA_TRY(cudaLaunchKernelEx(&lc, kern, pp));
     CUDA_TRY(cudaGetLastError());
@@ -455,11 +460,23 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
         for (uint32_t c = 0; c < chains; ++c) CUDA_TRY(cudaStreamWaitEvent(e->chain_stream[c], e->main_ev, 0));
         e->main_dirty = false;
     }
+    // only worth it when request vectors are queued behind each other (bgr_submit_requests with others un-collected):
+    // a synchronous caller collects before the next submit, so there is nothing to overlap with
+    const bool tiledep = e->tune_tiledep && chains == 1 && e->d_tile_done && (e->tune_tiledep > 1 || !e->pending.empty());
+    if (tiledep) {
+        pp.flags |= PF_TILE_SIGNAL;
+        pp.grid_done = e->d_tile_done + e->tiles_for(e->cfg.max_entities);  // the extra word behind the per-tile flags
+        pp.tile_done = e->d_tile_done; pp.tile_cnt = e->d_tile_cnt;
+        pp.done_seq = uint32_t(e->seq);
+        if (e->tiledep_chain) { pp.flags |= PF_TILE_WAIT; pp.wait_seq = e->tiledep_seq; pp.wait_tiles = e->tiledep_tiles; }
+    }
     for (uint32_t c = 0; c < chains; ++c) {
         pp.tile_begin = uint32_t(uint64_t(total_tiles) * c / chains);
         pp.n_tiles = uint32_t(uint64_t(total_tiles) * (c + 1) / chains);
-        pp.accum = e->d_accum_c[c];
-        pp.ticket = e->d_ticket_c[c];
+        // overlapping launches (tile dependencies) must not share accumulators / tickets: rotate over four sets
+        const uint32_t set = tiledep ? uint32_t(e->seq & 3u) : c;
+        pp.accum = e->d_accum_c[set];
+        pp.ticket = e->d_ticket_c[set];
         pp.out = e->d_out[buf] + size_t(c) * kResultStride;
         cudaStream_t stream = chains > 1 ? e->chain_stream[c] : e->stream;
         int rc = launch_fused_variant(e, pp, stream);
@@ -469,6 +486,8 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
             CUDA_TRY(cudaStreamWaitEvent(e->stream, e->chain_ev[c], 0));
         }
     }
+    e->tiledep_chain = tiledep;
+    e->tiledep_seq = uint32_t(e->seq); e->tiledep_tiles = total_tiles;
     return BGR_OK;
 }
 
@@ -531,6 +550,7 @@ int launch_tma(bgr_engine* e, const uint8_t* src, uint8_t* dst, uint32_t n_rows_
 // ---------------------------------------------------------------------------------------------
 int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
     e->main_dirty = true;
+    e->tiledep_chain = false;
     uint32_t live_rows = pg.live_rows;
     uint8_t* live = e->image(0);
     for (uint32_t i = 0; i < pg.n_ops; ++i) {
@@ -667,7 +687,8 @@ int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs,
     uint32_t chains = 1;
     rc = fused ? run_fused(e, pg, buf, &chains) : run_stepwise(e, pg, buf);
     if (rc != BGR_OK) return rc;
-    CUDA_TRY(cudaEventRecord(e->ev[buf], e->stream));
+    // an event between two launches would serialise them; with host polling it is only a fallback, taken lazily
+    if (!(e->tune_tiledep && e->tune_poll)) CUDA_TRY(cudaEventRecord(e->ev[buf], e->stream));
     e->last_fused = fused;
     e->st = s;
     Pending pd;
@@ -706,7 +727,11 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
                 __builtin_ia32_pause();
             }
         }
-        if (!done) { CUDA_TRY(cudaEventSynchronize(e->ev[pd.buf])); break; }  // the event is ordered after every chain
+        if (!done) {  // the event / the stream is ordered after every chain
+            if (e->tune_tiledep && e->tune_poll) CUDA_TRY(cudaStreamSynchronize(e->stream));
+            else CUDA_TRY(cudaEventSynchronize(e->ev[pd.buf]));
+            break;
+        }
     }
     // fold the chains' result blocks: XOR the column words, sum the live-row counts, OR the flags
     unsigned long long folded[kMaxSaves * kAccStride];
@@ -746,6 +771,7 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
 }
 
 int drain(bgr_engine* e) {
+    e->tiledep_chain = false;  // callers enqueue ordinary (fully ordered) work next
     while (!e->pending.empty()) {
         int rc = collect(e, nullptr, 0, nullptr);
         if (rc != BGR_OK && rc != BGR_ERR_NON_FINITE) return rc;
@@ -850,6 +876,7 @@ int download_begin(bgr_engine* e, uint32_t column, uint32_t off, uint32_t len, u
         e->launches += 1;
         CUDA_TRY(cudaGetLastError());
         e->main_dirty = true;  // later chain launches overwrite the live image this kernel reads
+        e->tiledep_chain = false;
         CUDA_TRY(cudaEventRecord(d.packed, e->stream));
         CUDA_TRY(cudaStreamWaitEvent(e->copy_stream, d.packed, 0));
         CUDA_TRY(cudaMemcpyAsync(host, d.d_buf, bytes, cudaMemcpyDeviceToHost, e->copy_stream));
@@ -960,6 +987,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_pdl = env_int("BGR_TUNE_PDL", 0);
     e->tune_prefetch = env_int("BGR_TUNE_PREFETCH", 1);
     e->tune_grid = env_int("BGR_TUNE_GRID", 0);
+    e->tune_tiledep = env_int("BGR_TUNE_TILEDEP", 1);
     e->n_chains = std::max(1, std::min(int(bgr_engine::kMaxChains), env_int("BGR_TUNE_CHAINS", 1)));
     if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 2;
     e->st.confirmed = 0;
@@ -982,6 +1010,8 @@ BGR_API void bgr_engine_destroy(bgr_engine* e) {
     if (e->d_accum) cudaFree(e->d_accum);
     if (e->d_ticket) cudaFree(e->d_ticket);
     if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+    if (e->d_tile_done) cudaFree(e->d_tile_done);
+    if (e->d_tile_cnt) cudaFree(e->d_tile_cnt);
     for (auto& d : e->dl) {
         if (d.d_buf) cudaFree(d.d_buf);
         if (d.packed) cudaEventDestroy(d.packed);
@@ -1117,6 +1147,13 @@ BGR_API int bgr_build(bgr_engine* e) {
     for (int c = 0; c < bgr_engine::kMaxChains; ++c) {
         e->d_accum_c[c] = e->d_accum + size_t(c) * kMaxSaves * kAccStride;
         e->d_ticket_c[c] = e->d_ticket + 4 * c;
+    }
+    if (e->tune_tiledep) {
+        const size_t nt = size_t(e->tiles_for(e->cfg.max_entities)) + 1;
+        CUDA_TRY(cudaMalloc(&e->d_tile_done, nt * sizeof(unsigned int)));
+        CUDA_TRY(cudaMalloc(&e->d_tile_cnt, nt * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemsetAsync(e->d_tile_done, 0, nt * sizeof(unsigned int), e->stream));
+        CUDA_TRY(cudaMemsetAsync(e->d_tile_cnt, 0, nt * sizeof(unsigned int), e->stream));
     }
     if (e->n_chains > 1) {
         for (int c = 0; c < e->n_chains; ++c) {

@@ -84,6 +84,12 @@ enum ProgFlags : uint32_t {
     PF_CK_T = 16u, PF_CK_V = 32u, PF_FIN_T = 64u, PF_FIN_V = 128u,  // which bundle columns are checksummed / assert finite
     PF_DYNAMIC_TILES = 256u,     // tiles handed out by an atomic counter instead of a static stride
     PF_PREFETCH_NEXT = 512u,     // warp 0 pulls the next tile's active planes into L2 while this tile computes
+    PF_TILE_SIGNAL = 1024u,      // announce each block's FIRST tile in tile_done[] as soon as its stores are visible, and the
+                                 // whole launch in *grid_done: what the next launch's first wave needs to start early
+    PF_TILE_WAIT = 2048u,        // the previous launch on the stream was a PF_TILE_SIGNAL launch: start without waiting for
+                                 // its grid (no griddepcontrol.wait) and wait per tile for tile_done[tile] or grid_done >=
+                                 // wait_seq instead.  Tile i of tick k+1 only depends on tile i of tick k, so this grid's
+                                 // first wave runs in the previous grid's tail instead of after it.
 };
 
 struct PassiveRun { uint32_t off, bytes; };  // inside a tile; adjacent passive planes form one run
@@ -98,6 +104,10 @@ struct ProgramParams {
     unsigned long long seq;     // written to out[kSeqIndex] after the results (completion flag the host polls)
     uint32_t words, tile_bytes, n_ops, n_saves;
     uint32_t tile_begin, n_tiles;  // this launch covers tiles [tile_begin, n_tiles) (one chain of the entity range)
+    unsigned int* tile_done;       // [tiles] sequence number of the last PF_TILE_SIGNAL launch that finished the tile
+    unsigned int* tile_cnt;        // [tiles] warps of the current launch that finished the tile
+    unsigned int* grid_done;       // sequence number of the last PF_TILE_SIGNAL launch that completed entirely
+    uint32_t done_seq, wait_seq, wait_tiles;  // PF_TILE_WAIT: tiles < wait_tiles wait for tile_done >= wait_seq
     uint32_t live_rows, flags;
     uint32_t t_off, v_off, l_off, alive_off;  // byte offsets inside a tile of Transform / Velocity / Ttl word 0 / alive plane
     uint32_t ck_t_slot, ck_v_slot;            // accumulator column of each checksummed type
@@ -174,6 +184,18 @@ __device__ __forceinline__ void tma_store_1d(void* gdst, const void* smem_src, u
                  ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const unsigned int* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(unsigned int* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// release / acquire fence at gpu scope (MEMBAR.ALL.GPU): __threadfence() is the sequentially-consistent one
+// (MEMBAR.SC.GPU + ERRBAR + L1 invalidate), several times more expensive and not needed for a flag hand-off
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence.proxy.async;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -243,7 +265,8 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     __syncthreads();
 
     // ... while this grid touches no global memory before the previous grid has completed and flushed
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const bool tile_wait = (p.flags & PF_TILE_WAIT) != 0, tile_signal = (p.flags & PF_TILE_SIGNAL) != 0;
+    if (!tile_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
 
     const uint32_t i0 = tid * VEC;  // first row of this thread inside the tile
     // Dynamic tile hand-off WITHOUT a block barrier: at the top of a tile thread 0 claims the block's NEXT tile
@@ -266,8 +289,30 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     // iteration 0 runs tile blockIdx.x and never enters the ring
     uint32_t claimed = 0;        // thread 0: tile claimed for iteration it + 1
     uint32_t it = 0;
+    // PF_TILE_SIGNAL: a fence per announced tile stalls the warp until its stores are acknowledged (8 % when every tile
+    // was announced), so only the first tile of each block is — the tiles the next grid's first wave starts with
+    auto signal_tile = [&](uint32_t t) {
+        if (use_tma && tid == 0) tma_wait_all();  // that tile's bulk stores have landed (not just released their buffer)
+        fence_acq_rel_gpu();                      // every thread's stores are visible gpu-wide before its warp arrives
+        __syncwarp();
+        if (lane == 0) {
+            if (atomicAdd(&p.tile_cnt[t], 1u) == BLOCK / 32 - 1) {  // last warp of the block to announce this tile
+                p.tile_cnt[t] = 0u;
+                fence_acq_rel_gpu();
+                st_release_gpu(&p.tile_done[t], p.done_seq);
+            }
+        }
+    };
     for (uint32_t tile = p.tile_begin + blockIdx.x; tile < p.n_tiles; ++it) {
         if (dynamic && tid == 0) claimed = p.tile_begin + gridDim.x + atomicAdd(&p.ticket[1], 1u);  // published after the loads below
+        if (tile_wait && tile < p.wait_tiles) {
+            // the previous tick's kernel may still be running: this tile's images are complete once it has signalled
+            if (lane == 0)
+                while (int32_t(ld_acquire_gpu(&p.tile_done[tile]) - p.wait_seq) < 0 &&
+                       int32_t(ld_acquire_gpu(p.grid_done) - p.wait_seq) < 0) __nanosleep(100);
+            __syncwarp();
+            if (tid == 0) fence_proxy_async_global();  // ... also for the bulk (async-proxy) loads below
+        }
         const size_t tile_off = size_t(tile) * p.tile_bytes;
         const uint32_t row0 = tile * kTileRows + i0;
         const size_t woff = tile_off + size_t(i0) * 4u;  // + plane offset (+ image offset) = address of this thread's words
@@ -499,6 +544,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                 }
             }
         }
+        if (tile_signal && it == 0) signal_tile(tile);
         if (dynamic) {
             const uint32_t slot = it % kRing, use = it / kRing;  // entry of iteration it + 1
             mbar_wait(&s_full[slot], use & 1u);
@@ -533,6 +579,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         __threadfence_system();
         __syncthreads();
         if (tid == 0) {
+            if (tile_signal) st_release_gpu(p.grid_done, p.done_seq);  // every block's stores precede its ticket (fence above)
             p.ticket[0] = 0u;
             p.ticket[1] = 0u;
             *reinterpret_cast<volatile unsigned long long*>(&p.out[kSeqIndex]) = p.seq;  // host polls this word

@@ -1,13 +1,15 @@
 #!/bin/bash
 mkdir -p gpurun_out; rm -f gpurun_out/pf_*.json
-for bt in 2 4; do
-BENCH_BATCH_TICKS=$bt timeout 120 python bench.py --steps 400 --warmup 5 --no-cpu-baseline --no-snapshot-bench > gpurun_out/pf_bt$bt.json 2>gpurun_out/pf_bt$bt.err
-python - <<PY
-import json
-try:
-    d=json.loads([l for l in open('gpurun_out/pf_bt$bt.json') if l.startswith('{')][0])
-    print("bt$bt ms=%.4f"%d['ms_per_step'], d.get('batched_ticks_experiment'), d['synctest_consistent'])
-except Exception as e:
-    print("FAILED", e, open('gpurun_out/pf_bt$bt.err').read()[-500:])
+BGR_TUNE_TILEDEP=9 timeout 400 python -m pytest tests/test_gpu_parity_particles.py -m gpu -x -q -k "pipelined_submits or catch_up" 2>&1 | tail -3
+run() { name=$1; wl=$2; steps=$3; shift 3; env "$@" timeout 60 python bench.py --workload $wl --steps $steps --warmup 5 --no-cpu-baseline --no-snapshot-bench > gpurun_out/pf_$name.json 2>gpurun_out/pf_$name.err; echo "$name rc=$?"; }
+for td in 0 5 9 11 13; do run 1m_td$td stress_1m_d8 1000 BGR_TUNE_TILEDEP=$td; done
+for td in 5 9; do run 100k_td$td stress_100k_d8 2000 BGR_TUNE_TILEDEP=$td; run p2p_td$td p2p_1m_maxpred8 500 BGR_TUNE_TILEDEP=$td; run d16_td$td stress_1m_d16 500 BGR_TUNE_TILEDEP=$td; done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/pf_*.json')):
+    try:
+        d=json.loads([l for l in open(f) if l.startswith('{')][0])
+        print(f, "ms=%.4f frac=%.3f e2e=%.0f ok=%s"%(d['ms_per_step'],d['roofline']['frac'],d['e2e']['value'],d['synctest_consistent']), (d.get('catch_up_batch') or {}).get('ms_per_tick'))
+    except Exception as e:
+        print(f, "FAILED", open(f.replace('.json','.err')).read()[-300:])
 PY
-done

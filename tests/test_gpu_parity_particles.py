@@ -227,3 +227,56 @@ def test_catch_up_ticks_in_one_request_vector_match_tick_by_tick(group, flags):
             pe, po = eng.peek(f, c, 0, rows), orc.peek(f, c, 0, rows)
             m = po[1].astype(bool)
             assert np.array_equal(pe[1].astype(bool), m) and np.array_equal(pe[0][m], po[0][m])
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("tiledep", ["0", "1", "2"])
+@pytest.mark.parametrize("n,spawn", [(3000, 40), (300_000, 0)])
+def test_pipelined_submits_overlap_without_observable_change(monkeypatch, tiledep, n, spawn):
+    """Four request vectors in flight (bgr_submit_requests / bgr_collect).  With BGR_TUNE_TILEDEP=1 consecutive fused
+    launches overlap on the GPU: tile i of tick k+1 starts as soon as tile i of tick k has signalled, not when the
+    whole grid of tick k is done.  Checksums of every tick, the final world and every snapshot equal the oracle's.
+    A dependency bug hangs or corrupts: bounded by pytest-timeout."""
+    from bevy_ggrs_b200.session import SAVE, SyncTestSession
+    from bevy_ggrs_b200.stress import populate, register_particles, synth_particles
+    from oracle_backend import OracleWorld
+    monkeypatch.setenv("BGR_TUNE_TILEDEP", tiledep)
+    d, maxp, n_ticks = 3, 8, 30 if n < 100_000 else 12
+    eng, orc = Engine(max_entities=n + (spawn + 1) * n_ticks, max_depth=maxp), OracleWorld()
+    cols = None
+    for w in (eng, orc):
+        cols = register_particles(w, spawn_rate=spawn, spawn_ttl=7) if spawn else register_particles(w)
+        w.build()
+        populate(w, cols, *synth_particles(n, 33, 3, 40))
+    sess = SyncTestSession(2, d, maxp, input_delay=2)
+    vectors = []
+    for t in range(n_ticks):
+        sess.add_local_input(0, (1 << 4) if (spawn and t % 5 in (1, 2)) else 0)
+        sess.add_local_input(1, (1 << 5) if t % 3 == 0 else 0)
+        reqs = sess.advance_frame()
+        for r in reqs:
+            if r.kind == SAVE:
+                sess.save_cell(r.frame, 0)
+        vectors.append(reqs)
+    got, want, inflight = [], [], 0
+    for v in vectors:
+        eng.submit_requests(sess.info(), v)
+        inflight += 1
+        if inflight == 4:
+            got += eng.collect()
+            inflight -= 1
+        want += orc.handle_requests(sess.info(), v)
+    while inflight:
+        got += eng.collect()
+        inflight -= 1
+    assert got == want and len(got) >= n_ticks
+    assert eng.last_path_fused()
+    rows = eng.row_count()
+    assert rows == orc.row_count()
+    assert compare_state(eng, orc, cols, rows)
+    assert eng.snapshot_frames() == orc.snapshot_frames()
+    for f in eng.snapshot_frames()[:3]:
+        for c in cols:
+            pe, po = eng.peek(f, c, 0, rows), orc.peek(f, c, 0, rows)
+            m = po[1].astype(bool)
+            assert np.array_equal(pe[1].astype(bool), m) and np.array_equal(pe[0][m], po[0][m])
