@@ -69,6 +69,9 @@ pub struct B200Columns(pub bevy::platform::collections::HashMap<std::any::TypeId
 pub trait B200RollbackApp {
     fn rollback_component_with_copy_b200<T: Component + Copy + bytemuck::Pod>(&mut self) -> &mut Self;
     fn rollback_component_with_clone_b200<T: Component + Clone + bytemuck::Pod>(&mut self) -> &mut Self;
+    /// Same, for a component that single entities may lose / regain inside the rollback window
+    /// (`Option<&mut S::Target>` in `ComponentSnapshotPlugin::load`, component_snapshot.rs:99-115).
+    fn rollback_optional_component_with_copy_b200<T: Component + Copy + bytemuck::Pod>(&mut self) -> &mut Self;
     /// `checksum_component::<T>(hasher)` where the hasher is "seahash of bytes [offset, offset+len) of T"
     fn checksum_component_b200<T: Component>(&mut self, offset: u32, len: u32, assert_finite: bool) -> &mut Self;
 }
@@ -88,6 +91,10 @@ impl B200RollbackApp for App {
     }
     fn rollback_component_with_clone_b200<T: Component + Clone + bytemuck::Pod>(&mut self) -> &mut Self {
         register::<T>(self, sys::BGR_STRATEGY_CLONE);
+        self
+    }
+    fn rollback_optional_component_with_copy_b200<T: Component + Copy + bytemuck::Pod>(&mut self) -> &mut Self {
+        register::<T>(self, sys::BGR_STRATEGY_COPY | sys::BGR_STRATEGY_OPTIONAL);
         self
     }
     fn checksum_component_b200<T: Component>(&mut self, offset: u32, len: u32, assert_finite: bool) -> &mut Self {
@@ -158,4 +165,62 @@ pub fn download_column<T: Component + bytemuck::Pod>(world: &World, first_row: u
     check(unsafe {
         sys::bgr_read_component(engine, col, first_row, out.len() as u32, out.as_mut_ptr().cast(), core::mem::size_of::<T>() as u32)
     });
+}
+
+/// `commands.entity(e).remove::<T>()` for a component registered with `rollback_optional_component_with_copy_b200`
+/// (`row` = the entity's `RollbackOrdered` index).
+pub fn remove_component<T: Component>(world: &World, row: u32) {
+    let col = world.resource::<B200Columns>().0[&std::any::TypeId::of::<T>()];
+    check(unsafe { sys::bgr_remove_component(world.non_send_resource::<B200Engine>().0, col, row) });
+}
+
+/// `commands.entity(e).insert(value)` for an optional component.
+pub fn insert_component<T: Component + bytemuck::Pod>(world: &World, row: u32, value: &T) {
+    let col = world.resource::<B200Columns>().0[&std::any::TypeId::of::<T>()];
+    check(unsafe { sys::bgr_insert_component(world.non_send_resource::<B200Engine>().0, col, row, (value as *const T).cast()) });
+}
+
+/// Page-locked double buffer for the per-tick mirror of one field range of a component (INTEGRATION.md "Per-tick mirror").
+pub struct B200Mirror {
+    pub bufs: [*mut u8; 2],
+    pub bytes_per_row: u32,
+    pub rows: u32,
+    pub in_flight: Option<(u32, usize)>, // (ticket, buffer index)
+}
+
+impl B200Mirror {
+    pub fn new(rows: u32, bytes_per_row: u32) -> Self {
+        let mut bufs = [core::ptr::null_mut::<u8>(); 2];
+        for b in bufs.iter_mut() {
+            let mut p: *mut core::ffi::c_void = core::ptr::null_mut();
+            check(unsafe { sys::bgr_host_alloc(rows as usize * bytes_per_row as usize, &mut p) });
+            *b = p.cast();
+        }
+        Self { bufs, bytes_per_row, rows, in_flight: None }
+    }
+    /// End of `run_ggrs_schedules`: start mirroring bytes [offset, offset + bytes_per_row) of every `T`; returns at once.
+    pub fn begin<T: Component>(&mut self, world: &World, offset: u32, frame: usize) {
+        let col = world.resource::<B200Columns>().0[&std::any::TypeId::of::<T>()];
+        let mut ticket = 0u32;
+        let idx = frame & 1;
+        check(unsafe {
+            sys::bgr_download_begin(world.non_send_resource::<B200Engine>().0, col, offset, self.bytes_per_row, 0, self.rows,
+                                    self.bufs[idx].cast(), &mut ticket)
+        });
+        self.in_flight = Some((ticket, idx));
+    }
+    /// Before the first host-side reader (e.g. sprite extraction): the previous `begin`'s bytes are now readable.
+    pub fn wait(&mut self, world: &World) -> Option<&[u8]> {
+        let (ticket, idx) = self.in_flight.take()?;
+        check(unsafe { sys::bgr_download_wait(world.non_send_resource::<B200Engine>().0, ticket) });
+        Some(unsafe { core::slice::from_raw_parts(self.bufs[idx], self.rows as usize * self.bytes_per_row as usize) })
+    }
+}
+
+impl Drop for B200Mirror {
+    fn drop(&mut self) {
+        for b in self.bufs {
+            unsafe { sys::bgr_host_free(b.cast()) };
+        }
+    }
 }
