@@ -181,6 +181,13 @@ class App:
     def rollback_component_with_clone(self, type_name: str, size_of: int) -> int:
         return self.world.rollback_component(type_name, size_of, capi.BGR_STRATEGY_CLONE)
 
+    def rollback_optional_component_with_copy(self, type_name: str, size_of: int) -> int:
+        """A component single entities may lose / regain inside the rollback window: the ``Option<&mut S::Target>``
+        match of ``ComponentSnapshotPlugin::load`` (component_snapshot.rs:99-115).  ``world.remove_component`` /
+        ``world.insert_component`` are the ``commands.entity(e).remove::<T>()`` / ``.insert(t)`` of code outside
+        ``GgrsSchedule``."""
+        return self.world.rollback_component(type_name, size_of, capi.BGR_STRATEGY_COPY | capi.BGR_STRATEGY_OPTIONAL)
+
     def checksum_component(self, column: int, byte_offset: int, byte_len: int, assert_finite: bool = False) -> "App":
         self.world.checksum_component(column, byte_offset, byte_len,
                                       capi.BGR_HASH_FLAG_ASSERT_FINITE_F32 if assert_finite else 0)

@@ -49,3 +49,39 @@ def test_checksum_only_covers_entities_that_have_the_component():
     assert a.handle_requests(NOSESS, [Request(SAVE, 0)]) == b.handle_requests(NOSESS, [Request(SAVE, 0)])
     c, sc = _world()
     assert c.handle_requests(NOSESS, [Request(SAVE, 0)]) != a.handle_requests(NOSESS, [Request(SAVE, 0)])
+
+
+def test_app_synctest_rollback_reinserts_and_removes_optional_components():
+    """Through the plugin mirror (App) on the oracle backend — the same scenario tests/cpp/test_host_mirror.cpp runs on
+    the engine: a component removed by code outside GgrsSchedule comes back with the next rollback (resimulated from the
+    snapshot, so Score == RollbackFrameCount), one inserted there disappears again, and SyncTest never sees a mismatch."""
+    from bevy_ggrs_b200.plugin import (App, GgrsPlugin, GgrsSchedule, LocalInputs, ReadInputs, Session, Startup,
+                                       SyncTestMismatch, System)
+    from bevy_ggrs_b200.session import SyncTestSession
+    w = OracleWorld()
+    app = App(w)
+    app.add_plugins(GgrsPlugin())
+    app.add_systems(ReadInputs, lambda a: a.insert_resource(LocalInputs({h: 0 for h in a.local_players.handles})))
+    score = app.rollback_optional_component_with_copy("Score", 4)
+    health = app.rollback_optional_component_with_copy("Health", 4)
+    app.checksum_component_with_hash(score)
+    app.add_systems(GgrsSchedule, System(capi.BGR_SYS_U32_ADD, [score], [0, 1]))
+
+    def startup(a):
+        a.world.spawn(2)
+        a.world.remove_component(health, 1)
+    app.add_systems(Startup, startup)
+    app.insert_resource(Session.SyncTest(SyncTestSession(1, 3, 8, input_delay=0)))
+    mism = []
+    app.add_observer(SyncTestMismatch, lambda ev: mism.append(ev))
+    for _ in range(10):
+        app.update()
+    assert w.has_component(score, 0, 2).tolist() == [1, 1] and w.has_component(health, 0, 2).tolist() == [1, 0]
+    w.remove_component(score, 0)
+    w.insert_component(health, 1, np.uint32(77))
+    assert w.has_component(score, 0, 2).tolist() == [0, 1] and w.has_component(health, 0, 2).tolist() == [1, 1]
+    app.update()
+    assert w.has_component(score, 0, 2).tolist() == [1, 1] and w.has_component(health, 0, 2).tolist() == [1, 0]
+    vals = w.read_component(score, 0, 2).view(np.uint32).ravel()
+    assert vals[0] == vals[1] == app.rollback_frame_count()
+    assert not mism
