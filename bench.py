@@ -188,9 +188,15 @@ def run_ours(args):
         from bevy_ggrs_b200.sharded import PartialBuffer, all_fold_array
         pbuf = PartialBuffer(64 * (maxp + 2))
 
+    # the exchange (H2D of the partials, all_gather, D2H) runs on its own stream: on the engine's stream its
+    # synchronising D2H copy would drain the whole queue of submitted ticks every time
+    xchg_stream = torch.cuda.Stream(device=dev) if sharded else None
+
     def flush_partials():
         if pbuf.n:
-            history.extend(all_fold_array(pbuf.take(), device=dev))
+            with torch.cuda.stream(xchg_stream):
+                folded = all_fold_array(pbuf.take(), device=dev)
+            history.extend(folded)
 
     def collect_one():
         if sharded:
