@@ -463,6 +463,12 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
     // only worth it when request vectors are queued behind each other (bgr_submit_requests with others un-collected):
     // a synchronous caller collects before the next submit, so there is nothing to overlap with
     const bool tiledep = e->tune_tiledep && chains == 1 && e->d_tile_done && (e->tune_tiledep > 1 || !e->pending.empty());
+    if (e->tiledep_chain && total_tiles != e->tiledep_tiles) {
+        // The tile range changed (rows crossed a tile boundary): a tile outside the previous launch's range may still be
+        // in use by an OLDER overlapping launch that nothing would make this one wait for.  Rare: drain the stream.
+        CUDA_TRY(cudaStreamSynchronize(e->stream));
+        e->tiledep_chain = false;
+    }
     if (tiledep) {
         pp.flags |= PF_TILE_SIGNAL;
         pp.grid_done = e->d_tile_done + e->tiles_for(e->cfg.max_entities);  // the extra word behind the per-tile flags
@@ -473,8 +479,11 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
     for (uint32_t c = 0; c < chains; ++c) {
         pp.tile_begin = uint32_t(uint64_t(total_tiles) * c / chains);
         pp.n_tiles = uint32_t(uint64_t(total_tiles) * (c + 1) / chains);
-        // overlapping launches (tile dependencies) must not share accumulators / tickets: rotate over four sets
-        const uint32_t set = tiledep ? uint32_t(e->seq & 3u) : c;
+        // overlapping launches (tile dependencies) must not share accumulators / tickets: rotate over kBufs sets — at
+        // most kBufs request vectors are un-collected, so a set is re-armed (before its launch's completion word is
+        // written) long before the launch kBufs later touches it
+        static_assert(bgr_engine::kMaxChains >= bgr_engine::kBufs, "one accumulator set per in-flight request vector");
+        const uint32_t set = tiledep ? uint32_t(e->seq % bgr_engine::kBufs) : c;
         pp.accum = e->d_accum_c[set];
         pp.ticket = e->d_ticket_c[set];
         pp.out = e->d_out[buf] + size_t(c) * kResultStride;
