@@ -288,8 +288,7 @@ def run_ours(args):
         # ---------------- e2e with a host mirror: every tick also downloads Transform.translation ----------------
         # What a host-resident ECS needs back per tick to draw the particles (INTEGRATION.md "mirror"): 12 B/entity
         # packed on the GPU, copied D2H on a copy stream into page-locked memory while the next tick runs.
-        mirror = None
-        if K2:
+        def mirror_leg():
             m_ticks = ticks[fill + W + K + K: fill + W + K + K + K2]
             bufs = [eng.host_alloc(n, 12), eng.host_alloc(n, 12)]
             pending = None
@@ -309,9 +308,16 @@ def run_ours(args):
                       "d2h_gbs": 12 * n * K2 / m_s / 1e9,
                       "note": "e2e + bgr_download_begin/wait of Transform.translation (12 B/entity) every tick, "
                               "double-buffered pinned host memory; PCIe-bound when 12 B x entities / tick exceeds the link"}
+            return mirror
 
-        batched = None
-        if K3:
+        mirror = None
+        if K2:
+            try:
+                mirror = mirror_leg()
+            except Exception as exc:  # an optional leg must not cost the headline line
+                mirror = {"error": repr(exc)}
+
+        def batch_leg():
             # catch-up shape of run_ggrs_schedules' inner loop (schedule_systems.rs:60-82): several ticks' request
             # vectors handed over in one call
             b_ticks = ticks[fill + W + K + K + K2:]
@@ -339,6 +345,14 @@ def run_ours(args):
                        "note": "NOT the headline: several ticks' request vectors per bgr_handle_requests call (the catch-up "
                                "shape of run_ggrs_schedules' inner loop); one launch per call, the live image is written "
                                "once per call"}
+            return batched
+
+        batched = None
+        if K3:
+            try:
+                batched = batch_leg()
+            except Exception as exc:
+                batched = {"error": repr(exc)}
 
     consistent = check_synctest_consistency(history)
     fused = eng.last_path_fused()
