@@ -130,3 +130,44 @@ def test_box_game_synctest_c1_plumbing():
     v = w.read_component(vel, 0, 2).view(np.float32)
     assert np.all(np.linalg.norm(v, axis=1) <= 3.0 + 1e-5)
     assert np.any(v != 0)
+
+
+def test_catch_up_vectors_merged_equal_tick_by_tick_on_the_oracle():
+    """handle_requests is a plain loop over the request vector (schedule_systems.rs:222-269), so several ticks' vectors
+    concatenated into one call must leave the same world, ring and checksums as one call per tick — the property the
+    engine's catch-up batches (one fused launch for the merged vector) are tested against on the GPU."""
+    import numpy as np
+    from bevy_ggrs_b200.session import SAVE, SyncTestSession
+    from bevy_ggrs_b200.stress import populate, register_particles, synth_particles
+    from oracle_backend import OracleWorld
+    n, d, maxp, n_ticks, group = 400, 4, 8, 18, 3
+    worlds = []
+    for _ in range(2):
+        w = OracleWorld()
+        cols = register_particles(w, spawn_rate=15, spawn_ttl=6)
+        w.build()
+        populate(w, cols, *synth_particles(n, 5, 3, 30))
+        worlds.append((w, cols))
+    sess = SyncTestSession(2, d, maxp, input_delay=2)
+    vectors = []
+    for t in range(n_ticks):
+        sess.add_local_input(0, (1 << 4) if t % 4 == 1 else 0)
+        sess.add_local_input(1, 0)
+        reqs = sess.advance_frame()
+        for r in reqs:
+            if r.kind == SAVE:
+                sess.save_cell(r.frame, 0)
+        vectors.append(reqs)
+    (a, cols), (b, _) = worlds
+    got_a, got_b = [], []
+    for g in range(0, n_ticks, group):
+        got_a += a.handle_requests(sess.info(), [r for v in vectors[g:g + group] for r in v])
+        for v in vectors[g:g + group]:
+            got_b += b.handle_requests(sess.info(), v)
+    assert got_a == got_b and len(got_a) > n_ticks
+    assert a.row_count() == b.row_count() > n and a.snapshot_frames() == b.snapshot_frames()
+    rows = a.row_count()
+    for c in cols:
+        va, ha = a.read_component_alive(c, 0, rows)
+        vb, hb = b.read_component_alive(c, 0, rows)
+        assert np.array_equal(ha, hb) and np.array_equal(va[ha.astype(bool)], vb[hb.astype(bool)])
