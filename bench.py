@@ -142,75 +142,154 @@ def check_synctest_consistency(history):
 # =================================================================================================
 # our arm
 # =================================================================================================
+class StdoutGuard:
+    """N > 1: NCCL's INFO banner (the driver checks `nranks` in it) is printf'ed to fd 1.  Point fd 1 at stderr for the
+    whole run and keep the real stdout for the ONE JSON line."""
+
+    def __init__(self, active):
+        self.real = None
+        if active:
+            sys.stdout.flush()
+            self.real = os.dup(1)
+            os.dup2(2, 1)
+
+    def emit(self, text):
+        if self.real is None:
+            print(text, flush=True)
+        else:
+            sys.stdout.flush()
+            os.write(self.real, (text + "\n").encode())
+
+
+def load_caller():
+    """tools/libbgr_e2e_caller.so: the compiled per-tick caller of bgr_handle_requests (tools/e2e_caller.c)."""
+    from bevy_ggrs_b200 import capi
+    path = os.path.join(ROOT, "tools", "libbgr_e2e_caller.so")
+    if not os.path.exists(path):
+        import __graft_entry__ as g
+        g.build_e2e_caller()
+    capi.load_library()
+    lib = C.CDLL(path)
+    lib.bgr_caller_run_ticks.restype = C.c_int
+    lib.bgr_caller_run_ticks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                                         C.c_void_p, C.c_uint32, C.c_void_p, C.POINTER(C.c_double), C.c_void_p]
+    return lib
+
+
+class CallerBatch:
+    """The ticks of one e2e leg as the flat host arrays the compiled caller walks."""
+
+    def __init__(self, tick_list):
+        from bevy_ggrs_b200 import capi
+        import numpy as np
+        self.n = len(tick_list)
+        total = sum(t[1] for t in tick_list)
+        self.reqs = (capi.bgr_request * max(1, total))()
+        self.infos = (capi.bgr_session_info * max(1, self.n))()
+        self.offsets = np.zeros(self.n, dtype=np.uint32)
+        self.counts = np.zeros(self.n, dtype=np.uint32)
+        o = 0
+        for i, (arr, nreq, _, info, _) in enumerate(tick_list):
+            C.memmove(C.byref(self.reqs, o * C.sizeof(capi.bgr_request)), arr, nreq * C.sizeof(capi.bgr_request))
+            self.infos[i] = info
+            self.offsets[i], self.counts[i] = o, nreq
+            o += nreq
+        self.cap = sum(len(t[4]) for t in tick_list) + 8
+        self.out = (capi.bgr_checksum * self.cap)()
+        self.out_counts = np.zeros(self.n, dtype=np.uint32)
+        self.per_tick = np.zeros(self.n, dtype=np.float64)
+
+    def run(self, caller, eng):
+        from bevy_ggrs_b200 import capi
+        total = C.c_double()
+        st = caller.bgr_caller_run_ticks(eng._h, self.infos, self.reqs, self.offsets.ctypes.data, self.counts.ctypes.data,
+                                         self.n, self.out, self.cap, self.out_counts.ctypes.data, C.byref(total),
+                                         self.per_tick.ctypes.data)
+        if st != 0:
+            raise RuntimeError(capi.load_library().bgr_last_error().decode())
+        return total.value
+
+    def checksums(self):
+        k = int(self.out_counts.sum())
+        return [(self.out[i].frame, (self.out[i].hi << 64) | self.out[i].lo) for i in range(k)]
+
+
+def trace_stats(tr):
+    """(n, 2) [first block start, last block end] ns per launch -> period / duration / overlap with the next launch."""
+    import numpy as np
+    if tr.shape[0] < 3:
+        return None
+    s, e = tr[:, 0].astype(np.int64), tr[:, 1].astype(np.int64)
+    dur = (e - s) / 1e3
+    period = np.diff(s) / 1e3
+    overlap = (e[:-1] - s[1:]) / 1e3          # > 0: the next launch's first block started before this launch's last block ended
+    return {"launches": int(tr.shape[0]), "kernel_us_median": float(np.median(dur)), "period_us_median": float(np.median(period)),
+            "overlap_us_median": float(np.median(overlap)), "overlapping_launches": int((overlap > 0).sum())}
+
+
 def run_ours(args):
+    import numpy as np
     import torch
     import torch.distributed as dist
     from bevy_ggrs_b200 import capi
-    from bevy_ggrs_b200.engine import Engine, fold_partials
+    from bevy_ggrs_b200.engine import Engine
+    from bevy_ggrs_b200.sharded import shard_range
 
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if world_size != args.gpus and world_size > 1:
         args.gpus = world_size
+    sharded = world_size > 1
+    guard = StdoutGuard(sharded)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world_size > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("BENCH_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+    if sharded:
+        # the communicator is only the launcher-side plumbing (rendezvous, barriers, max-over-ranks of the timings);
+        # its INIT banner stays reachable on stderr so that the rank count can be checked
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
 
-    n, d, maxp = WORKLOADS[args.workload]
+    n_total, d, maxp = WORKLOADS[args.workload]
     if args.entities:
-        n = args.entities
+        n_total = args.entities
+    strong = args.scaling == "strong"
+    if strong:
+        first_row, n = shard_range(n_total, rank, world_size)
+        shard_rows = [shard_range(n_total, r, world_size)[1] for r in range(world_size)]
+    else:
+        n, first_row = n_total, rank * n_total          # weak scaling: the workload's entity count PER GPU
+        shard_rows = [n_total] * world_size
     K, W = args.steps, max(3, args.warmup)
-    stream = torch.cuda.Stream(device=dev)
-    sharded = world_size > 1
     eng = Engine(max_entities=n, max_depth=maxp, fps=60, device=local_rank,
-                 flags=capi.BGR_CFG_SHARDED if sharded else 0, order_base=rank * n, stream=stream.cuda_stream)
+                 flags=capi.BGR_CFG_SHARDED if sharded else 0, order_base=first_row)
     build_world(eng, n, d, SEED + rank)
+    stream = torch.cuda.ExternalStream(eng.stream(), device=dev)   # the stream the kernels are launched on
     slot_bytes = eng.slot_bytes()
+    if sharded:
+        # the cross-shard checksum exchange happens INSIDE the engine from here on (bgr_shard_group_join): every
+        # bgr_collect / bgr_handle_requests returns the whole world's frame checksum; no torch call per tick
+        names = [f"bgr_bench_{os.getpid()}_{int(time.time() * 1e6)}" if rank == 0 else None]
+        dist.broadcast_object_list(names, src=0)
+        eng.shard_group_join(names[0], rank, world_size, 120000)
 
     fill = max(d, maxp) + 2           # ticks until the request vector has its steady-state shape
     K2 = min(K, 500) if world_size == 1 else 0   # ticks of the host-mirror leg (N = 1 only)
     BT = int(os.environ.get("BENCH_BATCH_TICKS", "4")) if world_size == 1 and d > 0 else 0   # catch-up leg: ticks per request vector
     BT = min(BT, capi.BGR_MAX_REQUESTS // (2 * d + 2)) if d > 0 else 0                          # ... that fit one call
     K3 = (min(K, 400) // BT) * BT if BT > 1 else 0
-    ticks = pregenerate_ticks(fill + W + K + K + K2 + K3, d, maxp)
+    KT = 64                            # ticks of each traced leg (pipelined / synchronous)
+    ticks = pregenerate_ticks(fill + W + K + K + K + K2 + K3 + 2 * KT, d, maxp)
+    pos = [0]
+
+    def take(k):
+        out = ticks[pos[0]: pos[0] + k]
+        pos[0] += k
+        return out
+
     history = []
-
-    def fold_all(partials_list):
-        """cross-shard fold: all_gather the raw partials (u64 XORs + counts) over NCCL, fold locally."""
-        from bevy_ggrs_b200.sharded import all_fold
-        return all_fold(partials_list, device=dev)
-
-    pbuf = None
-    if sharded:
-        from bevy_ggrs_b200.sharded import PartialBuffer, all_fold_array
-        pbuf = PartialBuffer(64 * (maxp + 2))
-
-    # the exchange (H2D of the partials, all_gather, D2H) runs on its own stream: on the engine's stream its
-    # synchronising D2H copy would drain the whole queue of submitted ticks every time
-    xchg_stream = torch.cuda.Stream(device=dev) if sharded else None
-
-    def flush_partials():
-        if pbuf.n:
-            with torch.cuda.stream(xchg_stream):
-                folded = all_fold_array(pbuf.take(), device=dev)
-            history.extend(folded)
-
-    def collect_one():
-        if sharded:
-            # the cross-shard exchange is batched (one all_gather per ~32 ticks): desync checksums are only
-            # consumed every few frames (the stress example exchanges them every 10, particles.rs:48-50)
-            pbuf.collect_from(eng)
-            if pbuf.n >= 32 * max(1, d):
-                flush_partials()
-        else:
-            history.extend(eng.collect())
-
-    # un-collected submits kept queued on the GPU: 2 hide the host loop; the sharded loop keeps 6 so that the
-    # batched all_gather (every ~32 ticks) never drains the queue
-    depth = 6 if sharded else 2
+    depth = 4 if sharded else 2     # un-collected submits kept queued on the GPU (hides the host loop / rank jitter)
 
     def run_pipelined(tick_list):
         inflight = 0
@@ -218,13 +297,11 @@ def run_ours(args):
             eng.submit_prepared(info, arr, nreq)
             inflight += 1
             if inflight > depth:
-                collect_one()
+                history.extend(eng.collect())
                 inflight -= 1
         while inflight:
-            collect_one()
+            history.extend(eng.collect())
             inflight -= 1
-        if sharded:
-            flush_partials()
 
     def barrier():
         torch.cuda.synchronize()
@@ -232,130 +309,169 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
-    with torch.cuda.stream(stream):
-        run_pipelined(ticks[:fill + W])           # ring fill + warm-up (>= 3 steady-state ticks)
+    def max_over_ranks(x):
+        if not sharded:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    caller = load_caller()
+    lib = capi.load_library()
+
+    run_pipelined(take(fill + W))           # ring fill + warm-up (>= 3 steady-state ticks)
+    barrier()
+    # ---------------- value: device-timed, K ticks back to back ----------------
+    timed = take(K)
+    adv_total = sum(t[2] for t in timed)
+    adv_per_tick = adv_total / K
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    run_pipelined(timed)
+    ev1.record(stream)
+    barrier()
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = eng.launch_count() - l0
+    # ---------------- e2e: ONE synchronous bgr_handle_requests per tick, host arrays in / host checksums out ----------------
+    e2e_ticks = take(K)
+    batch = CallerBatch(e2e_ticks)
+    barrier()
+    e2e_s = max_over_ranks(batch.run(caller, eng))
+    history.extend(batch.checksums())
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_p50_us = float(np.median(batch.per_tick) * 1e6)
+    h2d = sum(C.sizeof(capi.bgr_request) * t[1] + C.sizeof(capi.bgr_session_info) for t in e2e_ticks) / K
+    d2h = sum(64 * len(t[4]) + 8 for t in e2e_ticks) / K  # one 8 x u64 result row per SaveGameState + the completion word, pinned host memory
+    # the same loop driven from Python through ctypes (what round 1 reported as e2e)
+    py_ticks = take(K)
+    out = (capi.bgr_checksum * capi.BGR_MAX_REQUESTS)()
+    nout = C.c_uint32()
+    barrier()
+    t0 = time.perf_counter()
+    for arr, nreq, _, info, _ in py_ticks:
+        st = lib.bgr_handle_requests(eng._h, C.byref(info), arr, nreq, out, capi.BGR_MAX_REQUESTS, C.byref(nout))
+        if st != 0:
+            raise RuntimeError(lib.bgr_last_error().decode())
+        history.extend((out[i].frame, (out[i].hi << 64) | out[i].lo) for i in range(nout.value))
+    e2e_py_s = max_over_ranks(time.perf_counter() - t0)
+
+    # ---------------- device-side timeline of both modes (bgr_trace_enable; NOT part of the timed regions above) ----------------
+    timeline = {}
+    try:
+        eng.trace_enable(2 * KT + 8)
+        tp = take(KT)
+        run_pipelined(tp)
         barrier()
-        # ---------------- value: device-timed, K ticks back to back ----------------
-        timed = ticks[fill + W: fill + W + K]
-        adv_total = sum(t[2] for t in timed)
-        adv_per_tick = adv_total / K
-        sampler = ClockSampler(local_rank)
-        if rank == 0:
-            sampler.start()
-        l0 = eng.launch_count()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        ev0.record(stream)
-        run_pipelined(timed)
-        ev1.record(stream)
-        barrier()
-        ms = ev0.elapsed_time(ev1)
-        launches = eng.launch_count() - l0
-        clocks = sampler.stop() if rank == 0 else None
-        if sharded:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        # ---------------- e2e: synchronous bgr_handle_requests per tick, host buffers ----------------
-        e2e_ticks = ticks[fill + W + K: fill + W + K + K]
-        lib = capi.load_library()
-        out = (capi.bgr_checksum * capi.BGR_MAX_REQUESTS)()
-        nout = C.c_uint32()
-        lp_buf = (capi.bgr_partial * capi.BGR_MAX_REQUESTS)()
-        lp_n = C.c_uint32()
-        import numpy as np
+        tr_p = eng.trace_read(2 * KT + 8)
+        tb = CallerBatch(take(KT))
+        tb.run(caller, eng)
+        history.extend(tb.checksums())
+        tr_all = eng.trace_read(2 * KT + 8)
+        tr_s = tr_all[tr_p.shape[0]:]
+        eng.trace_enable(0)
+        timeline = {"pipelined": trace_stats(tr_p), "synchronous": trace_stats(tr_s),
+                    "note": "GPU globaltimer, first block start .. last block end of every fused launch; "
+                            "overlap > 0 = the next tick's first wave ran inside this tick's tail (tile dependencies)"}
+        if args.trace_out and rank == 0:
+            with open(args.trace_out, "w") as f:
+                f.write("mode,launch,first_block_start_ns,last_block_end_ns\n")
+                for mode, tr in (("pipelined", tr_p), ("synchronous", tr_s)):
+                    base = int(tr[0, 0]) if tr.shape[0] else 0
+                    for i in range(tr.shape[0]):
+                        f.write(f"{mode},{i},{int(tr[i, 0]) - base},{int(tr[i, 1]) - base}\n")
+    except Exception as exc:  # an optional leg must not cost the headline line
+        timeline = {"error": repr(exc)}
+
+    # ---------------- e2e with a host mirror: every tick also downloads Transform.translation ----------------
+    # What a host-resident ECS needs back per tick to draw the particles (INTEGRATION.md "mirror"): 12 B/entity
+    # packed on the GPU, copied D2H on a copy stream into page-locked memory while the next tick runs.
+    def mirror_leg():
+        m_ticks = take(K2)
+        bufs = [eng.host_alloc(n, 12), eng.host_alloc(n, 12)]
+        pending = None
         barrier()
         t0 = time.perf_counter()
-        for arr, nreq, _, info, _ in e2e_ticks:
-            st = lib.bgr_handle_requests(eng._h, C.byref(info), arr, nreq, out, capi.BGR_MAX_REQUESTS, C.byref(nout))
-            if st != 0:
-                raise RuntimeError(lib.bgr_last_error().decode())
-            if sharded:  # the e2e tick includes its cross-shard exchange: one all_gather of the tick's partials
-                if lib.bgr_last_partials(eng._h, lp_buf, capi.BGR_MAX_REQUESTS, C.byref(lp_n)) != 0:
-                    raise RuntimeError(lib.bgr_last_error().decode())
-                pbuf.arr[:lp_n.value] = np.frombuffer(lp_buf, dtype=pbuf.arr.dtype, count=lp_n.value)
-                pbuf.n = lp_n.value
-                flush_partials()
-            else:
-                history.extend((out[i].frame, (out[i].hi << 64) | out[i].lo) for i in range(nout.value))
-        e2e_s = time.perf_counter() - t0
-        if sharded:
-            t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        h2d = sum(C.sizeof(capi.bgr_request) * t[1] + C.sizeof(capi.bgr_session_info) for t in e2e_ticks) / K
-        d2h = sum(64 * len(t[4]) + 8 for t in e2e_ticks) / K  # one 8 x u64 result row per SaveGameState + the completion word, pinned host memory
-        # ---------------- e2e with a host mirror: every tick also downloads Transform.translation ----------------
-        # What a host-resident ECS needs back per tick to draw the particles (INTEGRATION.md "mirror"): 12 B/entity
-        # packed on the GPU, copied D2H on a copy stream into page-locked memory while the next tick runs.
-        def mirror_leg():
-            m_ticks = ticks[fill + W + K + K: fill + W + K + K + K2]
-            bufs = [eng.host_alloc(n, 12), eng.host_alloc(n, 12)]
-            pending = None
-            barrier()
-            t0 = time.perf_counter()
-            for i, (arr, nreq, _, info, _) in enumerate(m_ticks):
-                eng.submit_prepared(info, arr, nreq)
-                tk = eng.download_begin(0, 0, 12, 0, n, bufs[i & 1])
-                history.extend(eng.collect())
-                if pending is not None:
-                    eng.download_wait(pending)   # the previous tick's mirror is now readable on the host
-                pending = tk
-            eng.download_wait(pending)
-            m_s = time.perf_counter() - t0
-            mirror = {"value": sum(t[2] for t in m_ticks) / m_s, "unit": "rollback frames/s", "ticks": K2,
-                      "d2h_bytes_per_step": 12 * n + sum(64 * len(t[4]) + 8 for t in m_ticks) / K2,
-                      "d2h_gbs": 12 * n * K2 / m_s / 1e9,
-                      "note": "e2e + bgr_download_begin/wait of Transform.translation (12 B/entity) every tick, "
-                              "double-buffered pinned host memory; PCIe-bound when 12 B x entities / tick exceeds the link"}
-            return mirror
+        for i, (arr, nreq, _, info, _) in enumerate(m_ticks):
+            eng.submit_prepared(info, arr, nreq)
+            tk = eng.download_begin(0, 0, 12, 0, n, bufs[i & 1])
+            history.extend(eng.collect())
+            if pending is not None:
+                eng.download_wait(pending)   # the previous tick's mirror is now readable on the host
+            pending = tk
+        eng.download_wait(pending)
+        m_s = time.perf_counter() - t0
+        return {"value": sum(t[2] for t in m_ticks) / m_s, "unit": "rollback frames/s", "ticks": K2,
+                "d2h_bytes_per_step": 12 * n + sum(64 * len(t[4]) + 8 for t in m_ticks) / K2,
+                "d2h_gbs": 12 * n * K2 / m_s / 1e9,
+                "note": "e2e + bgr_download_begin/wait of Transform.translation (12 B/entity) every tick, "
+                        "double-buffered pinned host memory; PCIe-bound when 12 B x entities / tick exceeds the link"}
 
-        mirror = None
-        if K2:
-            try:
-                mirror = mirror_leg()
-            except Exception as exc:  # an optional leg must not cost the headline line
-                mirror = {"error": repr(exc)}
+    mirror = None
+    if K2:
+        try:
+            mirror = mirror_leg()
+        except Exception as exc:
+            mirror = {"error": repr(exc)}
 
-        def batch_leg():
-            # catch-up shape of run_ggrs_schedules' inner loop (schedule_systems.rs:60-82): several ticks' request
-            # vectors handed over in one call
-            b_ticks = ticks[fill + W + K + K + K2:]
-            groups = []
-            for g in range(0, K3, BT):
-                grp = b_ticks[g:g + BT]
-                n_req = sum(t[1] for t in grp)
-                arr = (capi.bgr_request * n_req)()
-                o = 0
-                for t in grp:
-                    for i in range(t[1]):
-                        arr[o] = t[0][i]
-                        o += 1
-                groups.append((arr, n_req, sum(t[2] for t in grp), grp[0][3], None))
-            barrier()
-            evb0, evb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            lb0 = eng.launch_count()
-            evb0.record(stream)
-            run_pipelined(groups)
-            evb1.record(stream)
-            barrier()
-            bms = evb0.elapsed_time(evb1)
-            batched = {"ticks_per_call": BT, "value": sum(g[2] for g in groups) / (bms * 1e-3), "unit": "rollback frames/s",
-                       "ms_per_tick": bms / K3, "gpu_launches": eng.launch_count() - lb0, "fused": bool(eng.last_path_fused()),
-                       "note": "NOT the headline: several ticks' request vectors per bgr_handle_requests call (the catch-up "
-                               "shape of run_ggrs_schedules' inner loop); one launch per call, the live image is written "
-                               "once per call"}
-            return batched
+    def batch_leg():
+        # catch-up shape of run_ggrs_schedules' inner loop (schedule_systems.rs:60-82): several ticks' request
+        # vectors handed over in one call
+        b_ticks = take(K3)
+        groups = []
+        for g in range(0, K3, BT):
+            grp = b_ticks[g:g + BT]
+            n_req = sum(t[1] for t in grp)
+            arr = (capi.bgr_request * n_req)()
+            o = 0
+            for t in grp:
+                for i in range(t[1]):
+                    arr[o] = t[0][i]
+                    o += 1
+            groups.append((arr, n_req, sum(t[2] for t in grp), grp[0][3], None))
+        barrier()
+        evb0, evb1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lb0 = eng.launch_count()
+        evb0.record(stream)
+        run_pipelined(groups)
+        evb1.record(stream)
+        barrier()
+        bms = evb0.elapsed_time(evb1)
+        return {"ticks_per_call": BT, "value": sum(g[2] for g in groups) / (bms * 1e-3), "unit": "rollback frames/s",
+                "ms_per_tick": bms / K3, "gpu_launches": eng.launch_count() - lb0, "fused": bool(eng.last_path_fused()),
+                "note": "NOT the headline: several ticks' request vectors per bgr_handle_requests call (the catch-up "
+                        "shape of run_ggrs_schedules' inner loop); one launch per call, the live image is written "
+                        "once per call"}
 
-        batched = None
-        if K3:
-            try:
-                batched = batch_leg()
-            except Exception as exc:
-                batched = {"error": repr(exc)}
+    batched = None
+    if K3:
+        try:
+            batched = batch_leg()
+        except Exception as exc:
+            batched = {"error": repr(exc)}
 
     consistent = check_synctest_consistency(history)
     fused = eng.last_path_fused()
+
+    # ---------------- N > 1: the folded checksums against ONE engine holding the whole population ----------------
+    sharded_parity = None
+    if sharded:
+        barrier()
+        ok = 1
+        if rank == 0:
+            try:
+                sharded_parity = verify_against_unsharded(shard_rows, d, maxp, local_rank, ticks[:fill + 3], history)
+                ok = 1 if sharded_parity["equal"] else 0
+            except Exception as exc:
+                sharded_parity = {"error": repr(exc)}
+                ok = 0
+        t = torch.tensor([ok], device=dev, dtype=torch.int32)
+        dist.broadcast(t, src=0)
+        consistent = consistent and bool(t.item())
 
     # ---------------- roofline of the dominant (only) kernel ----------------
     ms_per_step = ms / K
@@ -369,13 +485,17 @@ def run_ours(args):
     unfused_bytes = (sum(2 * len(t[4]) for t in timed) + 2 * n_loads) / K * slot_bytes + 64.0 * n * adv_per_tick
     achieved_unfused = unfused_bytes / (ms_per_step * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
-    traffic = None
+    traffic = isolated = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get(args.workload)
+            tj = json.load(open(tp))
+            traffic = tj.get(args.workload)
+            isolated = tj.get("isolated_launch_us", {}).get(args.workload)
         except Exception:
             traffic = None
+    e2e_alg = sum(len(t[4]) + 2 for t in e2e_ticks) / K * slot_bytes
+    sync_kernel_us = (timeline.get("synchronous") or {}).get("kernel_us_median")
 
     # ---------------- CPU baseline (rank 0, N == 1 only): oracle port on host cores ----------------
     cpu = cpu_soa = None
@@ -383,39 +503,70 @@ def run_ours(args):
         cpu = run_cpu_sample(n, d, maxp, rollback_ticks=3)
         if d > 0:
             cpu_soa = run_cpu_soa_sample(n, d, maxp)
-    snap = None
-    skip = None
+    snap = snap10 = skip = None
     if rank == 0 and world_size == 1 and not args.no_snapshot_bench:
         eng.close()
         snap = snapshot_bench(n, maxp, local_rank)
+        try:
+            snap10 = snapshot_bench(10_000_000, maxp, local_rank, iters=20)   # 610 MB images: out of L2, an HBM measurement
+        except Exception as exc:
+            snap10 = {"error": repr(exc)}
         skip = skip_unchanged_bench(n, d, maxp, local_rank, ticks, fill, W, K, history)
 
     if rank == 0:
-        value = world_size * adv_total / (ms * 1e-3)
+        value = sum(shard_rows) / n_total * adv_total / (ms * 1e-3) if strong else world_size * adv_total / (ms * 1e-3)
+        scale = (sum(shard_rows) / n_total) if strong else world_size
+        e2e_value = scale * sum(t[2] for t in e2e_ticks) / e2e_s
         line = {
             "metric": "rollback frames/sec at 1M entities x 8-frame window (SyncTest: 1 Load + 8 Save+checksum + 9 Advance per tick)",
             "value": value, "unit": "rollback frames/s", "n_gpus": world_size, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
             "dtype": "u64 (seahash) + f32 (particles, no FMA) + u8 copy", "data": "synthetic (numpy PCG64 seed 0xB200; BASELINE.md shapes)",
-            "config": {"workload": args.workload, "entities_per_gpu": n, "check_distance": d, "max_prediction": maxp,
+            "config": {"workload": args.workload, "entities_per_gpu": n, "entities_total": sum(shard_rows), "check_distance": d,
+                       "max_prediction": maxp,
                        "columns": "Transform40+Velocity12+Ttl8+alive1 = 61 B/entity/slot", "checksum": "every saved frame",
                        "advances_per_step": adv_per_tick, "l2": "inputs larger than L2: each tick reads 1 slot and writes 9 images of "
                        f"{slot_bytes/1e6:.0f} MB (ring {maxp} slots)", "path": "fused" if fused else "stepwise",
-                       "sharding": f"entity-range x{world_size}, all_gather of checksum partials" if sharded else "none"},
+                       "value_is": "device-timed PIPELINED submits (bgr_submit_requests / bgr_collect, consecutive launches overlap); "
+                                   "the synchronous per-tick contract of the reference is `e2e`",
+                       "sharding": (f"entity-range x{world_size}; cross-shard checksum fold inside the engine "
+                                    "(bgr_shard_group_join: kernels store their 64 B partial rows into a shared host segment, "
+                                    "every rank's CPU polls and folds; no collective call per tick)") if sharded else "none"},
             "gpu_launches": launches,
             "clocks": clocks,
-            "e2e": {"value": world_size * sum(t[2] for t in e2e_ticks) / e2e_s, "unit": "rollback frames/s",
-                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "note": "bgr_handle_requests per tick: request vector from host memory, checksums to host memory; "
+            "e2e": {"value": e2e_value, "unit": "rollback frames/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / K * 1e3, "p50_us_per_call": e2e_p50_us,
+                    "caller": "compiled (tools/e2e_caller.c): one synchronous bgr_handle_requests per tick",
+                    "note": "request vector from host memory, checksums to host memory, every tick; "
                             "component columns live in HBM by design and never cross"},
+            "e2e_python_caller": {"value": scale * sum(t[2] for t in py_ticks) / e2e_py_s, "unit": "rollback frames/s",
+                                  "note": "the same per-tick call driven from Python through ctypes (round 1's e2e)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "k_particles_program",
+                         "traffic": traffic,
+                         "traffic_source": "constant: dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture "
+                                           "(profiles/traffic.json), NOT measured in this run",
+                         "peak_source": peak_src, "kernel": "k_particles_program",
                          "algorithmic_bytes_per_launch": alg_bytes,
+                         "pipelined": {"achieved": achieved, "frac": achieved / peak,
+                                       "how": "algorithmic bytes / (CUDA-event time of K back-to-back launches / K); launches overlap"},
+                         "sync": None if not sync_kernel_us else {
+                             "kernel_us": sync_kernel_us, "achieved": e2e_alg / (sync_kernel_us * 1e-6) / 1e9,
+                             "frac": e2e_alg / (sync_kernel_us * 1e-6) / 1e9 / peak,
+                             "how": "algorithmic bytes / median device duration (first block start .. last block end, globaltimer) "
+                                    "of the launches of synchronous bgr_handle_requests calls"},
+                         "e2e": {"achieved": e2e_alg / (e2e_s / K) / 1e9, "frac": e2e_alg / (e2e_s / K) / 1e9 / peak,
+                                 "how": "algorithmic bytes / host wall time per synchronous call"},
+                         "isolated": None if not isolated else {
+                             "kernel_us": isolated, "frac": alg_bytes / (isolated * 1e-6) / 1e9 / peak,
+                             "how": "constant: ncu gpu__time_duration of one serialised cold-cache launch (profiles/traffic.json)"},
                          "unfused_accounting": {"bytes_per_step": unfused_bytes, "effective_gbs": achieved_unfused,
                                                 "note": "bytes the reference's one-schedule-per-request path would move "
                                                         "(2S per Save/Load + 64 B per Advance per entity); not a roofline claim"}},
+            "timeline": timeline,
             "synctest_consistent": consistent,
         }
+        if sharded_parity is not None:
+            line["sharded_parity"] = sharded_parity
         if cpu:
             line["cpu_baseline"] = cpu
         if cpu_soa:
@@ -426,14 +577,45 @@ def run_ours(args):
             line["catch_up_batch"] = batched
         if snap:
             line["snapshot_save_restore"] = snap
+        if snap10:
+            line["snapshot_save_restore_10m"] = snap10
         if skip:
             line["opt_in_skip_unchanged_planes"] = skip
-        print(json.dumps(line), flush=True)
+        guard.emit(json.dumps(line))
     eng.close()
     if sharded:
+        dist.barrier()
         dist.destroy_process_group()
     if not consistent:
         sys.exit(3)
+
+
+def verify_against_unsharded(shard_rows, d, maxp, device_index, tick_list, history):
+    """Rank 0, N > 1: run the first ticks on ONE engine that holds every shard's population (order_base 0) and compare
+    its checksums, frame by frame, with what the sharded engines folded — parity of the multi-GPU path on hardware."""
+    import numpy as np
+    from bevy_ggrs_b200.engine import Engine
+    from bevy_ggrs_b200.stress import populate, register_particles, synth_particles
+    total = sum(shard_rows)
+    ref = Engine(max_entities=total, max_depth=maxp, fps=60, device=device_index)
+    cols = register_particles(ref)
+    ref.build()
+    for r, rows in enumerate(shard_rows):
+        tf, vel, ttl = synth_particles(rows, SEED + r, 300 + d + 100000, 300 + d + 100000)
+        populate(ref, cols, tf, vel, ttl)
+    got = {}
+    for f, c in history:
+        got.setdefault(f, c)
+    n_frames, equal = 0, True
+    for arr, nreq, _, info, _ in tick_list:
+        ref.submit_prepared(info, arr, nreq)
+        for f, c in ref.collect():
+            n_frames += 1
+            equal = equal and (got.get(f) == c)
+    ref.close()
+    return {"equal": bool(equal), "ticks": len(tick_list), "checksums_compared": n_frames, "entities": total,
+            "how": "rank 0 re-ran the first ticks on one unsharded engine holding every shard's population; "
+                   "every frame checksum must equal the cross-shard fold"}
 
 
 def skip_unchanged_bench(n, d, maxp, device_index, ticks, fill, W, K, reference_history):
@@ -443,10 +625,9 @@ def skip_unchanged_bench(n, d, maxp, device_index, ticks, fill, W, K, reference_
     import torch
     from bevy_ggrs_b200 import capi
     from bevy_ggrs_b200.engine import Engine
-    stream = torch.cuda.Stream()
-    eng = Engine(max_entities=n, max_depth=maxp, fps=60, device=device_index, flags=capi.BGR_CFG_SKIP_UNCHANGED_PLANES,
-                 stream=stream.cuda_stream)
+    eng = Engine(max_entities=n, max_depth=maxp, fps=60, device=device_index, flags=capi.BGR_CFG_SKIP_UNCHANGED_PLANES)
     build_world(eng, n, d, SEED)
+    stream = torch.cuda.ExternalStream(eng.stream())
     hist = []
 
     def run(tl):
@@ -495,9 +676,9 @@ def snapshot_bench(n, maxp, device_index, iters=50):
     out = {}
     peak, _ = measured_hbm_peak()
     for name, flags in (("fused_program", 0), ("tma_bulk_copy", capi.BGR_CFG_FORCE_STEPWISE)):
-        stream = torch.cuda.Stream()
-        eng = Engine(max_entities=n, max_depth=2, fps=60, device=device_index, flags=flags, stream=stream.cuda_stream)
+        eng = Engine(max_entities=n, max_depth=2, fps=60, device=device_index, flags=flags)
         build_world(eng, n, 8, SEED)
+        stream = torch.cuda.ExternalStream(eng.stream())
         info = capi.make_session_info((0, 0, 0, 0))
         save = capi.make_requests([Request(SAVE, 0)])
         load = capi.make_requests([Request(LOAD, 0)])
@@ -640,6 +821,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-snapshot-bench", action="store_true")
     ap.add_argument("--entities", type=int, default=0, help="override the workload's entity count (scaling studies)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = the workload's entity count per GPU; strong = the workload's entity count split over the GPUs (BASELINE C5)")
+    ap.add_argument("--trace-out", default="", help="write the device-side launch timeline (CSV) here")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

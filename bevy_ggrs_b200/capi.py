@@ -126,6 +126,16 @@ PROTOTYPES = {
     "bgr_slot_bytes": (C.c_int, [C.c_void_p, u64p]),
     "bgr_last_path": (C.c_int, [C.c_void_p, u32p]),
     "bgr_synchronize": (C.c_int, [C.c_void_p]),
+    "bgr_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
+    "bgr_trace_enable": (C.c_int, [C.c_void_p, C.c_uint32]),
+    "bgr_trace_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, u32p]),
+    "bgr_reset_session": (C.c_int, [C.c_void_p]),
+    "bgr_shard_group_join": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "bgr_shard_group_leave": (C.c_int, [C.c_void_p]),
+    "bgr_group_join": (C.c_void_p, [C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "bgr_group_leave": (None, [C.c_void_p]),
+    "bgr_group_publish": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint32]),
+    "bgr_group_collect": (C.c_int, [C.c_void_p, C.c_uint64, C.POINTER(bgr_checksum), C.c_uint32, u32p]),
     "bgr_ring_create": (C.c_void_p, [C.c_uint32]),
     "bgr_ring_destroy": (None, [C.c_void_p]),
     "bgr_ring_depth": (C.c_uint32, [C.c_void_p]),

@@ -22,6 +22,7 @@
 #include "kernels.cuh"
 #include "ring.hpp"
 #include "seahash.cuh"
+#include "shard_group.hpp"
 #include "tma_copy.cuh"
 
 using namespace bgr;
@@ -117,6 +118,8 @@ struct Pending {
     uint32_t buf = 0;
     uint32_t chains = 1;            // result blocks to wait for
     unsigned long long seq = 0;
+    unsigned long long gseq = 0;    // shard group sequence number (0: not in a group)
+    bool finished = false;          // the GPU work is known to be complete (drain() synchronised the stream)
     uint32_t n_saves = 0;
     int32_t frames[kMaxSaves];
     uint32_t totals[kMaxSaves];
@@ -186,6 +189,17 @@ struct bgr_engine {
     std::deque<Pending> pending;
     uint32_t next_buf = 0;
     std::vector<bgr_partial> last_partials;
+
+    // shard group (multi-GPU): result blocks live in a shared host segment every rank's GPU and CPU map
+    ShardGroup* group = nullptr;
+    unsigned long long gseq = 0;
+    unsigned long long* own_h_out[kBufs] = {};  // the engine's private result blocks while it is in a group
+    unsigned long long* own_d_out[kBufs] = {};
+    bool ticked = false;            // a request vector has been executed (the initial population is over)
+    // device-side launch trace (bgr_trace_enable): per launch [first block start, last block end] in globaltimer ns
+    unsigned long long* d_trace = nullptr;
+    uint32_t trace_cap = 0;
+    unsigned long long trace_first_seq = 0;
 
     uint64_t launches = 0;
     bool last_fused = false;
@@ -334,7 +348,7 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
             op.n_rows = s.n_rows;
             op.call_count = s.call_count;
             s.call_count += n_counter_systems;
-            for (uint32_t k = 0; k < 4 && k < rq.n_players; ++k) op.inputs[k] = rq.inputs[k];
+            for (uint32_t k = 0; k < BGR_MAX_PLAYERS && k < rq.n_players; ++k) op.inputs[k] = rq.inputs[k];
             op.flags |= (rq.n_players & 0xFu) << 8;  // PlayerInputs<T>.len() for systems that index it (box_game.rs:171)
             pg.has_advance = true;
             if (e->spawn_sys >= 0) {  // spawn_particles.run_if(spawn_pressed) (particles.rs:236, 254-256)
@@ -462,7 +476,9 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
     }
     // only worth it when request vectors are queued behind each other (bgr_submit_requests with others un-collected):
     // a synchronous caller collects before the next submit, so there is nothing to overlap with
-    const bool tiledep = e->tune_tiledep && chains == 1 && e->d_tile_done && (e->tune_tiledep > 1 || !e->pending.empty());
+    // ... and only on a stream the engine owns: on a caller's stream foreign work may sit between two submits and
+    // become the programmatic-launch primary, which the per-tile flags know nothing about
+    const bool tiledep = e->tune_tiledep && chains == 1 && e->d_tile_done && e->own_stream && (e->tune_tiledep > 1 || !e->pending.empty());
     if (e->tiledep_chain && total_tiles != e->tiledep_tiles) {
         // The tile range changed (rows crossed a tile boundary): a tile outside the previous launch's range may still be
         // in use by an OLDER overlapping launch that nothing would make this one wait for.  Rare: drain the stream.
@@ -487,6 +503,8 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
         pp.accum = e->d_accum_c[set];
         pp.ticket = e->d_ticket_c[set];
         pp.out = e->d_out[buf] + size_t(c) * kResultStride;
+        pp.trace = nullptr;
+        if (e->d_trace && c == 0 && e->seq - e->trace_first_seq < e->trace_cap) pp.trace = e->d_trace + (e->seq - e->trace_first_seq) * 2;
         cudaStream_t stream = chains > 1 ? e->chain_stream[c] : e->stream;
         int rc = launch_fused_variant(e, pp, stream);
         if (rc != BGR_OK) return rc;
@@ -640,7 +658,8 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
                 case BGR_SYS_PARTICLES_SPAWN:
                     continue;  // Commands: applied after the schedule (below)
                 case BGR_SYS_BOX_MOVE: {
-                    uint32_t packed = uint32_t(op.inputs[0]) | (uint32_t(op.inputs[1]) << 8) | (uint32_t(op.inputs[2]) << 16) | (uint32_t(op.inputs[3]) << 24);
+                    unsigned long long packed = 0;
+                    for (int k = 0; k < 8; ++k) packed |= (unsigned long long)(op.inputs[k]) << (8 * k);
                     k_sys_box_move<<<grid, 256, 0, e->stream>>>(live, e->words, e->cols[sy.cols[0]].first_plane, e->cols[sy.cols[1]].first_plane,
                                                                  n, op.dt_bits, packed, (op.flags >> 8) & 0xFu, e->cfg.order_base, need);
                     break;
@@ -690,8 +709,17 @@ int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs,
     int rc = compile_requests(e, s, sess, reqs, n, pg);
     if (rc != BGR_OK) return rc;  // nothing executed, nothing committed
     uint32_t buf = e->next_buf;
+    if (e->group) {
+        // the buffer of this request vector was last used kBufs vectors ago: every peer must have folded that one
+        std::string err;
+        if (!e->group->wait_reusable(e->gseq + 1, &err)) return fail(BGR_ERR_STATE, err);
+        e->gseq += 1;
+        buf = ShardGroup::buf_of(e->gseq);
+        e->group->publish_meta(e->gseq, pg.n_saves, e->n_ck, pg.save_frames, pg.save_totals);
+    }
     if (!pg.spawn_vals.empty()) std::memcpy(e->h_spawn[buf], pg.spawn_vals.data(), pg.spawn_vals.size() * sizeof(float2));
     e->seq += 1;
+    e->ticked = true;
     bool fused = e->bundle_particles && !(e->cfg.flags & BGR_CFG_FORCE_STEPWISE);
     uint32_t chains = 1;
     rc = fused ? run_fused(e, pg, buf, &chains) : run_stepwise(e, pg, buf);
@@ -701,7 +729,7 @@ int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs,
     e->last_fused = fused;
     e->st = s;
     Pending pd;
-    pd.buf = buf; pd.n_saves = pg.n_saves; pd.seq = e->seq; pd.chains = chains;
+    pd.buf = buf; pd.n_saves = pg.n_saves; pd.seq = e->seq; pd.chains = chains; pd.gseq = e->group ? e->gseq : 0;
     std::memcpy(pd.frames, pg.save_frames, sizeof(int32_t) * pg.n_saves);
     std::memcpy(pd.totals, pg.save_totals, sizeof(uint32_t) * pg.n_saves);
     e->pending.push_back(pd);
@@ -726,7 +754,7 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
     if (e->pending.empty()) return fail(BGR_ERR_STATE, "nothing to collect");
     Pending pd = e->pending.front();
     e->pending.pop_front();
-    for (uint32_t c = 0; c < pd.chains; ++c) {
+    for (uint32_t c = 0; c < pd.chains && !pd.finished; ++c) {
         // completion: each kernel's last block writes its sequence number after the results (system fence)
         const volatile unsigned long long* flag = &e->h_out[pd.buf][size_t(c) * kResultStride + kSeqIndex];
         bool done = false;
@@ -756,6 +784,16 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
     const unsigned long long* r = folded;
     e->last_partials.clear();
     bool nonfinite = false;
+    // shard group: wait for every rank's block of this request vector and combine (XOR / sum / OR) across ranks
+    bgr_partial combined[kMaxSaves];
+    if (pd.gseq) {
+        uint32_t n = 0;
+        uint64_t flags = 0;
+        std::string err;
+        if (!e->group || !e->group->combine(pd.gseq, combined, kMaxSaves, &n, &flags, &err))
+            return fail(BGR_ERR_STATE, e->group ? err : "request vector was submitted inside a shard group that has been left");
+        if (flags & 1ULL) nonfinite = true;
+    }
     for (uint32_t k = 0; k < pd.n_saves; ++k) {
         bgr_partial p;
         std::memset(&p, 0, sizeof p);
@@ -769,7 +807,9 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
     }
     if (n_out) *n_out = pd.n_saves;
     for (uint32_t k = 0; k < pd.n_saves && k < cap && out; ++k) {
-        if (e->cfg.flags & BGR_CFG_SHARDED) {
+        if (pd.gseq) {
+            fold(combined[k], &out[k]);  // the frame checksum of the WHOLE world, identical on every rank
+        } else if (e->cfg.flags & BGR_CFG_SHARDED) {
             out[k].frame = pd.frames[k]; out[k].has_checksum = 0; out[k].lo = 0; out[k].hi = 0;
         } else {
             fold(e->last_partials[k], &out[k]);
@@ -779,12 +819,14 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
     return BGR_OK;
 }
 
+// Entry points that touch the live world (read / write / spawn / peek ...) first wait for every submitted request
+// vector.  The results of un-collected submits STAY queued: a later bgr_collect still returns their checksums (and
+// the non-finite status), in order — nothing is dropped on the floor.
 int drain(bgr_engine* e) {
     e->tiledep_chain = false;  // callers enqueue ordinary (fully ordered) work next
-    while (!e->pending.empty()) {
-        int rc = collect(e, nullptr, 0, nullptr);
-        if (rc != BGR_OK && rc != BGR_ERR_NON_FINITE) return rc;
-    }
+    if (e->pending.empty()) return BGR_OK;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));  // every chain stream is joined into the main stream by an event
+    for (Pending& pd : e->pending) pd.finished = true;
     return BGR_OK;
 }
 
@@ -1008,6 +1050,13 @@ BGR_API void bgr_engine_destroy(bgr_engine* e) {
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->group) {
+        cudaHostUnregister(e->group->blocks_base());
+        for (int b = 0; b < bgr_engine::kBufs; ++b) { e->h_out[b] = e->own_h_out[b]; e->d_out[b] = e->own_d_out[b]; }
+        delete e->group;
+        e->group = nullptr;
+    }
+    if (e->d_trace) cudaFree(e->d_trace);
     for (int i = 0; i < bgr_engine::kBufs; ++i) {
         if (e->h_out[i]) cudaFreeHost(e->h_out[i]);
         if (e->h_spawn[i]) cudaFreeHost(e->h_spawn[i]);
@@ -1108,6 +1157,10 @@ BGR_API int bgr_add_system(bgr_engine* e, uint32_t system, const uint32_t* colum
         if (!need(3, 4) || eb(0) != 40 || eb(1) != 12 || eb(2) != 8)
             return fail(BGR_ERR_INVALID_ARGUMENT, "spawn_particles binds {Transform(40B), Velocity(12B), Ttl(8B)} with params {rate, ttl, seed_lo, seed_hi}");
         if (e->spawn_sys >= 0) return fail(BGR_ERR_INVALID_ARGUMENT, "spawn_particles registered twice");
+        // A shard appends rows locally: the RollbackOrdered index order_base + row of a newborn would collide with the
+        // next shard's range, and every shard would draw the same ParticleRng stream.  Dynamic spawning needs one GPU.
+        if ((e->cfg.flags & BGR_CFG_SHARDED) || e->cfg.order_base != 0)
+            return fail(BGR_ERR_UNSUPPORTED, "spawn_particles is not supported on a sharded engine (BGR_CFG_SHARDED / order_base != 0)");
         if (s.params[0] == 0 || s.params[0] > 4096) return fail(BGR_ERR_INVALID_ARGUMENT, "spawn rate must be in 1..4096");
         e->spawn_sys = int(e->systems.size());
         e->st.rng.seed_from_u64(uint64_t(s.params[2]) | (uint64_t(s.params[3]) << 32));  // insert_resource(ParticleRng(seed_from_u64(seed)))
@@ -1233,6 +1286,9 @@ BGR_API int bgr_spawn(bgr_engine* e, uint32_t count, uint32_t* first_row_out) {
     int rc = drain(e);
     if (rc != BGR_OK) return rc;
     if (uint64_t(e->st.n_rows) + count > e->cfg.max_entities) return fail(BGR_ERR_CAPACITY, "spawn exceeds max_entities");
+    if (count && e->ticked && ((e->cfg.flags & BGR_CFG_SHARDED) || e->cfg.order_base != 0))
+        return fail(BGR_ERR_UNSUPPORTED, "bgr_spawn after the initial population is not supported on a sharded engine "
+                                         "(the new rows' RollbackOrdered indices would collide with the next shard's range)");
     uint32_t first = e->st.n_rows;
     if (count) {
         k_spawn_rows<<<e->grid_for(count, 64), 256, 0, e->stream>>>(e->image(0), e->words, first, count);
@@ -1407,9 +1463,11 @@ BGR_API int bgr_handle_requests(bgr_engine* e, const bgr_session_info* session, 
                                 uint32_t n_requests, bgr_checksum* checksums_out, uint32_t checksums_cap,
                                 uint32_t* n_checksums_out) {
     if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
-    int rc = drain(e);
-    if (rc != BGR_OK) return rc;
-    rc = submit(e, session, requests, n_requests);
+    // the checksums returned must be THIS vector's: earlier bgr_submit_requests have to be collected first
+    if (!e->pending.empty())
+        return fail(BGR_ERR_STATE, "bgr_handle_requests with un-collected bgr_submit_requests pending: call bgr_collect first");
+    e->tiledep_chain = false;
+    int rc = submit(e, session, requests, n_requests);
     if (rc != BGR_OK) return rc;
     return collect(e, checksums_out, checksums_cap, n_checksums_out);
 }
@@ -1511,6 +1569,140 @@ BGR_API int bgr_last_path(bgr_engine* e, uint32_t* fused_out) {
 BGR_API int bgr_synchronize(bgr_engine* e) {
     if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
     CUDA_TRY(cudaStreamSynchronize(e->stream));
+    return BGR_OK;
+}
+
+
+// ---- shard group (multi-GPU cross-shard exchange inside the engine; shard_group.hpp) ----
+BGR_API int bgr_shard_group_join(bgr_engine* e, const char* name, uint32_t rank, uint32_t world_size, uint32_t timeout_ms) {
+    if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
+    if (!name || !*name) return fail(BGR_ERR_INVALID_ARGUMENT, "null group name");
+    if (!(e->cfg.flags & BGR_CFG_SHARDED)) return fail(BGR_ERR_STATE, "only a BGR_CFG_SHARDED engine can join a shard group");
+    if (e->group) return fail(BGR_ERR_STATE, "engine is already in a shard group");
+    if (!e->pending.empty()) return fail(BGR_ERR_STATE, "collect every submitted request vector before joining a shard group");
+    if (e->n_chains != 1) return fail(BGR_ERR_UNSUPPORTED, "BGR_TUNE_CHAINS > 1 cannot be combined with a shard group");
+    CUDA_TRY(cudaSetDevice(e->cfg.device));
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    auto* g = new ShardGroup();
+    if (timeout_ms) g->timeout_ms = timeout_ms;
+    std::string err;
+    const uint32_t block_words = uint32_t(kResultStride) * bgr_engine::kMaxChains;
+    static_assert(bgr_engine::kBufs == int(kGroupBufs) && kMaxSaves == int(kGroupMaxSaves) && kAccStride == int(kGroupAccStride),
+                  "shard_group.hpp mirrors the engine's result block layout");
+    if (!g->join(name, rank, world_size, block_words, e->seq, &err)) { delete g; return fail(BGR_ERR_STATE, err); }
+    // the block area becomes page-locked and visible to this GPU: the fused kernel's last block stores its result rows there
+    cudaError_t ce = cudaHostRegister(g->blocks_base(), g->blocks_bytes(), cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (ce != cudaSuccess) { delete g; return fail(BGR_ERR_CUDA, std::string("cudaHostRegister(shard group segment): ") + cudaGetErrorString(ce)); }
+    for (int b = 0; b < bgr_engine::kBufs; ++b) {
+        e->own_h_out[b] = e->h_out[b]; e->own_d_out[b] = e->d_out[b];
+        e->h_out[b] = reinterpret_cast<unsigned long long*>(g->block(rank, uint32_t(b)));
+        void* dp = nullptr;
+        ce = cudaHostGetDevicePointer(&dp, e->h_out[b], 0);
+        if (ce != cudaSuccess) {
+            for (int k = 0; k <= b; ++k) { e->h_out[k] = e->own_h_out[k]; e->d_out[k] = e->own_d_out[k]; }
+            cudaHostUnregister(g->blocks_base());
+            delete g;
+            return fail(BGR_ERR_CUDA, std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(ce));
+        }
+        e->d_out[b] = static_cast<unsigned long long*>(dp);
+    }
+    e->group = g;
+    e->gseq = 0;
+    e->next_buf = 0;
+    return BGR_OK;
+}
+
+BGR_API int bgr_shard_group_leave(bgr_engine* e) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    if (!e->group) return BGR_OK;
+    if (!e->pending.empty()) return fail(BGR_ERR_STATE, "collect every submitted request vector before leaving the shard group");
+    cudaSetDevice(e->cfg.device);
+    cudaStreamSynchronize(e->stream);
+    cudaHostUnregister(e->group->blocks_base());
+    for (int b = 0; b < bgr_engine::kBufs; ++b) { e->h_out[b] = e->own_h_out[b]; e->d_out[b] = e->own_d_out[b]; }
+    delete e->group;
+    e->group = nullptr;
+    return BGR_OK;
+}
+
+// the group's host logic on its own (no GPU): CPU tests drive join / publish / collect with a stand-in for the kernel's publish
+struct bgr_group { ShardGroup g; uint32_t n_columns = 0; };
+BGR_API bgr_group* bgr_group_join(const char* name, uint32_t rank, uint32_t world_size, uint32_t n_columns, uint32_t timeout_ms) {
+    if (!name) { fail(BGR_ERR_INVALID_ARGUMENT, "null group name"); return nullptr; }
+    auto* h = new bgr_group();
+    h->n_columns = n_columns;
+    if (timeout_ms) h->g.timeout_ms = timeout_ms;
+    std::string err;
+    if (!h->g.join(name, rank, world_size, uint32_t(kResultStride) * bgr_engine::kMaxChains, 0, &err)) { fail(BGR_ERR_STATE, err); delete h; return nullptr; }
+    return h;
+}
+BGR_API void bgr_group_leave(bgr_group* h) { delete h; }
+BGR_API int bgr_group_publish(bgr_group* h, uint64_t gseq, const bgr_partial* partials, uint32_t n) {
+    if (!h || (!partials && n) || gseq == 0 || n > uint32_t(kMaxSaves)) return fail(BGR_ERR_INVALID_ARGUMENT, "bad argument");
+    std::string err;
+    if (!h->g.wait_reusable(gseq, &err)) return fail(BGR_ERR_STATE, err);
+    int32_t frames[kMaxSaves]; uint32_t totals[kMaxSaves];
+    for (uint32_t k = 0; k < n; ++k) { frames[k] = partials[k].frame; totals[k] = uint32_t(partials[k].total); }
+    h->g.publish_meta(gseq, n, h->n_columns, frames, totals);
+    h->g.publish_block_from_host(gseq, partials, n);
+    return BGR_OK;
+}
+BGR_API int bgr_group_collect(bgr_group* h, uint64_t gseq, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
+    if (!h || gseq == 0) return fail(BGR_ERR_INVALID_ARGUMENT, "bad argument");
+    bgr_partial combined[kMaxSaves];
+    uint32_t n = 0;
+    uint64_t flags = 0;
+    std::string err;
+    if (!h->g.combine(gseq, combined, kMaxSaves, &n, &flags, &err)) return fail(BGR_ERR_STATE, err);
+    for (uint32_t k = 0; k < n && k < cap && out; ++k) fold(combined[k], &out[k]);
+    if (n_out) *n_out = n;
+    return BGR_OK;
+}
+
+// No session (schedule_systems.rs:70-79): "reset time data and snapshots" — the frame resources go back to their
+// session-less values; the caller (run_ggrs_schedules' mirror) also clears LocalPlayers and its accumulator.
+BGR_API int bgr_reset_session(bgr_engine* e) {
+    if (!e) return fail(BGR_ERR_INVALID_ARGUMENT, "null engine");
+    if (!e->pending.empty()) return fail(BGR_ERR_STATE, "collect every submitted request vector first");
+    e->st.frame_count = 0;        // RollbackFrameCount(0)
+    e->st.confirmed = -1;         // ConfirmedFrameCount(-1)
+    e->st.has_maxpred = true;     // MaxPredictionWindow(8)
+    e->st.maxpred = 8;
+    return BGR_OK;
+}
+
+BGR_API int bgr_stream(bgr_engine* e, void** stream_out) {
+    if (!e || !stream_out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *stream_out = e->stream;
+    return BGR_OK;
+}
+
+// Device-side launch trace: every fused launch records when its first block started and when its last block
+// finished (ns of the GPU's globaltimer) — the evidence for overlapping consecutive ticks when no
+// system profiler is available.  Two atomics per block; off unless enabled.
+BGR_API int bgr_trace_enable(bgr_engine* e, uint32_t capacity) {
+    if (!e || !e->built) return fail(BGR_ERR_STATE, "engine not built");
+    int rc = drain(e);
+    if (rc != BGR_OK) return rc;
+    if (e->d_trace) { CUDA_TRY(cudaFree(e->d_trace)); e->d_trace = nullptr; e->trace_cap = 0; }
+    if (capacity == 0) return BGR_OK;
+    std::vector<unsigned long long> init(size_t(capacity) * 2);
+    for (uint32_t i = 0; i < capacity; ++i) { init[2 * i] = ~0ULL; init[2 * i + 1] = 0ULL; }
+    CUDA_TRY(cudaMalloc(&e->d_trace, init.size() * sizeof(unsigned long long)));
+    CUDA_TRY(cudaMemcpy(e->d_trace, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+    e->trace_cap = capacity;
+    e->trace_first_seq = e->seq + 1;
+    return BGR_OK;
+}
+BGR_API int bgr_trace_read(bgr_engine* e, uint64_t* start_end_ns_out, uint32_t cap, uint32_t* n_out) {
+    if (!e || !e->d_trace) return fail(BGR_ERR_STATE, "trace not enabled");
+    int rc = drain(e);
+    if (rc != BGR_OK) return rc;
+    CUDA_TRY(cudaStreamSynchronize(e->stream));
+    const uint64_t done = e->seq + 1 > e->trace_first_seq ? e->seq + 1 - e->trace_first_seq : 0;
+    const uint32_t n = uint32_t(std::min<uint64_t>(std::min<uint64_t>(done, e->trace_cap), cap));
+    if (n && start_end_ns_out) CUDA_TRY(cudaMemcpy(start_end_ns_out, e->d_trace, size_t(n) * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (n_out) *n_out = n;
     return BGR_OK;
 }
 

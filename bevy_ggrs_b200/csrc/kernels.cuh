@@ -72,9 +72,9 @@ struct Op {
     uint32_t save_index;    // SAVE: which accumulator row.  ADVANCE+SPAWN: number of spawned rows
     uint32_t flags;
     uint32_t call_count;    // ADVANCE: value of the un-rolled-back host counter (test system).  ADVANCE+SPAWN: offset into spawn_vals
-    uint8_t inputs[4];      // ADVANCE: first 4 player inputs (u8)
+    uint8_t inputs[8];      // ADVANCE: PlayerInputs<T>.0[handle].0 for every handle (u8, BGR_MAX_PLAYERS)
 };
-static_assert(sizeof(Op) == 32, "Op must stay 32 bytes");
+static_assert(sizeof(Op) == 36, "Op layout");
 
 enum ProgFlags : uint32_t {
     PF_READ_LIVE = 1u,           // program does not start with LOAD: initial state comes from image 0
@@ -102,6 +102,7 @@ struct ProgramParams {
     unsigned int* ticket;       // [0] block-completion ticket, [1] dynamic tile counter
     const float2* spawn_vals;   // (vx, vy) of every particle spawned by this program (host-mapped), particles.rs:265
     unsigned long long seq;     // written to out[kSeqIndex] after the results (completion flag the host polls)
+    unsigned long long* trace;  // nullptr, or this launch's row of the launch trace: [0] min block start, [1] max block end (globaltimer ns)
     uint32_t words, tile_bytes, n_ops, n_saves;
     uint32_t tile_begin, n_tiles;  // this launch covers tiles [tile_begin, n_tiles) (one chain of the entity range)
     unsigned int* tile_done;       // [tiles] sequence number of the last PF_TILE_SIGNAL launch that finished the tile
@@ -144,6 +145,11 @@ template <> __device__ __forceinline__ void alive_store<1>(uint8_t* p, uint32_t 
 template <> __device__ __forceinline__ void alive_store<2>(uint8_t* p, uint32_t a) { __stcs(reinterpret_cast<unsigned short*>(p), (unsigned short)a); }
 template <> __device__ __forceinline__ void alive_store<4>(uint8_t* p, uint32_t a) { __stcs(reinterpret_cast<uint32_t*>(p), a); }
 
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 __device__ __forceinline__ uint32_t f32_bits_nonfinite(uint32_t b) { return ((b & 0x7f800000u) == 0x7f800000u) ? 1u : 0u; }
 
 // mask with byte j = 0x01 for every row (row0 + j) < n_rows
@@ -252,6 +258,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     __shared__ unsigned int s_last;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    if (p.trace && tid == 0) atomicMin(&p.trace[0], globaltimer_ns());  // bgr_trace_enable: when did this launch's first block start
     // Programmatic dependent launch: let the NEXT request vector's kernel be launched and its blocks scheduled
     // into SM slots as this grid drains (hides launch latency and block ramp-up between back-to-back ticks) ...
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -570,6 +577,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     }
     __threadfence();
     __syncthreads();
+    if (p.trace && tid == 0) atomicMax(&p.trace[1], globaltimer_ns());  // ... and when did its last block finish its tiles
     if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1u);
     __syncthreads();
     if (s_last) {
@@ -799,7 +807,7 @@ __global__ void __launch_bounds__(256) k_sys_particles_spawn(uint8_t* img, uint3
 // `FRICTION.powf(dt)` is libm on the CPU and CUDA powf here: this is the one system of the path whose f32
 // results are only guaranteed within a tolerance (|d| <= 1e-5 * max(1, |x|), tested), not bit-exact.
 __global__ void k_sys_box_move(uint8_t* img, uint32_t words, uint32_t t_plane, uint32_t v_plane, uint32_t n_rows,
-                               uint32_t dt_bits, uint32_t inputs_packed, uint32_t n_players, unsigned long long order_base,
+                               uint32_t dt_bits, unsigned long long inputs_packed, uint32_t n_players, unsigned long long order_base,
                                uint32_t need) {
     const float dt = __uint_as_float(dt_bits);
     const float ACCELERATION = 18.0f, MAX_SPEED = 3.0f, FRICTION = 0.0018f, PLANE_SIZE = 5.0f, CUBE_SIZE = 0.2f;
@@ -810,7 +818,7 @@ __global__ void k_sys_box_move(uint8_t* img, uint32_t words, uint32_t t_plane, u
         float tx = t[0], ty = t[kTileRows], tz = t[2 * kTileRows];
         float vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
         const unsigned long long handle = order_base + r;
-        const uint32_t input = handle < n_players && handle < 4 ? (inputs_packed >> (8 * uint32_t(handle))) & 0xffu : 0u;
+        const uint32_t input = handle < n_players && handle < 8 ? uint32_t(inputs_packed >> (8 * uint32_t(handle))) & 0xffu : 0u;
         const bool up = input & 1u, down = input & 2u, left = input & 4u, right = input & 8u;
         const float a = __fmul_rn(ACCELERATION, dt);
         if (up && !down) vz = __fsub_rn(vz, a);

@@ -244,6 +244,34 @@ class Engine:
     def synchronize(self) -> None:
         self._check(self._lib.bgr_synchronize(self._h))
 
+    def stream(self) -> int:
+        """cudaStream_t (as an int) the engine launches on — for timing events recorded by the caller."""
+        p = C.c_void_p()
+        self._check(self._lib.bgr_stream(self._h, C.byref(p)))
+        return p.value or 0
+
+    def reset_session(self) -> None:
+        """schedule_systems.rs:70-79: no session -> RollbackFrameCount(0), ConfirmedFrameCount(-1), MaxPredictionWindow(8)."""
+        self._check(self._lib.bgr_reset_session(self._h))
+
+    # ---- device-side launch trace ----
+    def trace_enable(self, capacity: int) -> None:
+        self._check(self._lib.bgr_trace_enable(self._h, capacity))
+
+    def trace_read(self, capacity: int) -> np.ndarray:
+        """(n, 2) uint64: [first block start, last block end] of each traced fused launch, GPU globaltimer ns."""
+        out = np.zeros((capacity, 2), dtype=np.uint64)
+        n = C.c_uint32()
+        self._check(self._lib.bgr_trace_read(self._h, out.ctypes.data, capacity, C.byref(n)))
+        return out[: n.value]
+
+    # ---- shard group (multi-GPU): cross-shard checksum fold inside the engine ----
+    def shard_group_join(self, name: str, rank: int, world_size: int, timeout_ms: int = 0) -> None:
+        self._check(self._lib.bgr_shard_group_join(self._h, name.encode(), rank, world_size, timeout_ms))
+
+    def shard_group_leave(self) -> None:
+        self._check(self._lib.bgr_shard_group_leave(self._h))
+
 
 def fold_partials(partial: "capi.bgr_partial") -> int:
     lib = capi.load_library()

@@ -143,6 +143,14 @@ class App:
         plugin.build(self)
         return self
 
+    def remove_resource(self, kind) -> "App":
+        """`world.remove_resource::<Session<T>>()`: the next update takes the session-less branch."""
+        if kind is Session:
+            self._session = None
+        else:
+            raise TypeError(f"unsupported resource {kind!r}")
+        return self
+
     def insert_resource(self, res) -> "App":
         if isinstance(res, Session):
             self._session = res
@@ -245,8 +253,11 @@ class App:
         while self._accumulator_ns >= fps_delta:
             self._accumulator_ns -= fps_delta
             if self._session is None:
+                # "No session has been started yet, reset time data and snapshots" (schedule_systems.rs:70-79)
                 self._accumulator_ns = 0
                 self._run_slow = False
+                self.local_players = LocalPlayers([])
+                self.world.reset_session()  # RollbackFrameCount(0), ConfirmedFrameCount(-1), MaxPredictionWindow(8)
                 return
             self._tick()
 

@@ -43,7 +43,7 @@ extern "C" {
 #define BGR_API __attribute__((visibility("default")))
 
 #define BGR_ABI_VERSION 1u
-#define BGR_MAX_PLAYERS 8u
+#define BGR_MAX_PLAYERS 8u      /* every handle 0..7 reaches the systems (PlayerInputs<T>.0[handle], box_game.rs:171) */
 #define BGR_MAX_REQUESTS 80u  /* max requests per bgr_handle_requests call (2*32+2 for a 32-frame SyncTest) */
 
 typedef enum bgr_status {
@@ -237,6 +237,9 @@ BGR_API int bgr_rollback_frame_count(bgr_engine* e, int32_t* out);
 BGR_API int bgr_set_rollback_frame_count(bgr_engine* e, int32_t frame);
 BGR_API int bgr_confirmed_frame_count(bgr_engine* e, int32_t* out);
 BGR_API int bgr_max_prediction_window(bgr_engine* e, uint32_t* out);
+/* the session-less branch of run_ggrs_schedules (schedule_systems.rs:70-79): RollbackFrameCount(0),
+ * ConfirmedFrameCount(-1), MaxPredictionWindow(8) */
+BGR_API int bgr_reset_session(bgr_engine* e);
 
 /* ---- snapshot ring (GgrsSnapshots, src/snapshot/mod.rs:94-271) -------------------------- */
 BGR_API int bgr_set_depth(bgr_engine* e, uint32_t depth);                 /* :120-135 */
@@ -261,7 +264,10 @@ BGR_API int bgr_handle_requests(bgr_engine* e, const bgr_session_info* session,
                                 const bgr_request* requests, uint32_t n_requests,
                                 bgr_checksum* checksums_out, uint32_t checksums_cap, uint32_t* n_checksums_out);
 /* Asynchronous pair: submit enqueues on the engine stream and returns; collect waits and
- * returns the checksums of the oldest un-collected submit.  At most 8 submits may be un-collected. */
+ * returns the checksums of the oldest un-collected submit.  At most 8 submits may be un-collected.
+ * Entry points that read or edit the world (bgr_read_component, bgr_spawn, bgr_peek ...) wait for the submitted
+ * vectors but leave their results queued for bgr_collect; bgr_handle_requests (and the one-schedule helpers above)
+ * return BGR_ERR_STATE while submits are un-collected. */
 BGR_API int bgr_submit_requests(bgr_engine* e, const bgr_session_info* session,
                                 const bgr_request* requests, uint32_t n_requests);
 BGR_API int bgr_collect(bgr_engine* e, bgr_checksum* checksums_out, uint32_t checksums_cap,
@@ -275,6 +281,24 @@ BGR_API int bgr_fold_partials(const bgr_partial* combined, bgr_checksum* out);
  * no per-tick allocation), and the fold over an array of already combined partials. */
 BGR_API int bgr_collect_partials(bgr_engine* e, bgr_partial* partials_out, uint32_t cap, uint32_t* n_out);
 BGR_API int bgr_fold_partials_n(const bgr_partial* combined, uint32_t n, bgr_checksum* out);
+
+/* ---- shard group: the cross-shard step inside the engine (multi-GPU, one process per GPU, one node) -----------------
+ * Entity-range shards never exchange state (systems read no other entity, box_game.rs:162-169; the
+ * checksum is an XOR over entities, component_checksum.rs:88-89).  The only exchange is 64 bytes of partials per
+ * SaveGameState.  After every rank's BGR_CFG_SHARDED engine has joined the same group, bgr_handle_requests /
+ * bgr_collect on ANY rank return the frame checksum of the WHOLE world (has_checksum = 1) — what
+ * `cell.save(frame, None, checksum)` needs (schedule_systems.rs:231-236) — with no call outside this library:
+ * the result blocks live in one shared host segment that every rank's GPU stores into and every rank's CPU polls.
+ * Every rank must be handed the same request vectors in the same order (they all replay the same GGRS session).
+ * `name` must be unique per group instance (e.g. "<launcher pid>_<port>"); timeout_ms = 0 selects 60 s. */
+BGR_API int bgr_shard_group_join(bgr_engine* e, const char* name, uint32_t rank, uint32_t world_size, uint32_t timeout_ms);
+BGR_API int bgr_shard_group_leave(bgr_engine* e);
+/* the group's host logic without an engine (no GPU call): CPU tests publish partials computed elsewhere */
+typedef struct bgr_group bgr_group;
+BGR_API bgr_group* bgr_group_join(const char* name, uint32_t rank, uint32_t world_size, uint32_t n_columns, uint32_t timeout_ms);
+BGR_API void bgr_group_leave(bgr_group* g);
+BGR_API int bgr_group_publish(bgr_group* g, uint64_t group_seq, const bgr_partial* partials, uint32_t n);  /* group_seq = 1, 2, ... */
+BGR_API int bgr_group_collect(bgr_group* g, uint64_t group_seq, bgr_checksum* out, uint32_t cap, uint32_t* n_out);
 
 /* ---- checksum_hasher() (src/snapshot/mod.rs:315-317) for host-side parts -------------------------------
  * Resources stay on the host (a few bytes, not data-parallel).  A shim that registers
@@ -290,6 +314,11 @@ BGR_API int bgr_launch_count(bgr_engine* e, uint64_t* kernels_launched_out);
 BGR_API int bgr_slot_bytes(bgr_engine* e, uint64_t* bytes_out);  /* algorithmic bytes of one frame slot at the current row count */
 BGR_API int bgr_last_path(bgr_engine* e, uint32_t* fused_out);   /* 1 if the last handle_requests used the fused program kernel */
 BGR_API int bgr_synchronize(bgr_engine* e);
+BGR_API int bgr_stream(bgr_engine* e, void** stream_out);        /* the cudaStream_t the engine launches on (timing events) */
+/* device-side launch trace: [first block start, last block end] (GPU globaltimer ns) of every fused launch after the
+ * call, up to `capacity` launches; bgr_trace_read copies pairs out (waits for the GPU).  capacity 0 disables. */
+BGR_API int bgr_trace_enable(bgr_engine* e, uint32_t capacity);
+BGR_API int bgr_trace_read(bgr_engine* e, uint64_t* start_end_ns_out, uint32_t cap_launches, uint32_t* n_out);
 
 /* ---- host-side ring bookkeeping on its own ------------------------------------------------------
  * The frame -> HBM-slot queue the engine keeps for GgrsSnapshots (mod.rs:94-271), exposed without

@@ -10,7 +10,7 @@
 //   peek      mod.rs:233-240
 //   set_depth mod.rs:120-135, default depth = DEFAULT_FPS = 60 (mod.rs:112, lib.rs:58)
 // PINNING: the reference's own 11 unit tests (mod.rs:365-508) are ported verbatim in
-// tests/test_oracle_ring.py and run against this class through oracle_capi.
+// tests/test_ring_kats.py and run against this class through oracle_capi.
 #pragma once
 #include <cstdint>
 #include <cstdlib>

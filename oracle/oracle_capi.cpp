@@ -212,6 +212,8 @@ ORC_API int32_t orc_rollback_frame_count(World* w) { return w->rollback_frame_co
 ORC_API void orc_set_rollback_frame_count(World* w, int32_t f) { w->rollback_frame_count = f; }
 ORC_API int32_t orc_confirmed_frame_count(World* w) { return w->confirmed_frame_count; }
 ORC_API void orc_set_max_prediction(World* w, uint32_t p) { w->max_prediction = p; }
+// the session-less branch of run_ggrs_schedules (schedule_systems.rs:70-79)
+ORC_API void orc_reset_session(World* w) { w->rollback_frame_count = 0; w->confirmed_frame_count = -1; w->max_prediction = 8; }
 ORC_API uint32_t orc_last_dt_bits(World* w) { uint32_t b; std::memcpy(&b, &w->ggrs_time.delta_secs, 4); return b; }
 
 ORC_API int orc_save_world(World* w, bgr_checksum* out) {

@@ -90,6 +90,8 @@ pub struct bgr_config {
 }
 
 pub enum bgr_engine {}
+#[allow(non_camel_case_types)]
+pub enum bgr_group {}
 
 extern "C" {
     pub fn bgr_abi_version() -> u32;
@@ -139,4 +141,14 @@ extern "C" {
     pub fn bgr_slot_bytes(e: *mut bgr_engine, bytes_out: *mut u64) -> c_int;
     pub fn bgr_last_path(e: *mut bgr_engine, fused_out: *mut u32) -> c_int;
     pub fn bgr_synchronize(e: *mut bgr_engine) -> c_int;
+    pub fn bgr_stream(e: *mut bgr_engine, stream_out: *mut *mut c_void) -> c_int;
+    pub fn bgr_trace_enable(e: *mut bgr_engine, capacity: u32) -> c_int;
+    pub fn bgr_trace_read(e: *mut bgr_engine, start_end_ns_out: *mut u64, cap_launches: u32, n_out: *mut u32) -> c_int;
+    pub fn bgr_reset_session(e: *mut bgr_engine) -> c_int;
+    pub fn bgr_shard_group_join(e: *mut bgr_engine, name: *const c_char, rank: u32, world_size: u32, timeout_ms: u32) -> c_int;
+    pub fn bgr_shard_group_leave(e: *mut bgr_engine) -> c_int;
+    pub fn bgr_group_join(name: *const c_char, rank: u32, world_size: u32, n_columns: u32, timeout_ms: u32) -> *mut bgr_group;
+    pub fn bgr_group_leave(g: *mut bgr_group);
+    pub fn bgr_group_publish(g: *mut bgr_group, group_seq: u64, partials: *const bgr_partial, n: u32) -> c_int;
+    pub fn bgr_group_collect(g: *mut bgr_group, group_seq: u64, out: *mut bgr_checksum, cap: u32, n_out: *mut u32) -> c_int;
 }

@@ -83,6 +83,7 @@ def load_oracle() -> C.CDLL:
         "orc_set_rollback_frame_count": (None, [vp, i32]),
         "orc_confirmed_frame_count": (i32, [vp]),
         "orc_set_max_prediction": (None, [vp, u32]),
+        "orc_reset_session": (None, [vp]),
         "orc_last_dt_bits": (u32, [vp]),
         "orc_save_world": (C.c_int, [vp, C.POINTER(capi.bgr_checksum)]),
         "orc_load_world": (C.c_int, [vp]),
@@ -219,6 +220,9 @@ class OracleWorld:
 
     def set_depth(self, depth):
         self._lib.orc_set_max_prediction(self._h, depth)
+
+    def reset_session(self):
+        self._lib.orc_reset_session(self._h)
 
     def snapshot_frames(self):
         buf = (C.c_int32 * 128)()

@@ -74,3 +74,33 @@ def test_box_game_synctest_c1_gpu_vs_oracle():
     v = eng.read_component(vel, 0, 2).view(np.float32)
     assert np.all(np.linalg.norm(v, axis=1) <= 3.0 + 1e-5) and np.any(v != 0)
     assert not eng.last_path_fused()                    # box_game has no fused bundle: stepwise path
+
+
+def test_box_game_eight_players_every_handle_reaches_move_cube_system():
+    """`inputs[p.handle]` for EVERY handle (box_game.rs:171): BGR_MAX_PLAYERS = 8 inputs cross the ABI and all of them
+    steer their cube (round 1 silently gave handles 4..7 input 0)."""
+    from bevy_ggrs_b200.session import ADVANCE, SAVE, Request
+    eng, orc = Engine(max_entities=8, max_depth=4), OracleWorld()
+    cols = []
+    for w in (eng, orc):
+        vel = w.rollback_component("Velocity", 12)
+        tf = w.rollback_component("Transform", 40, capi.BGR_STRATEGY_CLONE)
+        w.add_system(capi.BGR_SYS_BOX_MOVE, [tf, vel])
+        w.build()
+        first = w.spawn(8)
+        t = np.zeros((8, 10), np.float32)
+        t[:, 0] = np.linspace(-1.5, 1.5, 8); t[:, 1] = 0.1; t[:, 6] = 1.0; t[:, 7:10] = 1.0
+        w.write_component(tf, first, t)
+        cols = [tf, vel]
+    nosess = (capi.BGR_SESSION_NONE, 0, 0, 0)
+    inputs = [0b0001, 0b0010, 0b0100, 0b1000, 0b0101, 0b1010, 0b1001, 0b0110]
+    reqs = []
+    for f in range(12):
+        reqs += [Request(SAVE, f), Request(ADVANCE, f, inputs)]
+    assert eng.handle_requests(nosess, reqs) == orc.handle_requests(nosess, reqs)
+    v = eng.read_component(cols[1], 0, 8).view(np.float32)
+    vo = orc.read_component(cols[1], 0, 8).view(np.float32)
+    assert np.all(np.abs(v - vo) <= 1e-5 * np.maximum(1.0, np.abs(vo)))
+    assert np.all(np.linalg.norm(v, axis=1) > 0.5)               # all eight cubes were accelerated by their own input
+    assert v[4, 0] < 0 and v[4, 2] < 0 and v[7, 0] < 0 and v[7, 2] > 0   # handles 4 and 7: LEFT|UP, LEFT|DOWN
+    eng.close(); orc.close()

@@ -202,3 +202,77 @@ def test_async_download_sees_the_world_at_begin_and_overlaps_later_ticks(flags):
     with pytest.raises(BgrError):
         eng.download_begin(t, 0, 12, n - 5, 10, host["tr"])  # beyond the spawned rows
     eng.close()
+
+
+def test_reads_between_submits_keep_their_results_queued_for_collect():
+    """An entry point that touches the world waits for the submitted request vectors but must not swallow their
+    results: a later bgr_collect still returns every checksum, in order (desync detection has no gaps)."""
+    n = 2000
+    eng, orc, cols = _pair(n, seed=3, ttl=(4, 30))
+    tick = lambda f: [Request(SAVE, f), Request(ADVANCE, f, [0, 0])]
+    want = []
+    for f in range(3):
+        eng.submit_requests(NOSESS, tick(f))
+        want += orc.handle_requests(NOSESS, tick(f))
+    with pytest.raises(BgrError) as ei:          # the synchronous call would return the wrong vector's checksums
+        eng.handle_requests(NOSESS, tick(3))
+    assert ei.value.status == capi.BGR_ERR_STATE and "bgr_collect" in str(ei.value)
+    alive = orc.read_alive(0, n).astype(bool)    # a read in the middle: waits for the GPU, results stay queued
+    assert np.array_equal(eng.read_alive(0, n).astype(bool), alive)
+    assert np.array_equal(eng.read_component(cols[0], 0, n)[alive], orc.read_component(cols[0], 0, n)[alive])
+    got = []
+    for _ in range(3):
+        got += eng.collect()
+    assert got == want and len(got) == 3
+    with pytest.raises(BgrError):
+        eng.collect()                            # nothing left
+    assert eng.handle_requests(NOSESS, tick(3)) == orc.handle_requests(NOSESS, tick(3))
+    eng.close()
+
+
+def test_non_finite_status_survives_a_drain():
+    eng, orc, cols = _pair(600, seed=4)
+    bad = eng.read_component(cols[1], 0, 1).copy()
+    bad.view(np.float32)[0, 1] = np.inf
+    eng.write_component(cols[1], 7, bad)
+    eng.submit_requests(NOSESS, [Request(SAVE, 0)])
+    eng.read_alive(0, 10)                        # drains
+    with pytest.raises(BgrError) as ei:
+        eng.collect()
+    assert ei.value.status == capi.BGR_ERR_NON_FINITE
+    eng.close()
+
+
+def test_sharded_engines_refuse_dynamic_spawning():
+    """A shard appends rows locally: a newborn's RollbackOrdered index would collide with the next shard's range and
+    every shard would draw the same ParticleRng stream — refused instead of silently diverging from one GPU."""
+    for flags, base in ((capi.BGR_CFG_SHARDED, 0), (0, 4096)):
+        eng = Engine(max_entities=4096, max_depth=4, flags=flags, order_base=base)
+        with pytest.raises(BgrError) as ei:
+            register_particles(eng, spawn_rate=8)
+        assert ei.value.status == capi.BGR_ERR_UNSUPPORTED
+        eng.close()
+    eng = Engine(max_entities=4096, max_depth=4, flags=capi.BGR_CFG_SHARDED, order_base=0)
+    cols = register_particles(eng)
+    eng.build()
+    populate(eng, cols, *synth_particles(1000, 1, 5, 50))       # the initial population is fine
+    eng.handle_requests(NOSESS, [Request(SAVE, 0), Request(ADVANCE, 0, [0])])
+    with pytest.raises(BgrError) as ei:
+        eng.spawn(10)
+    assert ei.value.status == capi.BGR_ERR_UNSUPPORTED
+    eng.close()
+
+
+def test_trace_records_one_interval_per_fused_launch():
+    eng, orc, cols = _pair(50_000, seed=5, ttl=(500, 500))
+    tick = lambda f: [Request(SAVE, f), Request(ADVANCE, f, [0, 0])]
+    eng.handle_requests(NOSESS, tick(0))
+    eng.trace_enable(16)
+    for f in range(1, 6):
+        eng.handle_requests(NOSESS, tick(f))
+    tr = eng.trace_read(16)
+    assert tr.shape == (5, 2)
+    assert np.all(tr[:, 1] > tr[:, 0]) and np.all(np.diff(tr[:, 0].astype(np.int64)) > 0)
+    assert np.all((tr[:, 1] - tr[:, 0]) < 5_000_000)             # a 50k-entity tick is microseconds, not milliseconds
+    eng.trace_enable(0)
+    eng.close()
