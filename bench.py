@@ -220,11 +220,13 @@ def trace_stats(tr):
     if tr.shape[0] < 3:
         return None
     s, e = tr[:, 0].astype(np.int64), tr[:, 1].astype(np.int64)
+    pub = (tr[:, 2].astype(np.int64) - e) / 1e3   # last block done -> results + completion word written
     dur = (e - s) / 1e3
     period = np.diff(s) / 1e3
     overlap = (e[:-1] - s[1:]) / 1e3          # > 0: the next launch's first block started before this launch's last block ended
     return {"launches": int(tr.shape[0]), "kernel_us_median": float(np.median(dur)), "period_us_median": float(np.median(period)),
-            "overlap_us_median": float(np.median(overlap)), "overlapping_launches": int((overlap > 0).sum())}
+            "overlap_us_median": float(np.median(overlap)), "overlapping_launches": int((overlap > 0).sum()),
+            "publish_us_median": float(np.median(pub))}
 
 
 def run_ours(args):
@@ -379,11 +381,11 @@ def run_ours(args):
                             "overlap > 0 = the next tick's first wave ran inside this tick's tail (tile dependencies)"}
         if args.trace_out and rank == 0:
             with open(args.trace_out, "w") as f:
-                f.write("mode,launch,first_block_start_ns,last_block_end_ns\n")
+                f.write("mode,launch,first_block_start_ns,last_block_end_ns,published_ns\n")
                 for mode, tr in (("pipelined", tr_p), ("synchronous", tr_s)):
                     base = int(tr[0, 0]) if tr.shape[0] else 0
                     for i in range(tr.shape[0]):
-                        f.write(f"{mode},{i},{int(tr[i, 0]) - base},{int(tr[i, 1]) - base}\n")
+                        f.write(f"{mode},{i},{int(tr[i, 0]) - base},{int(tr[i, 1]) - base},{int(tr[i, 2]) - base}\n")
     except Exception as exc:  # an optional leg must not cost the headline line
         timeline = {"error": repr(exc)}
 

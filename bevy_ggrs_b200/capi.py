@@ -122,6 +122,8 @@ PROTOTYPES = {
     "bgr_fold_partials_n": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p]),
     "bgr_seahash": (C.c_uint64, [C.c_void_p, C.c_uint64]),
     "bgr_ggrs_time_delta_bits": (C.c_uint32, [C.c_uint32, C.c_int32]),
+    "bgr_particle_rng_stream": (C.c_int, [C.c_uint64, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_float, C.c_float]),
+    "bgr_splitmix64_stream": (C.c_int, [C.c_uint64, C.c_uint32, C.c_void_p]),
     "bgr_launch_count": (C.c_int, [C.c_void_p, u64p]),
     "bgr_slot_bytes": (C.c_int, [C.c_void_p, u64p]),
     "bgr_last_path": (C.c_int, [C.c_void_p, u32p]),
@@ -129,6 +131,7 @@ PROTOTYPES = {
     "bgr_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bgr_trace_enable": (C.c_int, [C.c_void_p, C.c_uint32]),
     "bgr_trace_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, u32p]),
+    "bgr_host_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32]),
     "bgr_reset_session": (C.c_int, [C.c_void_p]),
     "bgr_shard_group_join": (C.c_int, [C.c_void_p, C.c_char_p, C.c_uint32, C.c_uint32, C.c_uint32]),
     "bgr_shard_group_leave": (C.c_int, [C.c_void_p]),

@@ -20,6 +20,7 @@
 
 #include "../../include/bevy_ggrs_b200.h"
 #include "kernels.cuh"
+#include "particle_rng.hpp"
 #include "ring.hpp"
 #include "seahash.cuh"
 #include "shard_group.hpp"
@@ -53,44 +54,6 @@ struct SystemReg {
 };
 
 constexpr uint32_t kReqAdvanceNoBump = 100;  // bgr_advance_world: caller already bumped RollbackFrameCount
-
-// ParticleRng = rand_xoshiro::Xoshiro256PlusPlus (particles.rs:125-128), kept host-side and rolled back with
-// every snapshot like the reference's rollback_resource_with_clone::<ParticleRng>() (:200).  Third-party
-// arithmetic restated from the published algorithms (rand_xoshiro 0.7 / rand 0.9): SplitMix64 seeding,
-// xoshiro256++ step, next_u32 = upper half, f32 range sample = ((u32 >> 9 | 0x3f800000) as f32 - 1) * scale + low.
-struct ParticleRng {
-    uint64_t s[4] = {0, 0, 0, 0};
-    static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
-    void seed_from_u64(uint64_t seed) {
-        uint64_t x = seed;
-        for (int i = 0; i < 4; ++i) {
-            x += 0x9E3779B97F4A7C15ULL;
-            uint64_t z = x;
-            z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-            z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-            s[i] = z ^ (z >> 31);
-        }
-    }
-    uint32_t next_u32() {
-        uint64_t result = rotl(s[0] + s[3], 23) + s[0];
-        uint64_t t = s[1] << 17;
-        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3];
-        s[2] ^= t;
-        s[3] = rotl(s[3], 45);
-        return uint32_t(result >> 32);
-    }
-    float random_range(float low, float high) {  // rng.random_range(low..high)
-        const float scale = high - low;
-        for (;;) {
-            uint32_t bits = (next_u32() >> 9) | 0x3f800000u;
-            float v12; std::memcpy(&v12, &bits, 4);
-            volatile float v01 = v12 - 1.0f;
-            volatile float prod = v01 * scale;   // mul and add rounded separately (no contraction)
-            float res = prod + low;
-            if (res < high) return res;
-        }
-    }
-};
 
 constexpr uint32_t kMaxSpawnVals = 1u << 16;  // particles spawned by one request vector
 
@@ -131,6 +94,12 @@ float duration_as_secs_f32(uint64_t ns) {  // core::time::Duration::as_secs_f32
     return float(secs) + float(nanos) / 1000000000.0f;
 }
 uint32_t f32_bits(float f) { uint32_t b; std::memcpy(&b, &f, 4); return b; }
+
+uint64_t host_ns() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return uint64_t(ts.tv_sec) * 1000000000ULL + uint64_t(ts.tv_nsec);
+}
 
 int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
@@ -202,6 +171,7 @@ struct bgr_engine {
     unsigned long long trace_first_seq = 0;
 
     uint64_t launches = 0;
+    uint64_t prof[8] = {};          // host-side time of the hot loop: [0] calls, [1] compile ns, [2] launch ns, [3] wait ns, [4] fold ns
     bool last_fused = false;
     unsigned long long seq = 0;   // sequence number of the last submit (completion flag value)
     int tune_poll = 1;            // collect() spins on the host-mapped flag before falling back to the event
@@ -504,7 +474,7 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
         pp.ticket = e->d_ticket_c[set];
         pp.out = e->d_out[buf] + size_t(c) * kResultStride;
         pp.trace = nullptr;
-        if (e->d_trace && c == 0 && e->seq - e->trace_first_seq < e->trace_cap) pp.trace = e->d_trace + (e->seq - e->trace_first_seq) * 2;
+        if (e->d_trace && c == 0 && e->seq - e->trace_first_seq < e->trace_cap) pp.trace = e->d_trace + (e->seq - e->trace_first_seq) * 4;
         cudaStream_t stream = chains > 1 ? e->chain_stream[c] : e->stream;
         int rc = launch_fused_variant(e, pp, stream);
         if (rc != BGR_OK) return rc;
@@ -704,10 +674,12 @@ int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs,
     if (!e->built) return fail(BGR_ERR_STATE, "bgr_build has not been called");
     if (e->pending.size() >= size_t(bgr_engine::kBufs)) return fail(BGR_ERR_STATE, "too many un-collected submits");
     if (n && !reqs) return fail(BGR_ERR_INVALID_ARGUMENT, "null requests");
+    const uint64_t t_begin = host_ns();
     HostState s = e->st;
     Program pg;
     int rc = compile_requests(e, s, sess, reqs, n, pg);
     if (rc != BGR_OK) return rc;  // nothing executed, nothing committed
+    const uint64_t t_compiled = host_ns();
     uint32_t buf = e->next_buf;
     if (e->group) {
         // the buffer of this request vector was last used kBufs vectors ago: every peer must have folded that one
@@ -734,6 +706,7 @@ int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs,
     std::memcpy(pd.totals, pg.save_totals, sizeof(uint32_t) * pg.n_saves);
     e->pending.push_back(pd);
     e->next_buf = (buf + 1) % bgr_engine::kBufs;
+    e->prof[0] += 1; e->prof[1] += t_compiled - t_begin; e->prof[2] += host_ns() - t_compiled;
     return BGR_OK;
 }
 
@@ -754,6 +727,7 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
     if (e->pending.empty()) return fail(BGR_ERR_STATE, "nothing to collect");
     Pending pd = e->pending.front();
     e->pending.pop_front();
+    const uint64_t t_wait0 = host_ns();
     for (uint32_t c = 0; c < pd.chains && !pd.finished; ++c) {
         // completion: each kernel's last block writes its sequence number after the results (system fence)
         const volatile unsigned long long* flag = &e->h_out[pd.buf][size_t(c) * kResultStride + kSeqIndex];
@@ -770,6 +744,8 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
             break;
         }
     }
+    const uint64_t t_wait1 = host_ns();
+    e->prof[3] += t_wait1 - t_wait0;
     // fold the chains' result blocks: XOR the column words, sum the live-row counts, OR the flags
     unsigned long long folded[kMaxSaves * kAccStride];
     for (uint32_t i = 0; i < pd.n_saves * kAccStride; ++i) {
@@ -815,6 +791,7 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
             fold(e->last_partials[k], &out[k]);
         }
     }
+    e->prof[4] += host_ns() - t_wait1;
     if (nonfinite) return fail(BGR_ERR_NON_FINITE, "Hashing is not stable for NaN f32 values.");
     return BGR_OK;
 }
@@ -1547,6 +1524,26 @@ BGR_API uint64_t bgr_seahash(const void* bytes, uint64_t len) {
     return sea_diffuse(a ^ b ^ c ^ d ^ len);
 }
 
+// the engine's ParticleRng arithmetic on its own (host only): known-answer tests of SplitMix64 / xoshiro256++ / the
+// f32 range sampling run against exactly the code that spawn_particles uses
+BGR_API int bgr_particle_rng_stream(uint64_t seed, const uint64_t* state4_or_null, uint32_t n, uint64_t* next_u64_out,
+                                    float* range_out, float low, float high) {
+    ParticleRng a, b;
+    if (state4_or_null) { for (int i = 0; i < 4; ++i) a.s[i] = b.s[i] = state4_or_null[i]; }
+    else { a.seed_from_u64(seed); b.seed_from_u64(seed); }
+    for (uint32_t i = 0; i < n; ++i) {
+        if (next_u64_out) next_u64_out[i] = a.next_u64();
+        if (range_out) range_out[i] = b.random_range(low, high);
+    }
+    return BGR_OK;
+}
+BGR_API int bgr_splitmix64_stream(uint64_t seed, uint32_t n, uint64_t* out) {
+    if (!out && n) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    SplitMix64 sm{seed};
+    for (uint32_t i = 0; i < n; ++i) out[i] = sm.next_u64();
+    return BGR_OK;
+}
+
 BGR_API uint32_t bgr_ggrs_time_delta_bits(uint32_t fps, int32_t frame) {
     if (fps == 0) return 0;
     uint64_t f = uint64_t(int64_t(frame));
@@ -1671,6 +1668,12 @@ BGR_API int bgr_reset_session(bgr_engine* e) {
     return BGR_OK;
 }
 
+BGR_API int bgr_host_profile(bgr_engine* e, uint64_t* out, uint32_t cap) {
+    if (!e || !out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    for (uint32_t i = 0; i < cap && i < 8; ++i) out[i] = e->prof[i];
+    return BGR_OK;
+}
+
 BGR_API int bgr_stream(bgr_engine* e, void** stream_out) {
     if (!e || !stream_out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
     *stream_out = e->stream;
@@ -1686,8 +1689,8 @@ BGR_API int bgr_trace_enable(bgr_engine* e, uint32_t capacity) {
     if (rc != BGR_OK) return rc;
     if (e->d_trace) { CUDA_TRY(cudaFree(e->d_trace)); e->d_trace = nullptr; e->trace_cap = 0; }
     if (capacity == 0) return BGR_OK;
-    std::vector<unsigned long long> init(size_t(capacity) * 2);
-    for (uint32_t i = 0; i < capacity; ++i) { init[2 * i] = ~0ULL; init[2 * i + 1] = 0ULL; }
+    std::vector<unsigned long long> init(size_t(capacity) * 4, 0ULL);
+    for (uint32_t i = 0; i < capacity; ++i) init[4 * i] = ~0ULL;
     CUDA_TRY(cudaMalloc(&e->d_trace, init.size() * sizeof(unsigned long long)));
     CUDA_TRY(cudaMemcpy(e->d_trace, init.data(), init.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
     e->trace_cap = capacity;
@@ -1701,7 +1704,7 @@ BGR_API int bgr_trace_read(bgr_engine* e, uint64_t* start_end_ns_out, uint32_t c
     CUDA_TRY(cudaStreamSynchronize(e->stream));
     const uint64_t done = e->seq + 1 > e->trace_first_seq ? e->seq + 1 - e->trace_first_seq : 0;
     const uint32_t n = uint32_t(std::min<uint64_t>(std::min<uint64_t>(done, e->trace_cap), cap));
-    if (n && start_end_ns_out) CUDA_TRY(cudaMemcpy(start_end_ns_out, e->d_trace, size_t(n) * 2 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (n && start_end_ns_out) CUDA_TRY(cudaMemcpy(start_end_ns_out, e->d_trace, size_t(n) * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (n_out) *n_out = n;
     return BGR_OK;
 }

@@ -102,7 +102,7 @@ struct ProgramParams {
     unsigned int* ticket;       // [0] block-completion ticket, [1] dynamic tile counter
     const float2* spawn_vals;   // (vx, vy) of every particle spawned by this program (host-mapped), particles.rs:265
     unsigned long long seq;     // written to out[kSeqIndex] after the results (completion flag the host polls)
-    unsigned long long* trace;  // nullptr, or this launch's row of the launch trace: [0] min block start, [1] max block end (globaltimer ns)
+    unsigned long long* trace;  // nullptr, or this launch's row of the launch trace: [0] min block start, [1] max block end, [2] results published (globaltimer ns)
     uint32_t words, tile_bytes, n_ops, n_saves;
     uint32_t tile_begin, n_tiles;  // this launch covers tiles [tile_begin, n_tiles) (one chain of the entity range)
     unsigned int* tile_done;       // [tiles] sequence number of the last PF_TILE_SIGNAL launch that finished the tile
@@ -591,6 +591,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
             p.ticket[0] = 0u;
             p.ticket[1] = 0u;
             *reinterpret_cast<volatile unsigned long long*>(&p.out[kSeqIndex]) = p.seq;  // host polls this word
+            if (p.trace) p.trace[2] = globaltimer_ns();
         }
     }
 }

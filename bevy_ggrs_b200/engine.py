@@ -259,11 +259,17 @@ class Engine:
         self._check(self._lib.bgr_trace_enable(self._h, capacity))
 
     def trace_read(self, capacity: int) -> np.ndarray:
-        """(n, 2) uint64: [first block start, last block end] of each traced fused launch, GPU globaltimer ns."""
-        out = np.zeros((capacity, 2), dtype=np.uint64)
+        """(n, 4) uint64 per traced fused launch, GPU globaltimer ns: first block start, last block end, results
+        published, reserved."""
+        out = np.zeros((capacity, 4), dtype=np.uint64)
         n = C.c_uint32()
         self._check(self._lib.bgr_trace_read(self._h, out.ctypes.data, capacity, C.byref(n)))
         return out[: n.value]
+
+    def host_profile(self) -> dict:
+        out = (C.c_uint64 * 8)()
+        self._check(self._lib.bgr_host_profile(self._h, out, 8))
+        return {"calls": out[0], "compile_ns": out[1], "launch_ns": out[2], "wait_ns": out[3], "fold_ns": out[4]}
 
     # ---- shard group (multi-GPU): cross-shard checksum fold inside the engine ----
     def shard_group_join(self, name: str, rank: int, world_size: int, timeout_ms: int = 0) -> None:

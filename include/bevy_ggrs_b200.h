@@ -306,6 +306,15 @@ BGR_API int bgr_group_collect(bgr_group* g, uint64_t group_seq, bgr_checksum* ou
  * per Save and XORs it into the engine's checksum (ChecksumPlugin::update, checksum.rs:88-99). */
 BGR_API uint64_t bgr_seahash(const void* bytes, uint64_t len);
 
+/* ---- ParticleRng arithmetic on its own (host only; examples/stress_tests/particles.rs:125-128, 258-270) -------
+ * The Xoshiro256PlusPlus stream spawn_particles draws from: `state4_or_null` = Xoshiro256PlusPlus::from_seed state
+ * words, or NULL for seed_from_u64(seed).  next_u64_out[i] = the i-th next_u64(); range_out[i] = the i-th
+ * random_range(low..high) of an identical, separate generator.  bgr_splitmix64_stream = rand_xoshiro's SplitMix64.
+ * Exposed so that published known-answer vectors run against the product's own code. */
+BGR_API int bgr_particle_rng_stream(uint64_t seed, const uint64_t* state4_or_null, uint32_t n, uint64_t* next_u64_out,
+                                    float* range_out, float low, float high);
+BGR_API int bgr_splitmix64_stream(uint64_t seed, uint32_t n, uint64_t* out);
+
 /* ---- GgrsTime (src/time.rs:63-76): delta_secs of the step that ends at `frame` ---------- */
 BGR_API uint32_t bgr_ggrs_time_delta_bits(uint32_t fps, int32_t frame);
 
@@ -315,10 +324,14 @@ BGR_API int bgr_slot_bytes(bgr_engine* e, uint64_t* bytes_out);  /* algorithmic 
 BGR_API int bgr_last_path(bgr_engine* e, uint32_t* fused_out);   /* 1 if the last handle_requests used the fused program kernel */
 BGR_API int bgr_synchronize(bgr_engine* e);
 BGR_API int bgr_stream(bgr_engine* e, void** stream_out);        /* the cudaStream_t the engine launches on (timing events) */
-/* device-side launch trace: [first block start, last block end] (GPU globaltimer ns) of every fused launch after the
- * call, up to `capacity` launches; bgr_trace_read copies pairs out (waits for the GPU).  capacity 0 disables. */
+/* device-side launch trace: 4 x u64 per fused launch after the call, up to `capacity` launches (GPU globaltimer ns):
+ * [0] first block started, [1] last block finished its tiles, [2] results + completion word written, [3] reserved.
+ * bgr_trace_read copies the rows out (waits for the GPU).  capacity 0 disables. */
 BGR_API int bgr_trace_enable(bgr_engine* e, uint32_t capacity);
-BGR_API int bgr_trace_read(bgr_engine* e, uint64_t* start_end_ns_out, uint32_t cap_launches, uint32_t* n_out);
+BGR_API int bgr_trace_read(bgr_engine* e, uint64_t* rows_out, uint32_t cap_launches, uint32_t* n_out);
+/* cumulative host-side time of the hot loop: out[0] request vectors, [1] ns compiling requests, [2] ns enqueueing the
+ * launch, [3] ns waiting for the completion word, [4] ns folding results (cap <= 8) */
+BGR_API int bgr_host_profile(bgr_engine* e, uint64_t* out, uint32_t cap);
 
 /* ---- host-side ring bookkeeping on its own ------------------------------------------------------
  * The frame -> HBM-slot queue the engine keeps for GgrsSnapshots (mod.rs:94-271), exposed without

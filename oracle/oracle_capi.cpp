@@ -121,6 +121,16 @@ ORC_API void orc_xoshiro_stream(uint64_t seed, uint32_t n, uint64_t* u64_out, fl
     a.seed_from_u64(seed); b.seed_from_u64(seed);
     for (uint32_t i = 0; i < n; ++i) { u64_out[i] = a.next_u64(); f32_out[i] = b.random_range_f32(low, high); }
 }
+ORC_API void orc_xoshiro_from_state(const uint64_t* state4, uint32_t n, uint64_t* u64_out) {
+    Xoshiro256pp a;
+    for (int i = 0; i < 4; ++i) a.s[i] = state4[i];
+    for (uint32_t i = 0; i < n; ++i) u64_out[i] = a.next_u64();
+}
+ORC_API void orc_xoshiro_seed_state(uint64_t seed, uint64_t* state4_out) {
+    Xoshiro256pp a;
+    a.seed_from_u64(seed);
+    for (int i = 0; i < 4; ++i) state4_out[i] = a.s[i];
+}
 ORC_API int orc_spawn(World* w, uint32_t count, uint32_t* first_out) { return guarded([&] { *first_out = w->spawn(count); }); }
 ORC_API uint32_t orc_row_count(World* w) { return uint32_t(w->rollback_ordered.len()); }
 ORC_API uint64_t orc_active_count(World* w) { return w->rows(); }

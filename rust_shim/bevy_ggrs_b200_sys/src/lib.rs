@@ -137,13 +137,16 @@ extern "C" {
     pub fn bgr_fold_partials_n(combined: *const bgr_partial, n: u32, out: *mut bgr_checksum) -> c_int;
     pub fn bgr_seahash(bytes: *const c_void, len: u64) -> u64;
     pub fn bgr_ggrs_time_delta_bits(fps: u32, frame: i32) -> u32;
+    pub fn bgr_particle_rng_stream(seed: u64, state4_or_null: *const u64, n: u32, next_u64_out: *mut u64, range_out: *mut f32, low: f32, high: f32) -> c_int;
+    pub fn bgr_splitmix64_stream(seed: u64, n: u32, out: *mut u64) -> c_int;
     pub fn bgr_launch_count(e: *mut bgr_engine, kernels_launched_out: *mut u64) -> c_int;
     pub fn bgr_slot_bytes(e: *mut bgr_engine, bytes_out: *mut u64) -> c_int;
     pub fn bgr_last_path(e: *mut bgr_engine, fused_out: *mut u32) -> c_int;
     pub fn bgr_synchronize(e: *mut bgr_engine) -> c_int;
     pub fn bgr_stream(e: *mut bgr_engine, stream_out: *mut *mut c_void) -> c_int;
     pub fn bgr_trace_enable(e: *mut bgr_engine, capacity: u32) -> c_int;
-    pub fn bgr_trace_read(e: *mut bgr_engine, start_end_ns_out: *mut u64, cap_launches: u32, n_out: *mut u32) -> c_int;
+    pub fn bgr_trace_read(e: *mut bgr_engine, rows_out: *mut u64, cap_launches: u32, n_out: *mut u32) -> c_int;
+    pub fn bgr_host_profile(e: *mut bgr_engine, out: *mut u64, cap: u32) -> c_int;
     pub fn bgr_reset_session(e: *mut bgr_engine) -> c_int;
     pub fn bgr_shard_group_join(e: *mut bgr_engine, name: *const c_char, rank: u32, world_size: u32, timeout_ms: u32) -> c_int;
     pub fn bgr_shard_group_leave(e: *mut bgr_engine) -> c_int;

@@ -31,7 +31,10 @@ def one(workload, env, K=300):
     eng.trace_enable(K + 8)
     b = bench.CallerBatch(ticks[fill + 5: fill + 5 + K])
     torch.cuda.synchronize()
+    hp0 = eng.host_profile()
     s = b.run(caller, eng)
+    hp1 = eng.host_profile()
+    host = {k: (hp1[k] - hp0[k]) / K / 1e3 for k in ("compile_ns", "launch_ns", "wait_ns", "fold_ns")}
     tr = eng.trace_read(K + 8)
     eng.trace_enable(0)
     # pipelined
@@ -52,7 +55,7 @@ def one(workload, env, K=300):
     res = {"workload": workload, "env": env, "sync_us_per_tick": s / K * 1e6, "sync_p50_us": float(np.median(b.per_tick) * 1e6),
            "sync_p10_us": float(np.percentile(b.per_tick, 10) * 1e6),
            "kernel": bench.trace_stats(tr), "pipelined_us_per_tick": e0.elapsed_time(e1) * 1e3 / len(pt),
-           "fused": eng.last_path_fused()}
+           "fused": eng.last_path_fused(), "host_us": host}
     eng.close()
     return res
 

@@ -69,6 +69,8 @@ def load_oracle() -> C.CDLL:
         "orc_spawn": (C.c_int, [vp, u32, u32p]),
         "orc_run_startup_system": (C.c_int, [vp, u32]),
         "orc_xoshiro_stream": (None, [u64, u32, u64p, C.POINTER(C.c_float), C.c_float, C.c_float]),
+        "orc_xoshiro_from_state": (None, [u64p, u32, u64p]),
+        "orc_xoshiro_seed_state": (None, [u64, u64p]),
         "orc_row_count": (u32, [vp]),
         "orc_active_count": (u64, [vp]),
         "orc_write_component": (C.c_int, [vp, u32, u32, u32, vp, u32]),

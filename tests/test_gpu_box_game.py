@@ -80,7 +80,7 @@ def test_box_game_eight_players_every_handle_reaches_move_cube_system():
     """`inputs[p.handle]` for EVERY handle (box_game.rs:171): BGR_MAX_PLAYERS = 8 inputs cross the ABI and all of them
     steer their cube (round 1 silently gave handles 4..7 input 0)."""
     from bevy_ggrs_b200.session import ADVANCE, SAVE, Request
-    eng, orc = Engine(max_entities=8, max_depth=4), OracleWorld()
+    eng, orc = Engine(max_entities=8, max_depth=16), OracleWorld()   # no session: nothing prunes the 12 snapshots
     cols = []
     for w in (eng, orc):
         vel = w.rollback_component("Velocity", 12)

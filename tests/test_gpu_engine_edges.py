@@ -271,7 +271,7 @@ def test_trace_records_one_interval_per_fused_launch():
     for f in range(1, 6):
         eng.handle_requests(NOSESS, tick(f))
     tr = eng.trace_read(16)
-    assert tr.shape == (5, 2)
+    assert tr.shape == (5, 4) and np.all(tr[:, 2] >= tr[:, 1])
     assert np.all(tr[:, 1] > tr[:, 0]) and np.all(np.diff(tr[:, 0].astype(np.int64)) > 0)
     assert np.all((tr[:, 1] - tr[:, 0]) < 5_000_000)             # a 50k-entity tick is microseconds, not milliseconds
     eng.trace_enable(0)
