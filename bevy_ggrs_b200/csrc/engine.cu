@@ -192,10 +192,12 @@ struct bgr_engine {
     std::vector<PassiveRun> runs;
     uint32_t passive_bytes = 0;
     bool bundle_static_ck = false;  // both columns checksummed with the finite assertion: fully specialised kernel
+    bool bundle_opt = false;        // a registered column is BGR_STRATEGY_OPTIONAL: the presence-aware kernel variant (MODE 2)
     int tune_vec = 2, tune_minb = 2, tune_bps = 0, tune_passive_tma = 1;
     int tune_tma = 1;          // stepwise Save/Load through the TMA-staged bulk-copy kernel
-    uint32_t tma_stage_tiles = 0;  // tiles per TMA stage (0: schema too wide for 3 stages of shared memory)
-    int occ_cache[3][2][3] = {};
+    uint32_t tma_stage_tiles = 0;  // one-tile stages of the TMA copy kernel (0: schema too wide for two stages of shared memory)
+    unsigned int* d_tma_ticket = nullptr;
+    int occ_cache[3][3][3] = {};
 
     uint8_t* image(uint32_t idx) const { return arena + size_t(idx) * image_bytes; }
     uint32_t image_off256(uint32_t idx) const { return uint32_t((size_t(idx) * image_bytes) >> 8); }
@@ -360,9 +362,9 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
 // ---------------------------------------------------------------------------------------------
 // launch: fused bundle kernel
 // ---------------------------------------------------------------------------------------------
-template <int VEC, bool STATIC_CK, int MINB>
+template <int VEC, int MODE, int MINB>
 int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int mi, cudaStream_t stream) {
-    auto kern = k_particles_program<VEC, STATIC_CK, MINB>;
+    auto kern = k_particles_program<VEC, MODE, MINB>;
     constexpr int BLOCK = kTileRows / VEC;
     const size_t smem = (pp.flags & PF_PASSIVE_TMA) ? size_t(2) * pp.passive_bytes : 0;
     if (e->occ_cache[vi][si][mi] == 0) {
@@ -420,6 +422,7 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
     if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_V; pp.ck_v_slot = uint32_t(cv.ck_slot); }
     pp.t_off = ct.first_plane * kPlaneBytes; pp.v_off = cv.first_plane * kPlaneBytes;
     pp.l_off = e->cols[e->bl].first_plane * kPlaneBytes; pp.alive_off = e->words * kPlaneBytes;
+    pp.need_t = ct.absent; pp.need_v = cv.absent; pp.need_tv = ct.absent | cv.absent; pp.need_l = e->cols[e->bl].absent;
     pp.n_runs = passive_needed ? uint32_t(e->runs.size()) : 0u; pp.passive_bytes = e->passive_bytes;
     for (size_t i = 0; i < e->runs.size(); ++i) pp.runs[i] = e->runs[i];
     pp.n_passive = passive_needed ? uint32_t(e->passive.size()) : 0u;
@@ -489,19 +492,23 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
 }
 
 int launch_fused_variant(bgr_engine* e, const ProgramParams& pp, cudaStream_t stream) {
-    const int v = e->tune_vec;
-    const bool st = e->bundle_static_ck;
+    const int v = e->bundle_opt ? 2 : e->tune_vec;
+    const bool st = e->bundle_static_ck && !e->bundle_opt;
     const int mb = e->tune_minb >= 8 ? 2 : (e->tune_minb >= 2 ? 1 : 0);  // launch-bounds tier: 1024 / 768 / unconstrained threads per SM
+    if (e->bundle_opt) {  // per-entity presence: one variant (2 rows per thread, 768 threads per SM)
+        constexpr int kMidOpt = 768 / int(kTileRows / 2);
+        return launch_particles<2, 2, kMidOpt>(e, pp, 1, 2, 1, stream);
+    }
 #define BGR_LAUNCH(VEC, VI)                                                                                \
     if (v == VEC) {                                                                                        \
         constexpr int kHi = (1024 / int(kTileRows / VEC)) > 32 ? 32 : (1024 / int(kTileRows / VEC));        \
         constexpr int kMid = (768 / int(kTileRows / VEC)) < 1 ? 1 : (768 / int(kTileRows / VEC));           \
-        if (st && mb == 2) return launch_particles<VEC, true, kHi>(e, pp, VI, 1, 2, stream);                       \
-        if (st && mb == 1) return launch_particles<VEC, true, kMid>(e, pp, VI, 1, 1, stream);                      \
-        if (st) return launch_particles<VEC, true, 1>(e, pp, VI, 1, 0, stream);                                    \
-        if (mb == 2) return launch_particles<VEC, false, kHi>(e, pp, VI, 0, 2, stream);                            \
-        if (mb == 1) return launch_particles<VEC, false, kMid>(e, pp, VI, 0, 1, stream);                           \
-        return launch_particles<VEC, false, 1>(e, pp, VI, 0, 0, stream);                                           \
+        if (st && mb == 2) return launch_particles<VEC, 1, kHi>(e, pp, VI, 1, 2, stream);                          \
+        if (st && mb == 1) return launch_particles<VEC, 1, kMid>(e, pp, VI, 1, 1, stream);                         \
+        if (st) return launch_particles<VEC, 1, 1>(e, pp, VI, 1, 0, stream);                                       \
+        if (mb == 2) return launch_particles<VEC, 0, kHi>(e, pp, VI, 0, 2, stream);                                \
+        if (mb == 1) return launch_particles<VEC, 0, kMid>(e, pp, VI, 0, 1, stream);                               \
+        return launch_particles<VEC, 0, 1>(e, pp, VI, 0, 0, stream);                                               \
     }
     BGR_LAUNCH(1, 0)
     BGR_LAUNCH(4, 2)
@@ -520,7 +527,8 @@ int launch_tma(bgr_engine* e, const uint8_t* src, uint8_t* dst, uint32_t n_rows_
     tp.src = src; tp.dst = dst;
     tp.order_base = e->cfg.order_base;
     tp.accum = save ? acc : nullptr;
-    tp.words = e->words; tp.tile_bytes = e->tile_bytes; tp.stage_tiles = e->tma_stage_tiles;
+    tp.words = e->words; tp.tile_bytes = e->tile_bytes; tp.stages = e->tma_stage_tiles;
+    tp.ticket = e->d_tma_ticket;
     tp.n_tiles = e->tiles_for(n_rows_copy);
     tp.n_rows_src = n_rows_src;
     tp.count_alive = save ? 1u : 0u;
@@ -533,9 +541,8 @@ int launch_tma(bgr_engine* e, const uint8_t* src, uint8_t* dst, uint32_t n_rows_
                 h.finite = c.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32; h.slot = uint32_t(c.ck_slot);
                 h.absent = c.absent;
             }
-    uint32_t n_chunks = (tp.n_tiles + tp.stage_tiles - 1) / tp.stage_tiles;
-    uint32_t grid = std::max(1u, std::min(n_chunks, uint32_t(e->num_sms)));
-    size_t smem = size_t(kTmaStages) * e->tma_stage_tiles * e->tile_bytes;
+    uint32_t grid = std::max(1u, std::min(tp.n_tiles, uint32_t(e->num_sms)));
+    size_t smem = size_t(tp.stages) * e->tile_bytes;
     k_image_tma<<<grid, kTmaBlock, smem, e->stream>>>(tp);
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
@@ -927,8 +934,9 @@ int download_wait(bgr_engine* e, uint32_t ticket) {
 void detect_bundles(bgr_engine* e) {
     e->bundle_particles = false;
     e->passive.clear();
+    e->bundle_opt = false;
     for (const Column& c : e->cols)
-        if (c.absent) return;  // per-entity presence is only implemented by the generic (stepwise) kernels
+        if (c.absent) e->bundle_opt = true;  // per-entity presence: the MODE 2 variant of the fused kernel
     const SystemReg* up = nullptr; const SystemReg* de = nullptr; const SystemReg* sp = nullptr;
     for (auto& s : e->systems) {
         if (s.id == BGR_SYS_PARTICLES_UPDATE && !up) up = &s;
@@ -1045,6 +1053,7 @@ BGR_API void bgr_engine_destroy(bgr_engine* e) {
     if (e->d_accum) cudaFree(e->d_accum);
     if (e->d_ticket) cudaFree(e->d_ticket);
     if (e->copy_stream) { cudaStreamSynchronize(e->copy_stream); cudaStreamDestroy(e->copy_stream); }
+    if (e->d_tma_ticket) cudaFree(e->d_tma_ticket);
     if (e->d_tile_done) cudaFree(e->d_tile_done);
     if (e->d_tile_cnt) cudaFree(e->d_tile_cnt);
     for (auto& d : e->dl) {
@@ -1219,13 +1228,15 @@ BGR_API int bgr_build(bgr_engine* e) {
             CUDA_TRY(cudaHostGetDevicePointer(&e->d_spawn[i], e->h_spawn[i], 0));
         }
     detect_bundles(e);
-    {   // TMA stage: kTmaStages x (stage_tiles tiles) must fit ~200 KB of shared memory, ~64 KB per stage
-        size_t per_stage = (200u * 1024u) / size_t(kTmaStages);
-        uint32_t st = uint32_t(std::min<size_t>(per_stage / e->tile_bytes, 8));
-        e->tma_stage_tiles = st;
-        if (st) {
-            size_t smem = size_t(kTmaStages) * st * e->tile_bytes;
+    {   // TMA copy kernel: up to six one-tile stages in ~200 KB of shared memory, at least two
+        uint32_t st = uint32_t(std::min<size_t>((200u * 1024u) / e->tile_bytes, size_t(kTmaMaxStages)));
+        if (env_int("BGR_TUNE_TMA_STAGES", 0) > 0) st = std::min(st, uint32_t(env_int("BGR_TUNE_TMA_STAGES", 0)));
+        e->tma_stage_tiles = st >= 2 ? st : 0;
+        if (e->tma_stage_tiles) {
+            size_t smem = size_t(e->tma_stage_tiles) * e->tile_bytes;
             CUDA_TRY(cudaFuncSetAttribute(k_image_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            CUDA_TRY(cudaMalloc(&e->d_tma_ticket, 4 * sizeof(unsigned int)));
+            CUDA_TRY(cudaMemsetAsync(e->d_tma_ticket, 0, 4 * sizeof(unsigned int), e->stream));
         }
     }
     CUDA_TRY(cudaStreamSynchronize(e->stream));

@@ -115,6 +115,9 @@ struct ProgramParams {
     uint32_t n_runs, passive_bytes;           // TMA path
     uint32_t n_passive;                       // per-thread fallback path
     uint32_t spawn_ttl_lo, spawn_ttl_hi;      // Ttl of a spawned particle (fps * 5, particles.rs:260)
+    // MODE 2 (per-entity presence, BGR_STRATEGY_OPTIONAL): absent bits (of the row's mask byte) that take a row out of
+    // update_particles' query (Transform | Velocity), despawn_particles' (Ttl) and the two checksum queries
+    uint32_t need_tv, need_l, need_t, need_v;
     PassiveRun runs[kMaxRuns];
     uint16_t passive[kMaxPassive];
     uint32_t passive_template[kMaxPassive];   // value of each passive word in a freshly spawned row (Transform::default())
@@ -157,6 +160,13 @@ template <int VEC> __device__ __forceinline__ uint32_t rows_mask(uint32_t row0, 
     uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < VEC; ++j) m |= (row0 + j < n_rows) ? (1u << (8 * j)) : 0u;
+    return m;
+}
+// ... byte j = 0xFF: keeps the absent bits of the row's mask byte (per-entity presence)
+template <int VEC> __device__ __forceinline__ uint32_t rows_mask_full(uint32_t row0, uint32_t n_rows) {
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) m |= (row0 + j < n_rows) ? (0xFFu << (8 * j)) : 0u;
     return m;
 }
 
@@ -243,9 +253,16 @@ __device__ __forceinline__ void particle_step(uint32_t& tx, uint32_t& ty, uint32
 // Dead rows are advanced and hashed like live ones and masked at the fold: their bytes are not
 // observable (a row only comes back to life through LOAD, which restores data and flag together).
 // =============================================================================================
-template <int VEC, bool STATIC_CK, int MINB>
+// MODE 0: checksum flags tested at run time; MODE 1: both columns checksummed with the finite assertion (the stress
+// test's registration) — the flag tests fold away; MODE 2: MODE 0 + per-entity component presence: the row's mask
+// byte carries absent bits (BGR_STRATEGY_OPTIONAL), every system and checksum applies the reference's query filter
+// (`Query<(&RollbackId, &T)>`, component_checksum.rs:73-77; `Query<(&mut Transform, &mut Velocity)>`, particles.rs:273)
+// per row, and Save / Load move the mask with the image (= the four-way match of component_snapshot.rs:99-115).
+template <int VEC, int MODE, int MINB>
 __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(const __grid_constant__ ProgramParams p) {
     constexpr int BLOCK = kTileRows / VEC;
+    constexpr bool STATIC_CK = MODE == 1;
+    constexpr bool OPT = MODE == 2;
     // STATIC_CK: both columns checksummed with the finite assertion (the stress test's registration) —
     // the flag tests fold away; otherwise they are warp-uniform runtime tests.
     const bool CKT = STATIC_CK ? true : (p.flags & PF_CK_T) != 0;
@@ -353,7 +370,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
             for (int k = 0; k < 3; ++k) vec_load<VEC>(pv + k * kPlaneBytes, vl[k]);
 #pragma unroll
             for (int k = 0; k < 2; ++k) vec_load<VEC>(pl + k * kPlaneBytes, tl[k]);
-            alive = alive_load<VEC>(img + aoff) & rows_mask<VEC>(row0, n_rows);
+            alive = alive_load<VEC>(img + aoff) & (OPT ? rows_mask_full<VEC>(row0, n_rows) : rows_mask<VEC>(row0, n_rows));
         };
         auto store_active = [&](uint8_t* img) {
             uint8_t* pt = img + p.t_off + woff;
@@ -419,6 +436,21 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                 const float dt = __uint_as_float(p.ops[i].dt_bits);
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
+                    if (OPT) {
+                        // the queries only match entities that have the components (and exist)
+                        const uint32_t m = (alive >> (8 * j)) & 0xFFu;
+                        uint32_t a0 = tr[0][j], a1 = tr[1][j], a2 = tr[2][j], b0 = vl[0][j], b1 = vl[1][j], b2 = vl[2][j];
+                        particle_step(a0, a1, a2, b0, b1, b2, dt);
+                        if (row_matches(m, p.need_tv)) { tr[0][j] = a0; tr[1][j] = a1; tr[2][j] = a2; vl[0][j] = b0; vl[1][j] = b1; vl[2][j] = b2; }
+                        if (row_matches(m, p.need_l)) {
+                            uint32_t lo = tl[0][j], hi = tl[1][j];
+                            hi -= (lo == 0u) ? 1u : 0u;
+                            lo -= 1u;
+                            tl[0][j] = lo; tl[1][j] = hi;
+                            alive &= ((lo | hi) == 0u) ? ~(0xFFu << (8 * j)) : 0xFFFFFFFFu;
+                        }
+                        continue;
+                    }
                     particle_step(tr[0][j], tr[1][j], tr[2][j], vl[0][j], vl[1][j], vl[2][j], dt);
                     // despawn_particles (particles.rs:282-289): ttl -= 1 (wrapping usize); despawn at 0
                     uint32_t lo = tl[0][j], hi = tl[1][j];
@@ -439,7 +471,7 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                             tr[0][j] = 0u; tr[1][j] = 0u; tr[2][j] = 0u;
                             vl[0][j] = __float_as_uint(v.x); vl[1][j] = __float_as_uint(v.y); vl[2][j] = 0u;
                             tl[0][j] = p.spawn_ttl_lo; tl[1][j] = p.spawn_ttl_hi;
-                            alive |= 1u << (8 * j);
+                            alive = (alive & ~(0xFFu << (8 * j))) | (1u << (8 * j));  // exists, every component present
                         }
                     }
                 }
@@ -461,18 +493,21 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                 const bool vz_zero = BGR_ZERO_TAIL && CKV && __all_sync(0xffffffffu, vz_any == 0u);
 #pragma unroll
                 for (int j = 0; j < VEC; ++j) {
-                    const uint64_t live = ((alive >> (8 * j)) & 1u) ? ~0ULL : 0ULL;
+                    const uint32_t m = (alive >> (8 * j)) & 0xFFu;
+                    const uint64_t live = (m & 1u) ? ~0ULL : 0ULL;
+                    const uint64_t live_t = OPT ? (row_matches(m, p.need_t) ? ~0ULL : 0ULL) : live;
+                    const uint64_t live_v = OPT ? (row_matches(m, p.need_v) ? ~0ULL : 0ULL) : live;
                     if (CKT) {
-                        if (FINT) bad |= (f32_bits_nonfinite(tr[0][j]) | f32_bits_nonfinite(tr[1][j]) | f32_bits_nonfinite(tr[2][j])) & uint32_t(live);
+                        if (FINT) bad |= (f32_bits_nonfinite(tr[0][j]) | f32_bits_nonfinite(tr[1][j]) | f32_bits_nonfinite(tr[2][j])) & uint32_t(live_t);
                         const uint64_t lane_t = tz_zero ? kSeaTailZero : sea_diffuse(kSeaB ^ uint64_t(tr[2][j]));
                         uint64_t c = sea_hash_12_lane(uint64_t(tr[0][j]) | (uint64_t(tr[1][j]) << 32), lane_t);
-                        hx_t ^= sea_hash_entity(t0[j], c) & live;
+                        hx_t ^= sea_hash_entity(t0[j], c) & live_t;
                     }
                     if (CKV) {
-                        if (FINV) bad |= (f32_bits_nonfinite(vl[0][j]) | f32_bits_nonfinite(vl[1][j]) | f32_bits_nonfinite(vl[2][j])) & uint32_t(live);
+                        if (FINV) bad |= (f32_bits_nonfinite(vl[0][j]) | f32_bits_nonfinite(vl[1][j]) | f32_bits_nonfinite(vl[2][j])) & uint32_t(live_v);
                         const uint64_t lane_v = vz_zero ? kSeaTailZero : sea_diffuse(kSeaB ^ uint64_t(vl[2][j]));
                         uint64_t c = sea_hash_12_lane(uint64_t(vl[0][j]) | (uint64_t(vl[1][j]) << 32), lane_v);
-                        hx_v ^= sea_hash_entity(t0[j], c) & live;
+                        hx_v ^= sea_hash_entity(t0[j], c) & live_v;
                     }
                 }
                 const uint32_t n_alive = __popc(alive & 0x01010101u);

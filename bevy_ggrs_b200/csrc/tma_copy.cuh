@@ -3,11 +3,17 @@
 //     HBM image A --cp.async.bulk(global->shared, mbarrier complete_tx)--> shared-memory stage
 //                 --cp.async.bulk(shared->global, bulk_group)-----------> HBM image B
 //
-// Images are tile-planar (kernels.cuh), so a group of tiles is ONE contiguous chunk: one elected
-// thread moves ~60 KB with a single bulk-copy instruction each way, a ring of stages keeps several
-// chunks in flight per SM, and no byte of the copy ever passes through a register.  For a Save all
-// threads hash the checksummed byte ranges straight out of the staged tiles (planar layout =>
-// conflict-free shared loads) while the TMA store streams them to the slot.
+// Images are tile-planar (kernels.cuh), so a tile is ONE contiguous chunk (31 KB for the stress schema): a dedicated
+// producer thread moves it with a single bulk-copy instruction each way, a ring of up to six stages keeps five loads
+// and a store in flight per SM, and no byte of the copy ever passes through a register.  For a Save sixteen consumer
+// warps hash the checksummed byte ranges straight out of the staged tile (planar layout => conflict-free shared
+// loads) while the TMA store streams it to the slot; producer and consumers are decoupled by full / hashed mbarriers
+// per stage, tiles are claimed from a global counter (no tail imbalance between SMs).
+//
+// Round-1 version and what the profile said (profiles/r01_k_image_tma.metrics.csv): one block of
+// 256 threads per SM did everything; thread 0 waited for the store of a stage (`wait_group.read 0`) right after issuing
+// it, and 8 warps per SM could not issue the Save's hash instructions fast enough (sm__warps_active 12.5 %): 35 us per
+// 1M-entity Save against 25 us for a Load.
 //
 // Reference semantics: ComponentSnapshotPlugin::save (component_snapshot.rs:66-84) + the checksum
 // systems of SaveWorld (component_checksum.rs:67-108, entity_checksum.rs:29-52) in ONE launch;
@@ -21,9 +27,11 @@
 
 namespace bgr {
 
-constexpr int kTmaStages = 3;
-constexpr int kTmaBlock = 256;
+constexpr int kTmaMaxStages = 6;
+constexpr int kTmaConsumers = kTileRows;          // one row of the staged tile per consumer thread
+constexpr int kTmaBlock = kTmaConsumers + 32;     // + the producer warp
 constexpr int kMaxHashCols = 6;
+constexpr uint32_t kTmaEnd = 0xffffffffu;
 
 struct HashSpec {
     uint32_t first_plane, off, len, finite, slot;
@@ -35,7 +43,8 @@ struct TmaCopyParams {
     uint8_t* dst;
     unsigned long long order_base;
     unsigned long long* accum;  // device row of this save (kAccStride u64) or nullptr
-    uint32_t words, tile_bytes, stage_tiles;
+    unsigned int* ticket;       // [0] finished blocks, [1] next tile to claim (re-armed by the last block)
+    uint32_t words, tile_bytes, stages;
     uint32_t n_tiles;           // tiles to move
     uint32_t n_rows_src;        // rows that exist in the source image (alive beyond is forced 0)
     uint32_t n_hash;            // 0 for Load
@@ -46,69 +55,92 @@ struct TmaCopyParams {
 
 __global__ void __launch_bounds__(kTmaBlock, 1) k_image_tma(const __grid_constant__ TmaCopyParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ __align__(8) uint64_t full[kTmaStages];
+    __shared__ __align__(8) uint64_t full[kTmaMaxStages], hashed[kTmaMaxStages];
+    __shared__ uint32_t s_tile[kTmaMaxStages];
+    __shared__ unsigned int s_acc[2 * kMaxHashCols + 2];
+    __shared__ unsigned int s_last;
 
-    const uint32_t G = p.stage_tiles;
-    const size_t stage_bytes = size_t(G) * p.tile_bytes;
-    const uint32_t n_chunks = (p.n_tiles + G - 1) / G;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t S = p.stages;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    // consumers have work when the launch hashes / counts, or when a Load shrinks the world (alive bytes of rows the
+    // snapshot never contained must come back dead before the tile is stored)
+    const bool consume = p.n_hash || p.count_alive || size_t(p.n_tiles) * kTileRows > p.n_rows_src;
 
     if (tid == 0) {
-        for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+        for (uint32_t s = 0; s < S; ++s) { mbar_init(&full[s], 1); mbar_init(&hashed[s], kTmaConsumers / 32); }
         fence_mbar_init();
     }
+    if (tid < 2 * kMaxHashCols + 2) s_acc[tid] = 0u;
     __syncthreads();
 
-    auto chunk_tiles = [&](uint32_t chunk) { return min(G, p.n_tiles - chunk * G); };
-    auto issue_load = [&](uint32_t chunk, uint32_t stage) {  // thread 0 only
-        const uint32_t bytes = chunk_tiles(chunk) * p.tile_bytes;
-        mbar_arrive_expect_tx(&full[stage], bytes);
-        tma_load_1d(smem + stage * stage_bytes, p.src + size_t(chunk) * stage_bytes, bytes, &full[stage]);
-    };
+    auto needs_fix = [&](uint32_t tile) { return size_t(tile + 1) * kTileRows > p.n_rows_src; };
 
-    const uint32_t my_chunks = (n_chunks > blockIdx.x) ? (n_chunks - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    if (tid == 0)
-        for (uint32_t k = 0; k < my_chunks && k < kTmaStages; ++k) issue_load(blockIdx.x + k * gridDim.x, k);
-
-    uint64_t hx[kMaxHashCols];
+    if (warp == kTmaConsumers / 32) {
+        // ------------------------------ producer: one thread drives every bulk copy ------------------------------
+        if (lane == 0) {
+            bool ended = false;
+            uint32_t loaded = 0;  // iterations whose load (or end marker) has been issued; iteration i uses stage i % S
+            auto issue = [&]() {
+                const uint32_t s = loaded % S;
+                const uint32_t tile = atomicAdd(&p.ticket[1], 1u);
+                if (tile >= p.n_tiles) {
+                    s_tile[s] = kTmaEnd;
+                    mbar_arrive(&full[s]);
+                    ended = true;
+                } else {
+                    s_tile[s] = tile;
+                    mbar_arrive_expect_tx(&full[s], p.tile_bytes);
+                    tma_load_1d(smem + size_t(s) * p.tile_bytes, p.src + size_t(tile) * p.tile_bytes, p.tile_bytes, &full[s]);
+                }
+                ++loaded;
+            };
+            while (loaded < S && !ended) issue();
+            for (uint32_t i = 0;; ++i) {
+                const uint32_t s = i % S, par = (i / S) & 1u;
+                mbar_wait(&full[s], par);
+                const uint32_t tile = s_tile[s];
+                if (tile == kTmaEnd) break;
+                if (p.store) {
+                    if (consume && needs_fix(tile)) mbar_wait(&hashed[s], par);  // alive bytes were patched in the stage
+                    tma_store_1d(p.dst + size_t(tile) * p.tile_bytes, smem + size_t(s) * p.tile_bytes, p.tile_bytes);
+                    tma_commit();
+                }
+                if (i >= 1 && !ended) {  // refill the stage of iteration i-1: its store has been read, its rows hashed
+                    const uint32_t sp = (i - 1) % S, parp = ((i - 1) / S) & 1u;
+                    if (p.store) tma_wait_read<1>();  // only the store issued just above may still be reading
+                    if (consume) mbar_wait(&hashed[sp], parp);
+                    issue();
+                }
+            }
+            tma_wait_all();  // every store has landed before the kernel (and its results) complete
+        }
+    } else if (consume) {
+        // ------------------------------ consumers: one row of the staged tile per thread ------------------------------
+        uint64_t hx[kMaxHashCols];
 #pragma unroll
-    for (int c = 0; c < kMaxHashCols; ++c) hx[c] = 0;
-    uint32_t n_alive = 0, bad = 0;
-
-    for (uint32_t k = 0; k < my_chunks; ++k) {
-        const uint32_t stage = k % kTmaStages, parity = (k / kTmaStages) & 1u;
-        const uint32_t chunk = blockIdx.x + k * gridDim.x;
-        const uint32_t tiles = chunk_tiles(chunk);
-        const uint32_t rows = tiles * kTileRows;
-        const uint32_t row_base = chunk * G * kTileRows;
-        uint8_t* st = smem + stage * stage_bytes;
-        mbar_wait(&full[stage], parity);
-
-        if (row_base + rows > p.n_rows_src) {
-            // a Load that shrinks the world: rows the snapshot never contained must come back dead
-            for (uint32_t r = tid; r < rows; r += kTmaBlock)
-                if (row_base + r >= p.n_rows_src) st[size_t(r / kTileRows) * p.tile_bytes + size_t(p.words) * kPlaneBytes + (r % kTileRows)] = 0;
-            fence_proxy_async();
-            __syncthreads();
-        }
-        if (tid == 0 && p.store) {
-            tma_store_1d(p.dst + size_t(chunk) * stage_bytes, st, tiles * p.tile_bytes);
-            tma_commit();
-        }
-        if (p.n_hash || p.count_alive) {
-            for (uint32_t r = tid; r < rows; r += kTmaBlock) {
-                const uint8_t* tile = st + size_t(r / kTileRows) * p.tile_bytes;
-                const uint32_t i = r % kTileRows;
-                const uint32_t m = tile[size_t(p.words) * kPlaneBytes + i];
-                if (!(m & 1u)) continue;
+        for (int c = 0; c < kMaxHashCols; ++c) hx[c] = 0;
+        uint32_t n_alive = 0, bad = 0;
+        for (uint32_t i = 0;; ++i) {
+            const uint32_t s = i % S, par = (i / S) & 1u;
+            mbar_wait(&full[s], par);
+            const uint32_t tile_idx = s_tile[s];
+            if (tile_idx == kTmaEnd) break;
+            uint8_t* tile = smem + size_t(s) * p.tile_bytes;
+            const uint32_t row = tile_idx * kTileRows + tid;
+            uint32_t m = tile[size_t(p.words) * kPlaneBytes + tid];
+            if (needs_fix(tile_idx)) {
+                if (row >= p.n_rows_src) { m = 0; tile[size_t(p.words) * kPlaneBytes + tid] = 0; }
+                fence_proxy_async();  // the patched bytes are visible to the bulk store that follows
+            }
+            if ((p.n_hash || p.count_alive) && (m & 1u)) {
                 ++n_alive;
-                const uint64_t t0 = sea_order_lane(p.order_base + row_base + r);
+                const uint64_t t0 = sea_order_lane(p.order_base + row);
 #pragma unroll
                 for (int c = 0; c < kMaxHashCols; ++c) {
                     if (c < p.n_hash) {
                         const HashSpec hs = p.hash[c];
                         if (m & hs.absent) continue;  // Query<(&RollbackId, &T)> does not match this entity
-                        const uint32_t* col = reinterpret_cast<const uint32_t*>(tile + size_t(hs.first_plane) * kPlaneBytes) + i;
+                        const uint32_t* col = reinterpret_cast<const uint32_t*>(tile + size_t(hs.first_plane) * kPlaneBytes) + tid;
                         uint64_t custom;
                         if (hs.off == 0 && hs.len == 12) {  // 3 x u32 `to_bits` fields (particles.rs:107-120, 207-222)
                             uint32_t a = col[0], b = col[kTileRows], d = col[2 * kTileRows];
@@ -127,31 +159,43 @@ __global__ void __launch_bounds__(kTmaBlock, 1) k_image_tma(const __grid_constan
                     }
                 }
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&hashed[s]);  // this warp is done with the stage
         }
-        __syncthreads();  // everyone is done reading this stage
-        if (tid == 0 && k + kTmaStages < my_chunks) {
-            tma_wait_read<0>();  // the bulk store has finished reading the stage
-            issue_load(blockIdx.x + (k + kTmaStages) * gridDim.x, stage);
-        }
-    }
-    if (tid == 0) tma_wait_all();  // all stores have landed before the kernel (and its results) complete
-
-    if (p.accum) {
-        const unsigned full_mask = 0xffffffffu;
+        if (p.accum) {
+            const unsigned full_mask = 0xffffffffu;
 #pragma unroll
-        for (int c = 0; c < kMaxHashCols; ++c) {
-            if (c < p.n_hash) {
-                uint32_t lo = __reduce_xor_sync(full_mask, uint32_t(hx[c])), hi = __reduce_xor_sync(full_mask, uint32_t(hx[c] >> 32));
-                if (lane == 0 && (lo | hi)) atomicXor(&p.accum[p.hash[c].slot], (unsigned long long)lo | ((unsigned long long)hi << 32));
+            for (int c = 0; c < kMaxHashCols; ++c) {
+                if (c < p.n_hash) {
+                    uint32_t lo = __reduce_xor_sync(full_mask, uint32_t(hx[c])), hi = __reduce_xor_sync(full_mask, uint32_t(hx[c] >> 32));
+                    if (lane == 0) { if (lo) atomicXor(&s_acc[2 * c], lo); if (hi) atomicXor(&s_acc[2 * c + 1], hi); }
+                }
+            }
+            uint32_t cnt = __reduce_add_sync(full_mask, n_alive);
+            uint32_t anybad = __reduce_or_sync(full_mask, bad);
+            if (lane == 0) {
+                if (cnt) atomicAdd(&s_acc[2 * kMaxHashCols], cnt);
+                if (anybad) atomicOr(&s_acc[2 * kMaxHashCols + 1], 1u);
             }
         }
-        uint32_t cnt = __reduce_add_sync(full_mask, n_alive);
-        uint32_t anybad = __reduce_or_sync(full_mask, bad);
-        if (lane == 0) {
-            if (p.count_alive && cnt) atomicAdd(&p.accum[6], (unsigned long long)cnt);
-            if (anybad) atomicOr(&p.accum[7], 1ULL);
+    }
+    __syncthreads();
+    if (p.accum && tid < kMaxHashCols + 2) {
+        if (tid < kMaxHashCols) {
+            const unsigned long long v = (unsigned long long)s_acc[2 * tid] | ((unsigned long long)s_acc[2 * tid + 1] << 32);
+            if (tid < p.n_hash && v) atomicXor(&p.accum[p.hash[tid].slot], v);
+        } else if (tid == kMaxHashCols) {
+            if (p.count_alive && s_acc[2 * kMaxHashCols]) atomicAdd(&p.accum[6], (unsigned long long)s_acc[2 * kMaxHashCols]);
+        } else if (s_acc[2 * kMaxHashCols + 1]) {
+            atomicOr(&p.accum[7], 1ULL);
         }
     }
+    // re-arm the tile counter for the next launch on this stream
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = (atomicAdd(&p.ticket[0], 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (s_last && tid == 0) { p.ticket[0] = 0u; p.ticket[1] = 0u; }
 }
 
 }  // namespace bgr

@@ -121,3 +121,73 @@ def test_presence_api_errors():
     with pytest.raises(BgrError) as ei:
         e2.rollback_component("C8", 4, OPT)
     assert ei.value.status == capi.BGR_ERR_CAPACITY
+
+
+def _particles_pair(n, depth=8, flags=0):
+    """The stress-test bundle with Velocity and Ttl registered optional (Transform always present)."""
+    from bevy_ggrs_b200.stress import synth_particles
+    worlds, cols = [], None
+    for w in (Engine(max_entities=n, max_depth=depth, flags=flags), OracleWorld()):
+        t = w.rollback_component("Transform", 40, capi.BGR_STRATEGY_CLONE)
+        v = w.rollback_component("Velocity", 12, capi.BGR_STRATEGY_COPY | OPT)
+        l = w.rollback_component("Ttl", 8, capi.BGR_STRATEGY_COPY | OPT)
+        w.checksum_component(v, 0, 12, capi.BGR_HASH_FLAG_ASSERT_FINITE_F32)
+        w.checksum_component(t, 0, 12, capi.BGR_HASH_FLAG_ASSERT_FINITE_F32)
+        w.add_system(capi.BGR_SYS_PARTICLES_UPDATE, [t, v])
+        w.add_system(capi.BGR_SYS_PARTICLES_DESPAWN, [l])
+        w.build()
+        w.spawn(n)
+        tf, vel, ttl = synth_particles(n, 17, 4, 30, z_fraction=0.2)
+        w.write_component(t, 0, tf); w.write_component(v, 0, vel); w.write_component(l, 0, ttl)
+        worlds.append(w)
+        cols = (t, v, l)
+    return worlds[0], worlds[1], cols
+
+
+@pytest.mark.parametrize("n", [700, 5000])
+def test_particles_bundle_with_optional_columns_stays_on_the_one_launch_path(n):
+    """Optional Velocity / Ttl on the particles bundle: update_particles only moves entities that have both Transform
+    and Velocity, despawn_particles only ages entities that have a Ttl, the Velocity checksum only covers entities
+    that have one, Load re-inserts / removes per entity — all inside the ONE fused launch per request vector, bit for
+    bit like the oracle (and like the generic kernels)."""
+    d = 4
+    SESS = (capi.BGR_SESSION_SYNCTEST, 8, d, 0)
+    eng, orc, cols = _particles_pair(n)
+    stp = _particles_pair(n, flags=capi.BGR_CFG_FORCE_STEPWISE)[0]
+    t, v, l = cols
+    rng = np.random.default_rng(23)
+    frame = 0
+    l0 = eng.launch_count()
+    ticks = 14
+    for tick in range(ticks):
+        reqs = []
+        if tick >= d:
+            reqs.append(Request(LOAD, frame - d))
+            for k in range(d):
+                reqs += [Request(ADVANCE, 0, [0]), Request(SAVE, frame - d + k + 1)] if k < d - 1 else [Request(ADVANCE, 0, [0])]
+        reqs += [Request(SAVE, frame), Request(ADVANCE, 0, [0])]
+        before = eng.launch_count()
+        a, b, c = [w.handle_requests(SESS, reqs) for w in (eng, orc, stp)]
+        assert eng.launch_count() - before == 1                 # ONE launch per request vector
+        assert a == b == c, f"tick {tick}"
+        assert eng.last_path_fused() and not stp.last_path_fused()
+        frame += 1
+        alive = orc.read_alive(0, n).astype(bool)
+        for r in rng.choice(np.flatnonzero(alive), 6, replace=False):
+            col = (v, l)[int(rng.integers(2))]
+            if orc.has_component(col, int(r), 1)[0]:
+                for w in (eng, orc, stp):
+                    w.remove_component(col, int(r))
+            else:
+                val = np.array([1.5, -2.5, 0.0], np.float32) if col == v else np.uint64(rng.integers(3, 20))
+                for w in (eng, orc, stp):
+                    w.insert_component(col, int(r), val)
+        _same(eng, orc, cols, n)
+        _same(stp, orc, cols, n)
+    assert 0 < orc.read_alive(0, n).sum() < n                   # Ttl ran out for some entities inside the run
+    vals, had = eng.peek(frame - 2, v, 0, n)
+    vo, ho = orc.peek(frame - 2, v, 0, n)
+    assert np.array_equal(had.astype(bool), ho.astype(bool)) and 0 < ho.sum() < n
+    assert np.array_equal(vals[ho.astype(bool)], vo[ho.astype(bool)])
+    for w in (eng, orc, stp):
+        w.close()
