@@ -25,6 +25,7 @@
 #include "seahash.cuh"
 #include "shard_group.hpp"
 #include "tma_copy.cuh"
+#include "generic_program.cuh"
 
 using namespace bgr;
 
@@ -192,6 +193,11 @@ struct bgr_engine {
     std::vector<PassiveRun> runs;
     uint32_t passive_bytes = 0;
     bool bundle_static_ck = false;  // both columns checksummed with the finite assertion: fully specialised kernel
+    // generic one-launch program (generic_program.cuh): any schema whose tile fits shared memory + the compiled systems
+    bool generic_ok = false;
+    int generic_bps = 0;            // resident blocks per SM of k_generic_program (occupancy query, cached)
+    int tune_generic = 1;
+    int tune_bundle = 1;            // 0: never use the specialised particles kernel (A/B tests of the generic program)
     bool bundle_opt = false;        // a registered column is BGR_STRATEGY_OPTIONAL: the presence-aware kernel variant (MODE 2)
     int tune_vec = 2, tune_minb = 2, tune_bps = 0, tune_passive_tma = 1;
     int tune_tma = 1;          // stepwise Save/Load through the TMA-staged bulk-copy kernel
@@ -669,6 +675,65 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
     return BGR_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// launch: generic one-launch program (any schema, compiled systems; generic_program.cuh)
+// ---------------------------------------------------------------------------------------------
+int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
+    e->main_dirty = true;
+    e->tiledep_chain = false;
+    GenericParams gp;
+    std::memset(&gp, 0, sizeof gp);
+    gp.arena = e->arena;
+    gp.order_base = e->cfg.order_base;
+    gp.accum = e->d_accum_c[0];
+    gp.ticket = e->d_ticket_c[0];
+    gp.out = e->d_out[buf];
+    gp.seq = e->seq;
+    if (e->d_trace && e->seq - e->trace_first_seq < e->trace_cap) gp.trace = e->d_trace + (e->seq - e->trace_first_seq) * 4;
+    gp.words = e->words; gp.tile_bytes = e->tile_bytes;
+    gp.n_ops = pg.n_ops; gp.n_saves = pg.n_saves;
+    gp.n_tiles = std::max(1u, e->tiles_for(pg.max_rows));
+    gp.live_rows = pg.live_rows;
+    if (!pg.first_is_load) gp.flags |= PF_READ_LIVE;
+    if (pg.has_load || pg.has_advance) gp.flags |= PF_WRITE_LIVE_ACTIVE;
+    for (const Column& c : e->cols)
+        if (c.hash_kind != BGR_HASH_NONE) {
+            HashSpec& h = gp.hash[gp.n_hash++];
+            h.first_plane = c.first_plane; h.off = c.hash_off; h.len = c.hash_len;
+            h.finite = c.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32; h.slot = uint32_t(c.ck_slot);
+            h.absent = c.absent;
+        }
+    uint32_t counter_index = 0;
+    for (const SystemReg& sy : e->systems) {
+        SysSpec& sp = gp.sys[gp.n_sys++];
+        sp.id = sy.id;
+        for (uint32_t c : sy.cols) sp.need |= e->cols[c].absent;
+        sp.plane0 = e->cols[sy.cols[0]].first_plane;
+        switch (sy.id) {
+        case BGR_SYS_U32_ADD:
+        case BGR_SYS_U32_SATSUB_DESPAWN: sp.plane0 += sy.params[0] / 4; sp.param = sy.params[1]; break;
+        case BGR_SYS_U32_STORE_CALL_COUNT: sp.plane0 += sy.params[0] / 4; sp.param = counter_index++; break;
+        case BGR_SYS_PARTICLES_UPDATE:
+        case BGR_SYS_BOX_MOVE: sp.plane1 = e->cols[sy.cols[1]].first_plane; break;
+        default: break;
+        }
+    }
+    std::memcpy(gp.ops, pg.ops, sizeof(Op) * pg.n_ops);
+    const size_t smem = e->tile_bytes;
+    if (e->generic_bps == 0) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generic_program, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_generic_program, kGenericBlock, smem));
+        e->generic_bps = std::max(1, nb);
+    }
+    const uint32_t grid = std::max(1u, std::min(gp.n_tiles, uint32_t(e->num_sms * e->generic_bps)));
+    k_generic_program<<<grid, kGenericBlock, smem, e->stream>>>(gp);
+    CUDA_TRY(cudaGetLastError());
+    e->launches += 1;
+    return BGR_OK;
+}
+
 // the reference's tracing span (schedule_systems.rs:171 `info_span!("ggrs", name = "HandleRequests")`) as an NVTX range
 struct NvtxRange {
     explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
@@ -699,9 +764,12 @@ int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs,
     if (!pg.spawn_vals.empty()) std::memcpy(e->h_spawn[buf], pg.spawn_vals.data(), pg.spawn_vals.size() * sizeof(float2));
     e->seq += 1;
     e->ticked = true;
-    bool fused = e->bundle_particles && !(e->cfg.flags & BGR_CFG_FORCE_STEPWISE);
+    const bool stepwise_forced = e->cfg.flags & BGR_CFG_FORCE_STEPWISE;
+    const bool bundle = e->bundle_particles && e->tune_bundle && !stepwise_forced;
+    const bool generic = !bundle && e->generic_ok && e->tune_generic && !stepwise_forced;
+    const bool fused = bundle || generic;   // one launch for the whole request vector
     uint32_t chains = 1;
-    rc = fused ? run_fused(e, pg, buf, &chains) : run_stepwise(e, pg, buf);
+    rc = bundle ? run_fused(e, pg, buf, &chains) : generic ? run_generic(e, pg, buf) : run_stepwise(e, pg, buf);
     if (rc != BGR_OK) return rc;
     // an event between two launches would serialise them; with host polling it is only a fallback, taken lazily
     if (!(e->tune_tiledep && e->tune_poll)) CUDA_TRY(cudaEventRecord(e->ev[buf], e->stream));
@@ -735,35 +803,51 @@ int collect(bgr_engine* e, bgr_checksum* out, uint32_t cap, uint32_t* n_out) {
     Pending pd = e->pending.front();
     e->pending.pop_front();
     const uint64_t t_wait0 = host_ns();
-    for (uint32_t c = 0; c < pd.chains && !pd.finished; ++c) {
-        // completion: each kernel's last block writes its sequence number after the results (system fence)
-        const volatile unsigned long long* flag = &e->h_out[pd.buf][size_t(c) * kResultStride + kSeqIndex];
+    // Completion: the last block of each chain's kernel publishes every result word as a self-validating pair
+    // (v, v ^ result_tag(seq, i)) plus a completion pair; a word is accepted when its halves XOR to this launch's tag.
+    unsigned long long folded[kMaxSaves * kAccStride];
+    for (uint32_t i = 0; i < pd.n_saves * kAccStride; ++i) folded[i] = 0;
+    const uint32_t n_words = pd.n_saves * kAccStride;
+    for (uint32_t c = 0; c < pd.chains; ++c) {
+        const volatile unsigned long long* blk = &e->h_out[pd.buf][size_t(c) * kResultStride];
+        unsigned long long words[kMaxSaves * kAccStride];
+        uint32_t valid = 0;
+        bool seq_ok = false;
+        auto ready = [&]() {
+            if (!seq_ok) {
+                const unsigned long long a = blk[2 * kSeqIndex], b = blk[2 * kSeqIndex + 1];
+                if ((a ^ b) != result_tag(pd.seq, kSeqIndex)) return false;
+                seq_ok = true;
+            }
+            while (valid < n_words) {
+                const unsigned long long a = blk[2 * valid], b = blk[2 * valid + 1];
+                if ((a ^ b) != result_tag(pd.seq, valid)) return false;
+                words[valid++] = a;
+            }
+            return true;
+        };
         bool done = false;
-        if (e->tune_poll) {
+        if (e->tune_poll && !pd.finished) {
             for (int spin = 0; spin < 200000; ++spin) {
-                if (*flag == pd.seq) { done = true; break; }
+                if (ready()) { done = true; break; }
                 __builtin_ia32_pause();
             }
         }
         if (!done) {  // the event / the stream is ordered after every chain
-            if (e->tune_tiledep && e->tune_poll) CUDA_TRY(cudaStreamSynchronize(e->stream));
-            else CUDA_TRY(cudaEventSynchronize(e->ev[pd.buf]));
-            break;
+            if (!pd.finished) {
+                if (e->tune_tiledep && e->tune_poll) CUDA_TRY(cudaStreamSynchronize(e->stream));
+                else CUDA_TRY(cudaEventSynchronize(e->ev[pd.buf]));
+            }
+            if (!ready()) return fail(BGR_ERR_CUDA, "request vector completed without publishing valid results");
+        }
+        // fold the chains' result blocks: XOR the column words, sum the live-row counts, OR the flags
+        for (uint32_t i = 0; i < n_words; ++i) {
+            const uint32_t w = i % kAccStride;
+            if (w == 6) folded[i] += words[i]; else if (w == 7) folded[i] |= words[i]; else folded[i] ^= words[i];
         }
     }
     const uint64_t t_wait1 = host_ns();
     e->prof[3] += t_wait1 - t_wait0;
-    // fold the chains' result blocks: XOR the column words, sum the live-row counts, OR the flags
-    unsigned long long folded[kMaxSaves * kAccStride];
-    for (uint32_t i = 0; i < pd.n_saves * kAccStride; ++i) {
-        unsigned long long v = 0;
-        const uint32_t w = i % kAccStride;
-        for (uint32_t c = 0; c < pd.chains; ++c) {
-            const unsigned long long x = e->h_out[pd.buf][size_t(c) * kResultStride + i];
-            if (w == 6) v += x; else if (w == 7) v |= x; else v ^= x;
-        }
-        folded[i] = v;
-    }
     const unsigned long long* r = folded;
     e->last_partials.clear();
     bool nonfinite = false;
@@ -1024,6 +1108,8 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_prefetch = env_int("BGR_TUNE_PREFETCH", 1);
     e->tune_grid = env_int("BGR_TUNE_GRID", 0);
     e->tune_tiledep = env_int("BGR_TUNE_TILEDEP", 1);
+    e->tune_generic = env_int("BGR_TUNE_GENERIC", 1);
+    e->tune_bundle = env_int("BGR_TUNE_BUNDLE", 1);
     e->n_chains = std::max(1, std::min(int(bgr_engine::kMaxChains), env_int("BGR_TUNE_CHAINS", 1)));
     if (e->tune_vec != 1 && e->tune_vec != 2 && e->tune_vec != 4) e->tune_vec = 2;
     e->st.confirmed = 0;
@@ -1228,6 +1314,13 @@ BGR_API int bgr_build(bgr_engine* e) {
             CUDA_TRY(cudaHostGetDevicePointer(&e->d_spawn[i], e->h_spawn[i], 0));
         }
     detect_bundles(e);
+    {   // generic one-launch program: every registered system has a shared-memory implementation, the tile fits twice per SM
+        bool ok = e->systems.size() <= size_t(kMaxGenericSys) && e->tile_bytes <= 100u * 1024u;
+        for (const SystemReg& sy : e->systems)
+            ok = ok && (sy.id == BGR_SYS_U32_ADD || sy.id == BGR_SYS_U32_SATSUB_DESPAWN || sy.id == BGR_SYS_U32_STORE_CALL_COUNT ||
+                        sy.id == BGR_SYS_PARTICLES_UPDATE || sy.id == BGR_SYS_PARTICLES_DESPAWN || sy.id == BGR_SYS_BOX_MOVE);
+        e->generic_ok = ok;
+    }
     {   // TMA copy kernel: up to six one-tile stages in ~200 KB of shared memory, at least two
         uint32_t st = uint32_t(std::min<size_t>((200u * 1024u) / e->tile_bytes, size_t(kTmaMaxStages)));
         if (env_int("BGR_TUNE_TMA_STAGES", 0) > 0) st = std::min(st, uint32_t(env_int("BGR_TUNE_TMA_STAGES", 0)));

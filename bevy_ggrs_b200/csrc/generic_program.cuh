@@ -1,0 +1,273 @@
+// The one-launch path for ANY registered schema and the compiled GgrsSchedule systems: a whole Vec<GgrsRequest>
+// (Load / Advance / Save ...) interpreted by one kernel, like k_particles_program, but without knowing the columns at
+// compile time.  One 512-row tile per block iteration lives in SHARED MEMORY for the whole program:
+//
+//     cp.async.bulk  slot/live image --> shared tile              (LOAD, or the program's first read)
+//     ADVANCE : every registered system updates its rows of the shared tile in place (a thread owns its rows for the
+//               whole program, so no barrier separates systems; despawn commands are applied after the last system)
+//     SAVE    : cp.async.bulk shared tile --> the frame's slot, while all threads hash the checksummed byte ranges
+//               of their rows out of the same tile (component_checksum.rs:67-108) and count live rows
+//     end     : cp.async.bulk shared tile --> live image
+//
+// so a SyncTest tick of a box_game / score-and-health style world is ONE launch instead of one launch per request
+// and per system (round 1's "stepwise" path, which stays as the fallback for schemas wider than a shared-memory tile).
+// Per-entity component presence (BGR_STRATEGY_OPTIONAL) is the row's mask byte: it travels with the tile, and every
+// system / checksum applies the reference's query filter per row (kernels.cuh row_matches).
+//
+// Reference semantics: handle_requests (schedule_systems.rs:170-289) over ComponentSnapshotPlugin::save / load
+// (component_snapshot.rs:66-123), the checksum plugins, and the systems listed in include/bevy_ggrs_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+#include "../../include/bevy_ggrs_b200.h"
+#include "kernels.cuh"
+#include "seahash.cuh"
+#include "tma_copy.cuh"
+
+namespace bgr {
+
+constexpr int kMaxGenericSys = 8;
+constexpr int kGenericBlock = 256;
+constexpr int kGenericRowsPerThread = kTileRows / kGenericBlock;
+
+struct SysSpec {
+    uint32_t id;      // bgr_system
+    uint32_t plane0;  // first word plane the system touches (column's first plane + byte_offset / 4)
+    uint32_t plane1;  // second bound column's first plane (Velocity for the Transform/Velocity systems)
+    uint32_t need;    // absent bits of the bound columns: the query matches a row iff row_matches(mask, need)
+    uint32_t param;   // k (U32_ADD / U32_SATSUB_DESPAWN) or the system's index among the call-count systems
+};
+
+struct GenericParams {
+    uint8_t* arena;
+    unsigned long long order_base;
+    unsigned long long* accum;  // device [kMaxSaves][kAccStride]
+    unsigned long long* out;    // host-mapped result block (same layout / protocol as k_particles_program)
+    unsigned int* ticket;       // [0] block-completion ticket, [1] dynamic tile counter
+    unsigned long long seq;
+    unsigned long long* trace;
+    uint32_t words, tile_bytes, n_ops, n_saves, n_tiles, live_rows, flags, n_hash, n_sys;
+    HashSpec hash[kMaxHashCols];
+    SysSpec sys[kMaxGenericSys];
+    Op ops[kMaxOps];
+};
+static_assert(sizeof(GenericParams) <= 4000, "kernel parameter block must fit 4 KB");
+
+// seahash of bytes [off, off+len) of one row's element whose words are `col[w * kTileRows]` (a column of the shared tile)
+__device__ __forceinline__ uint64_t hash_row_range(const uint32_t* col, uint32_t off, uint32_t len) {
+    if (((off | len) & 3u) == 0u) {  // word-aligned range (every POD of u32 / f32 / u64 fields): no byte shuffling
+        const uint32_t* w = col + size_t(off >> 2) * kTileRows;
+        uint64_t a = kSeaA, b = kSeaB, c = kSeaC, d = kSeaD;
+        uint32_t i = 0;
+        for (; i + 8 <= len; i += 8) {
+            const uint64_t x = uint64_t(w[0]) | (uint64_t(w[kTileRows]) << 32);
+            w += 2 * kTileRows;
+            const uint64_t t = sea_diffuse(a ^ x);
+            a = b; b = c; c = d; d = t;
+        }
+        if (i < len) a = sea_diffuse(a ^ uint64_t(w[0]));
+        return sea_diffuse(a ^ b ^ c ^ d ^ uint64_t(len));
+    }
+    auto byte_at = [&](uint32_t q) -> uint8_t {
+        const uint32_t bb = off + q;
+        return uint8_t(col[size_t(bb >> 2) * kTileRows] >> (8 * (bb & 3u)));
+    };
+    return sea_hash_stream(len, byte_at);
+}
+
+__global__ void __launch_bounds__(kGenericBlock) k_generic_program(const __grid_constant__ GenericParams p) {
+    extern __shared__ __align__(128) uint8_t s_tile[];
+    __shared__ unsigned int s_acc[kMaxSaves * kAccStride * 2];
+    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ uint32_t s_next;
+    __shared__ unsigned int s_last;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    if (p.trace && tid == 0) atomicMin(&p.trace[0], globaltimer_ns());
+    for (uint32_t i = tid; i < p.n_saves * kAccStride * 2; i += kGenericBlock) s_acc[i] = 0u;
+    if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
+    __syncthreads();
+
+    uint8_t* const s_alive = s_tile + size_t(p.words) * kPlaneBytes;
+    uint32_t phase = 0;
+    bool store_pending = false;  // a bulk store may still be reading the shared tile (block-uniform)
+
+    // bring tile `t` of image `img` into shared memory; rows the image never contained come back dead
+    auto load_tile = [&](const uint8_t* img, uint32_t t, uint32_t n_rows_src) {
+        __syncthreads();  // every thread is done with the previous content
+        if (tid == 0) {
+            tma_wait_read<0>();
+            mbar_arrive_expect_tx(&s_bar, p.tile_bytes);
+            tma_load_1d(s_tile, img + size_t(t) * p.tile_bytes, p.tile_bytes, &s_bar);
+        }
+        mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        store_pending = false;
+        if (size_t(t + 1) * kTileRows > n_rows_src) {
+#pragma unroll
+            for (int k = 0; k < kGenericRowsPerThread; ++k) {
+                const uint32_t r = tid + k * kGenericBlock;
+                if (t * kTileRows + r >= n_rows_src) s_alive[r] = 0;
+            }
+        }
+    };
+    auto store_tile = [&](uint8_t* img, uint32_t t) {
+        fence_proxy_async();  // generic-proxy writes of this thread are visible to the bulk (async-proxy) store
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_1d(img + size_t(t) * p.tile_bytes, s_tile, p.tile_bytes);
+            tma_commit();
+        }
+        store_pending = true;
+    };
+    auto before_write = [&]() {  // the shared tile is about to be modified: pending bulk stores must have read it
+        if (store_pending) {
+            if (tid == 0) tma_wait_read<0>();
+            __syncthreads();
+            store_pending = false;
+        }
+    };
+
+    const uint8_t* first_img = p.arena + ((p.flags & PF_READ_LIVE) ? size_t(0) : (size_t(p.ops[0].image_off256) << 8));
+    const uint32_t first_rows = (p.flags & PF_READ_LIVE) ? p.live_rows : p.ops[0].n_rows;
+
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles;) {
+        __syncthreads();  // every thread has read the previous s_next
+        if (tid == 0) s_next = gridDim.x + atomicAdd(&p.ticket[1], 1u);  // the block's next tile (read after the barrier in load_tile)
+        load_tile(first_img, tile, first_rows);
+        const uint32_t next_tile = s_next;
+
+        for (uint32_t i = (p.flags & PF_READ_LIVE) ? 0u : 1u; i < p.n_ops; ++i) {
+            const Op& op = p.ops[i];
+            if (op.kind == OP_ADVANCE) {
+                before_write();
+                const float dt = __uint_as_float(op.dt_bits);
+#pragma unroll
+                for (int k = 0; k < kGenericRowsPerThread; ++k) {
+                    const uint32_t r = tid + k * kGenericBlock;
+                    const uint32_t m = s_alive[r];  // the schedule's systems all see the entity as it was before the frame:
+                    bool kill = false;              // despawn commands are applied after the last system
+                    uint32_t* row = reinterpret_cast<uint32_t*>(s_tile) + r;
+                    for (uint32_t s = 0; s < p.n_sys; ++s) {
+                        const SysSpec sy = p.sys[s];
+                        if (!row_matches(m, sy.need)) continue;
+                        uint32_t* w0 = row + size_t(sy.plane0) * kTileRows;
+                        switch (sy.id) {
+                        case BGR_SYS_U32_ADD: w0[0] += sy.param; break;
+                        case BGR_SYS_U32_SATSUB_DESPAWN: {
+                            uint32_t v = w0[0];
+                            v = v > sy.param ? v - sy.param : 0u;
+                            w0[0] = v;
+                            kill = kill || v == 0u;
+                            break;
+                        }
+                        case BGR_SYS_U32_STORE_CALL_COUNT: w0[0] = op.call_count + sy.param; break;
+                        case BGR_SYS_PARTICLES_UPDATE: {
+                            uint32_t* v = row + size_t(sy.plane1) * kTileRows;
+                            uint32_t tx = w0[0], ty = w0[kTileRows], tz = w0[2 * kTileRows], vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
+                            particle_step(tx, ty, tz, vx, vy, vz, dt);
+                            w0[0] = tx; w0[kTileRows] = ty; w0[2 * kTileRows] = tz; v[0] = vx; v[kTileRows] = vy; v[2 * kTileRows] = vz;
+                            break;
+                        }
+                        case BGR_SYS_PARTICLES_DESPAWN: {
+                            uint64_t ttl = (uint64_t(w0[kTileRows]) << 32) | w0[0];
+                            ttl -= 1;
+                            w0[0] = uint32_t(ttl); w0[kTileRows] = uint32_t(ttl >> 32);
+                            kill = kill || ttl == 0;
+                            break;
+                        }
+                        case BGR_SYS_BOX_MOVE: {
+                            float* t = reinterpret_cast<float*>(w0);
+                            float* v = reinterpret_cast<float*>(row + size_t(sy.plane1) * kTileRows);
+                            float tx = t[0], ty = t[kTileRows], tz = t[2 * kTileRows], vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
+                            const unsigned long long handle = p.order_base + size_t(tile) * kTileRows + r;
+                            const uint32_t n_players = (op.flags >> 8) & 0xFu;
+                            const uint32_t input = handle < n_players && handle < 8 ? op.inputs[handle] : 0u;
+                            box_move_step(tx, ty, tz, vx, vy, vz, dt, input);
+                            t[0] = tx; t[kTileRows] = ty; t[2 * kTileRows] = tz; v[0] = vx; v[kTileRows] = vy; v[2 * kTileRows] = vz;
+                            break;
+                        }
+                        default: break;
+                        }
+                    }
+                    if (kill) s_alive[r] = 0;
+                }
+            } else if (op.kind == OP_SAVE) {
+                // the bulk store streams the tile to the frame's slot while the threads hash their rows out of it
+                if (!(op.flags & OPF_NO_STORE)) store_tile(p.arena + (size_t(op.image_off256) << 8), tile);
+                uint64_t hx[kMaxHashCols];
+#pragma unroll
+                for (int c = 0; c < kMaxHashCols; ++c) hx[c] = 0;
+                uint32_t n_alive = 0, bad = 0;
+#pragma unroll
+                for (int k = 0; k < kGenericRowsPerThread; ++k) {
+                    const uint32_t r = tid + k * kGenericBlock;
+                    const uint32_t m = s_alive[r];
+                    if (!(m & 1u)) continue;
+                    ++n_alive;
+                    const uint64_t t0 = sea_order_lane(p.order_base + size_t(tile) * kTileRows + r);
+#pragma unroll
+                    for (int c = 0; c < kMaxHashCols; ++c) {
+                        if (c < p.n_hash) {
+                            const HashSpec hs = p.hash[c];
+                            if (m & hs.absent) continue;  // Query<(&RollbackId, &T)> does not match this entity
+                            const uint32_t* col = reinterpret_cast<const uint32_t*>(s_tile) + size_t(hs.first_plane) * kTileRows + r;
+                            if (hs.finite)
+                                for (uint32_t q = 0; q + 4 <= hs.len; q += 4) bad |= f32_bits_nonfinite(col[size_t((hs.off + q) >> 2) * kTileRows]);
+                            hx[c] ^= sea_hash_entity(t0, hash_row_range(col, hs.off, hs.len));
+                        }
+                    }
+                }
+                const unsigned full = 0xffffffffu;
+                unsigned int* a = &s_acc[op.save_index * kAccStride * 2];
+#pragma unroll
+                for (int c = 0; c < kMaxHashCols; ++c) {
+                    if (c < p.n_hash) {
+                        const uint32_t lo = __reduce_xor_sync(full, uint32_t(hx[c])), hi = __reduce_xor_sync(full, uint32_t(hx[c] >> 32));
+                        if (lane == 0) { atomicXor(&a[2 * p.hash[c].slot], lo); atomicXor(&a[2 * p.hash[c].slot + 1], hi); }
+                    }
+                }
+                const uint32_t cnt = __reduce_add_sync(full, n_alive);
+                const uint32_t anybad = __reduce_or_sync(full, bad);
+                if (lane == 0) { atomicAdd(&a[12], cnt); if (anybad) atomicOr(&a[14], 1u); }
+            } else {  // OP_LOAD
+                load_tile(p.arena + (size_t(op.image_off256) << 8), tile, op.n_rows);
+            }
+        }
+        if (p.flags & PF_WRITE_LIVE_ACTIVE) store_tile(p.arena, tile);
+        tile = next_tile;
+    }
+    if (tid == 0) tma_wait_all();  // every bulk store has landed before the results are published
+
+    // ---- block partials -> global accumulators -> (last block) host-visible results: k_particles_program's protocol ----
+    __syncthreads();
+    for (uint32_t i = tid; i < p.n_saves * kAccStride; i += kGenericBlock) {
+        unsigned long long v = (unsigned long long)s_acc[2 * i] | ((unsigned long long)s_acc[2 * i + 1] << 32);
+        const uint32_t c = i % kAccStride;
+        if (v) {
+            if (c == 6) atomicAdd(&p.accum[i], v);
+            else if (c == 7) atomicOr(&p.accum[i], v);
+            else atomicXor(&p.accum[i], v);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (p.trace && tid == 0) atomicMax(&p.trace[1], globaltimer_ns());
+    if (tid == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (s_last) {
+        __threadfence();
+        for (uint32_t i = tid; i < p.n_saves * kAccStride; i += kGenericBlock)
+            publish_pair(p.out, i, atomicExch(&p.accum[i], 0ULL), p.seq);
+        if (tid == 0) publish_pair(p.out, kSeqIndex, p.seq, p.seq);
+        __syncthreads();
+        if (tid == 0) {
+            p.ticket[0] = 0u;
+            p.ticket[1] = 0u;
+            if (p.trace) p.trace[2] = globaltimer_ns();
+        }
+    }
+}
+
+}  // namespace bgr

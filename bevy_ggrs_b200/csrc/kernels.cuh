@@ -40,8 +40,17 @@ constexpr int kMaxSaves = 40;
 constexpr int kMaxPassive = 64;   // word planes that no compiled system touches (per-thread fallback)
 constexpr int kMaxRuns = 8;       // runs of adjacent passive planes (TMA path)
 constexpr int kAccStride = 8;     // u64 per save: [0..5] column xors, [6] active rows, [7] flags
-constexpr int kSeqIndex = kMaxSaves * kAccStride;  // result block word that receives the launch sequence number last
-constexpr int kResultStride = kSeqIndex + 8;         // u64 words per result block (one block per chain per buffer)
+// Result block (host-mapped, one per chain per buffer): kResultPairs PAIRS of u64.  Result word i is published as
+// (v, v ^ result_tag(seq, i)); pair kSeqIndex is the completion pair (v = seq).  The host accepts a word when the two
+// halves XOR to the tag of the sequence number it is waiting for: every word validates itself, so the GPU needs no
+// system-scope fence and no separate flag store behind the data (that round trip was 3.2 us of every synchronous call,
+// tools/launch_latency.cu), a torn or stale pair simply fails the test and is polled again.
+constexpr int kSeqIndex = kMaxSaves * kAccStride;   // index of the completion pair
+constexpr int kResultPairs = kSeqIndex + 1;
+constexpr int kResultStride = 2 * kResultPairs + 6;  // u64 words per result block
+__host__ __device__ inline unsigned long long result_tag(unsigned long long seq, uint32_t i) {
+    return ((seq * 0x9E3779B97F4A7C15ULL) ^ ((unsigned long long)(i + 1) * 0xD6E8FEB86659FD93ULL)) | 1ULL;  // never 0: zeroed memory is invalid
+}
 
 __host__ __device__ inline uint32_t tile_bytes_of(uint32_t words) { return kTileRows * (4u * words + 1u); }
 __host__ __device__ inline size_t word_offset(uint32_t words, uint32_t row, uint32_t plane) {
@@ -101,7 +110,7 @@ struct ProgramParams {
     unsigned long long* out;    // host-mapped [kMaxSaves][kAccStride]
     unsigned int* ticket;       // [0] block-completion ticket, [1] dynamic tile counter
     const float2* spawn_vals;   // (vx, vy) of every particle spawned by this program (host-mapped), particles.rs:265
-    unsigned long long seq;     // written to out[kSeqIndex] after the results (completion flag the host polls)
+    unsigned long long seq;     // sequence number of this launch: tags every published result pair (result_tag)
     unsigned long long* trace;  // nullptr, or this launch's row of the launch trace: [0] min block start, [1] max block end, [2] results published (globaltimer ns)
     uint32_t words, tile_bytes, n_ops, n_saves;
     uint32_t tile_begin, n_tiles;  // this launch covers tiles [tile_begin, n_tiles) (one chain of the entity range)
@@ -152,6 +161,9 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     return t;
+}
+__device__ __forceinline__ void publish_pair(unsigned long long* out, uint32_t i, unsigned long long v, unsigned long long seq) {
+    reinterpret_cast<ulonglong2*>(out)[i] = make_ulonglong2(v, v ^ result_tag(seq, i));  // one 16-byte store
 }
 __device__ __forceinline__ uint32_t f32_bits_nonfinite(uint32_t b) { return ((b & 0x7f800000u) == 0x7f800000u) ? 1u : 0u; }
 
@@ -618,14 +630,13 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     if (s_last) {
         __threadfence();
         for (uint32_t i = tid; i < p.n_saves * kAccStride; i += BLOCK)
-            p.out[i] = atomicExch(&p.accum[i], 0ULL);  // publish and re-arm for the next launch
-        __threadfence_system();
+            publish_pair(p.out, i, atomicExch(&p.accum[i], 0ULL), p.seq);  // publish (self-validating pair) and re-arm for the next launch
+        if (tid == 0) publish_pair(p.out, kSeqIndex, p.seq, p.seq);       // completion pair: also there when nothing was saved
         __syncthreads();
         if (tid == 0) {
             if (tile_signal) st_release_gpu(p.grid_done, p.done_seq);  // every block's stores precede its ticket (fence above)
             p.ticket[0] = 0u;
             p.ticket[1] = 0u;
-            *reinterpret_cast<volatile unsigned long long*>(&p.out[kSeqIndex]) = p.seq;  // host polls this word
             if (p.trace) p.trace[2] = globaltimer_ns();
         }
     }
@@ -699,10 +710,8 @@ __global__ void __launch_bounds__(256) k_checksum_column(const uint8_t* __restri
 
 // copy the accumulators of n_saves saves to the host-mapped result block and re-arm them
 __global__ void k_publish(unsigned long long* accum, unsigned long long* out, uint32_t n, unsigned long long seq) {
-    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) out[i] = atomicExch(&accum[i], 0ULL);
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) *reinterpret_cast<volatile unsigned long long*>(&out[kSeqIndex]) = seq;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) publish_pair(out, i, atomicExch(&accum[i], 0ULL), seq);
+    if (threadIdx.x == 0) publish_pair(out, kSeqIndex, seq, seq);
 }
 
 // ---- ECS column (array of T, `stride` bytes apart) <-> tile-planar image -----------------------
@@ -842,11 +851,33 @@ __global__ void __launch_bounds__(256) k_sys_particles_spawn(uint8_t* img, uint3
 // move_cube_system (box_game.rs:154-206), BASELINE config C1.  player handle == RollbackOrdered index.
 // `FRICTION.powf(dt)` is libm on the CPU and CUDA powf here: this is the one system of the path whose f32
 // results are only guaranteed within a tolerance (|d| <= 1e-5 * max(1, |x|), tested), not bit-exact.
+__device__ __forceinline__ void box_move_step(float& tx, float& ty, float& tz, float& vx, float& vy, float& vz, float dt, uint32_t input) {
+    const float ACCELERATION = 18.0f, MAX_SPEED = 3.0f, FRICTION = 0.0018f, PLANE_SIZE = 5.0f, CUBE_SIZE = 0.2f;
+    const bool up = input & 1u, down = input & 2u, left = input & 4u, right = input & 8u;
+    const float a = __fmul_rn(ACCELERATION, dt);
+    if (up && !down) vz = __fsub_rn(vz, a);
+    if (!up && down) vz = __fadd_rn(vz, a);
+    if (left && !right) vx = __fsub_rn(vx, a);
+    if (!left && right) vx = __fadd_rn(vx, a);
+    const float fr = powf(FRICTION, dt);
+    if (!up && !down) vz = __fmul_rn(vz, fr);
+    if (!left && !right) vx = __fmul_rn(vx, fr);
+    vy = __fmul_rn(vy, fr);
+    // glam Vec3::clamp_length_max(MAX_SPEED)
+    const float len_sq = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
+    if (len_sq > __fmul_rn(MAX_SPEED, MAX_SPEED)) {
+        const float l = __fsqrt_rn(len_sq);
+        vx = __fmul_rn(MAX_SPEED, __fdiv_rn(vx, l)); vy = __fmul_rn(MAX_SPEED, __fdiv_rn(vy, l)); vz = __fmul_rn(MAX_SPEED, __fdiv_rn(vz, l));
+    }
+    tx = __fadd_rn(tx, __fmul_rn(vx, dt)); ty = __fadd_rn(ty, __fmul_rn(vy, dt)); tz = __fadd_rn(tz, __fmul_rn(vz, dt));
+    const float hw = __fmul_rn(__fsub_rn(PLANE_SIZE, CUBE_SIZE), 0.5f);
+    tx = tx < -hw ? -hw : (tx > hw ? hw : tx);
+    tz = tz < -hw ? -hw : (tz > hw ? hw : tz);
+}
 __global__ void k_sys_box_move(uint8_t* img, uint32_t words, uint32_t t_plane, uint32_t v_plane, uint32_t n_rows,
                                uint32_t dt_bits, unsigned long long inputs_packed, uint32_t n_players, unsigned long long order_base,
                                uint32_t need) {
     const float dt = __uint_as_float(dt_bits);
-    const float ACCELERATION = 18.0f, MAX_SPEED = 3.0f, FRICTION = 0.0018f, PLANE_SIZE = 5.0f, CUBE_SIZE = 0.2f;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x) {
         if (!row_matches(img[alive_offset(words, r)], need)) continue;
         float* t = reinterpret_cast<float*>(img + word_offset(words, r, t_plane));
@@ -855,26 +886,7 @@ __global__ void k_sys_box_move(uint8_t* img, uint32_t words, uint32_t t_plane, u
         float vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
         const unsigned long long handle = order_base + r;
         const uint32_t input = handle < n_players && handle < 8 ? uint32_t(inputs_packed >> (8 * uint32_t(handle))) & 0xffu : 0u;
-        const bool up = input & 1u, down = input & 2u, left = input & 4u, right = input & 8u;
-        const float a = __fmul_rn(ACCELERATION, dt);
-        if (up && !down) vz = __fsub_rn(vz, a);
-        if (!up && down) vz = __fadd_rn(vz, a);
-        if (left && !right) vx = __fsub_rn(vx, a);
-        if (!left && right) vx = __fadd_rn(vx, a);
-        const float fr = powf(FRICTION, dt);
-        if (!up && !down) vz = __fmul_rn(vz, fr);
-        if (!left && !right) vx = __fmul_rn(vx, fr);
-        vy = __fmul_rn(vy, fr);
-        // glam Vec3::clamp_length_max(MAX_SPEED)
-        const float len_sq = __fadd_rn(__fadd_rn(__fmul_rn(vx, vx), __fmul_rn(vy, vy)), __fmul_rn(vz, vz));
-        if (len_sq > __fmul_rn(MAX_SPEED, MAX_SPEED)) {
-            const float l = __fsqrt_rn(len_sq);
-            vx = __fmul_rn(MAX_SPEED, __fdiv_rn(vx, l)); vy = __fmul_rn(MAX_SPEED, __fdiv_rn(vy, l)); vz = __fmul_rn(MAX_SPEED, __fdiv_rn(vz, l));
-        }
-        tx = __fadd_rn(tx, __fmul_rn(vx, dt)); ty = __fadd_rn(ty, __fmul_rn(vy, dt)); tz = __fadd_rn(tz, __fmul_rn(vz, dt));
-        const float hw = __fmul_rn(__fsub_rn(PLANE_SIZE, CUBE_SIZE), 0.5f);
-        tx = tx < -hw ? -hw : (tx > hw ? hw : tx);
-        tz = tz < -hw ? -hw : (tz > hw ? hw : tz);
+        box_move_step(tx, ty, tz, vx, vy, vz, dt, input);
         t[0] = tx; t[kTileRows] = ty; t[2 * kTileRows] = tz;
         v[0] = vx; v[kTileRows] = vy; v[2 * kTileRows] = vz;
     }

@@ -39,6 +39,17 @@ constexpr uint32_t kGroupBufs = 8;             // result buffers per rank == max
 constexpr uint32_t kGroupMaxRanks = 64;
 constexpr uint32_t kGroupMaxSaves = 40;        // == kMaxSaves
 constexpr uint32_t kGroupAccStride = 8;        // == kAccStride: [0..5] column xors, [6] active rows, [7] flags
+// Result words are published as self-validating pairs (v, v ^ tag(seq, i)), kernels.cuh result_tag / publish_pair;
+// pair kGroupMaxSaves * kGroupAccStride is the completion pair.
+inline uint64_t group_result_tag(uint64_t seq, uint32_t i) {
+    return ((seq * 0x9E3779B97F4A7C15ULL) ^ (uint64_t(i + 1) * 0xD6E8FEB86659FD93ULL)) | 1ULL;
+}
+inline bool group_pair_valid(const volatile uint64_t* blk, uint32_t i, uint64_t seq, uint64_t* v_out) {
+    const uint64_t a = blk[2 * i], b = blk[2 * i + 1];
+    if ((a ^ b) != group_result_tag(seq, i)) return false;
+    *v_out = a;
+    return true;
+}
 
 struct alignas(64) GroupHeader {
     std::atomic<uint32_t> magic, world, block_words, joined, left;
@@ -201,7 +212,21 @@ public:
             const volatile uint64_t* blk = block(r, buf);
             const uint64_t want = ranks_[r].seq_base.load(std::memory_order_acquire) + gseq;
             const uint32_t seq_index = kGroupMaxSaves * kGroupAccStride;
-            if (!spin_until([&] { return m.gseq.load(std::memory_order_acquire) == gseq && blk[seq_index] == want; }, timeout_ms)) {
+            uint64_t words[kGroupMaxSaves * kGroupAccStride];
+            uint32_t valid = 0;  // pairs [0, valid) of this rank's block have been accepted
+            bool seq_ok = false;
+            auto ready = [&] {
+                if (m.gseq.load(std::memory_order_acquire) != gseq) return false;
+                uint64_t v;
+                if (!seq_ok) { if (!group_pair_valid(blk, seq_index, want, &v)) return false; seq_ok = true; }
+                const uint32_t n = m.n_saves * kGroupAccStride;
+                while (valid < n) {
+                    if (!group_pair_valid(blk, valid, want, &words[valid])) return false;
+                    ++valid;
+                }
+                return true;
+            };
+            if (!spin_until(ready, timeout_ms)) {
                 *err = "shard group: rank " + std::to_string(r) + " did not publish request vector " + std::to_string(gseq) + " (timeout)";
                 return false;
             }
@@ -212,7 +237,7 @@ public:
                 return false;
             }
             for (uint32_t k = 0; k < n_saves && k < cap; ++k) {
-                const volatile uint64_t* row = blk + size_t(k) * kGroupAccStride;
+                const uint64_t* row = words + size_t(k) * kGroupAccStride;
                 for (uint32_t c = 0; c < BGR_MAX_CHECKSUM_COLUMNS; ++c) out[k].xor_[c] ^= row[c];
                 out[k].active += row[6];
                 out[k].total += m.totals[k];
@@ -226,16 +251,16 @@ public:
 
     // CPU stand-in for the kernel's publish (tests): write the partials of group sequence g into this rank's block
     void publish_block_from_host(uint64_t gseq, const bgr_partial* parts, uint32_t n) {
-        uint64_t* blk = block(rank, buf_of(gseq));
+        volatile uint64_t* blk = block(rank, buf_of(gseq));
+        const uint64_t seq = ranks_[rank].seq_base.load() + gseq;
+        auto put = [&](uint32_t i, uint64_t v) { blk[2 * i] = v; blk[2 * i + 1] = v ^ group_result_tag(seq, i); };
         for (uint32_t k = 0; k < n; ++k) {
-            uint64_t* row = blk + size_t(k) * kGroupAccStride;
-            for (uint32_t c = 0; c < BGR_MAX_CHECKSUM_COLUMNS; ++c) row[c] = parts[k].xor_[c];
-            row[6] = parts[k].active;
-            row[7] = 0;
+            for (uint32_t c = 0; c < BGR_MAX_CHECKSUM_COLUMNS; ++c) put(k * kGroupAccStride + c, parts[k].xor_[c]);
+            put(k * kGroupAccStride + 6, parts[k].active);
+            put(k * kGroupAccStride + 7, 0);
         }
+        put(kGroupMaxSaves * kGroupAccStride, seq);
         std::atomic_thread_fence(std::memory_order_release);
-        reinterpret_cast<std::atomic<uint64_t>*>(&blk[kGroupMaxSaves * kGroupAccStride])
-            ->store(ranks_[rank].seq_base.load() + gseq, std::memory_order_release);
     }
 
 private:

@@ -80,9 +80,16 @@ __global__ void __launch_bounds__(kTmaBlock, 1) k_image_tma(const __grid_constan
         if (lane == 0) {
             bool ended = false;
             uint32_t loaded = 0;  // iterations whose load (or end marker) has been issued; iteration i uses stage i % S
+            // Tiles are claimed TWO issues ahead of their use: the first one is the block's own index, later ones come
+            // from the global counter, and the atomic's round trip (~1 us, once per 31 KB tile — it cost a third of a
+            // 1M-entity Load when it sat on the producer's critical path) is hidden behind the previous tile's copies.
+            uint32_t claim = blockIdx.x;
+            uint32_t pending = gridDim.x + atomicAdd(&p.ticket[1], 1u);
             auto issue = [&]() {
                 const uint32_t s = loaded % S;
-                const uint32_t tile = atomicAdd(&p.ticket[1], 1u);
+                const uint32_t tile = claim;
+                claim = pending;
+                if (tile < p.n_tiles) pending = gridDim.x + atomicAdd(&p.ticket[1], 1u);
                 if (tile >= p.n_tiles) {
                     s_tile[s] = kTmaEnd;
                     mbar_arrive(&full[s]);

@@ -53,13 +53,17 @@ def _app(backend, native_resource):
     return app, tf, vel, bad
 
 
-def test_box_game_synctest_c1_gpu_vs_oracle():
-    eng, orc = Engine(max_entities=4, max_depth=9), OracleWorld()
+@pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])
+def test_box_game_synctest_c1_gpu_vs_oracle(flags):
+    eng, orc = Engine(max_entities=4, max_depth=9, flags=flags), OracleWorld()
     app_e, tf, vel, bad_e = _app(eng, native_resource=False)
     app_o, _, _, bad_o = _app(orc, native_resource=True)
     cs_e, cs_o = [], []
+    launches_per_tick = set()
     for _ in range(120):
+        l0 = eng.launch_count()
         app_e.update(); app_o.update()
+        launches_per_tick.add(eng.launch_count() - l0)
         cs_e += app_e.last_checksums; cs_o += app_o.last_checksums
     assert not bad_e and not bad_o                     # SyncTest self-consistent on both
     assert cs_e == cs_o and len(cs_e) > 500            # FrameCount part ^ entity part: bit-identical
@@ -73,7 +77,9 @@ def test_box_game_synctest_c1_gpu_vs_oracle():
     assert np.all(np.abs(t[:, [0, 2]]) <= 2.4 + 1e-6)   # constrained to the plane
     v = eng.read_component(vel, 0, 2).view(np.float32)
     assert np.all(np.linalg.norm(v, axis=1) <= 3.0 + 1e-5) and np.any(v != 0)
-    assert not eng.last_path_fused()                    # box_game has no fused bundle: stepwise path
+    # default: the generic one-launch program (move_cube_system + snapshots + checksums of a whole tick in ONE launch)
+    assert eng.last_path_fused() == (flags == 0)
+    assert (launches_per_tick <= {0, 1}) == (flags == 0)
 
 
 def test_box_game_eight_players_every_handle_reaches_move_cube_system():

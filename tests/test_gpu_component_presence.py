@@ -15,10 +15,10 @@ NOSESS = (capi.BGR_SESSION_NONE, 0, 0, 0)
 OPT = capi.BGR_STRATEGY_OPTIONAL
 
 
-def _pair(n, depth=8):
+def _pair(n, depth=8, flags=0):
     """Score (optional, checksummed, +1 per frame), Health (optional, satsub-despawn), Tag (always present, checksummed)."""
     worlds, cols = [], None
-    for w in (Engine(max_entities=n + 8, max_depth=depth), OracleWorld()):
+    for w in (Engine(max_entities=n + 8, max_depth=depth, flags=flags), OracleWorld()):
         score = w.rollback_component("Score", 4, capi.BGR_STRATEGY_COPY | OPT)
         health = w.rollback_component("Health", 4, capi.BGR_STRATEGY_CLONE | OPT)
         tag = w.rollback_component("Tag", 12, capi.BGR_STRATEGY_COPY)
@@ -48,18 +48,22 @@ def _same(eng, orc, cols, n):
     assert np.array_equal(alive_e, orc.read_alive(0, n).astype(bool))
 
 
-def test_optional_columns_take_the_generic_path_and_match_the_oracle():
+@pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])
+def test_optional_columns_take_the_generic_path_and_match_the_oracle(flags):
+    """flags = 0: the generic ONE-launch program (generic_program.cuh); FORCE_STEPWISE: one launch per request and system."""
     n = 1300  # three tiles, the last one partial
-    eng, orc, cols = _pair(n)
+    eng, orc, cols = _pair(n, flags=flags)
     score, health, tag = cols
     both = lambda f, *a: [getattr(w, f)(*a) for w in (eng, orc)]
     rows = [0, 1, 511, 512, 513, 1023, 1024, 1299]
     for r in rows[::2]:
         both("remove_component", score, r)
     both("remove_component", health, 512)
+    l0 = eng.launch_count()
     a, b = both("handle_requests", NOSESS, [Request(SAVE, 0), Request(ADVANCE, 0, [0]), Request(SAVE, 1), Request(ADVANCE, 0, [0])])
     assert a == b and len(a) == 2
-    assert not eng.last_path_fused()
+    assert eng.last_path_fused() == (flags == 0)
+    assert (eng.launch_count() - l0 == 1) == (flags == 0)
     _same(eng, orc, cols, n)
     # change presence after the snapshots: every arm of the four-way match is hit by the Load below
     for r in rows[1::2]:
@@ -78,12 +82,13 @@ def test_optional_columns_take_the_generic_path_and_match_the_oracle():
     assert np.array_equal(vals[ho.astype(bool)], vo[ho.astype(bool)])
 
 
-def test_synctest_shaped_run_with_presence_changes_between_ticks():
+@pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])
+def test_synctest_shaped_run_with_presence_changes_between_ticks(flags):
     """Load(f-d), d x (Advance, Save) every tick, with removals / insertions applied between ticks (a system outside
     GgrsSchedule): rollbacks undo them for the resimulated frames exactly as in the oracle; entities also die (Health)."""
     n, d = 700, 4
     SESS = (capi.BGR_SESSION_SYNCTEST, 8, d, 0)  # max_prediction 8: the ring keeps 8 frames, confirmed = frame - d
-    eng, orc, cols = _pair(n)
+    eng, orc, cols = _pair(n, flags=flags)
     score, health, tag = cols
     both = lambda f, *a: [getattr(w, f)(*a) for w in (eng, orc)]
     rng = np.random.default_rng(11)
@@ -95,8 +100,10 @@ def test_synctest_shaped_run_with_presence_changes_between_ticks():
             for k in range(d):
                 reqs += [Request(ADVANCE, 0, [0]), Request(SAVE, frame - d + k + 1)] if k < d - 1 else [Request(ADVANCE, 0, [0])]
         reqs += [Request(SAVE, frame), Request(ADVANCE, 0, [0])]
+        l0 = eng.launch_count()
         a, b = both("handle_requests", SESS, reqs)
         assert a == b, f"tick {tick}"
+        assert (eng.launch_count() - l0 == 1) == (flags == 0)     # the whole request vector is ONE launch on the default path
         frame += 1
         alive = orc.read_alive(0, n).astype(bool)
         for r in rng.choice(np.flatnonzero(alive), 5, replace=False):

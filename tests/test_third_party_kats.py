@@ -134,9 +134,10 @@ def test_duration_as_secs_f32_vectors(oracle_lib):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("flags", [capi.BGR_CFG_FORCE_STEPWISE])
+@pytest.mark.parametrize("flags", [capi.BGR_CFG_FORCE_STEPWISE, 0])
 def test_gpu_generic_hash_kernels_reproduce_the_buffer_form_vectors(flags):
-    """The CUDA byte-range hashers (k_image_tma / k_checksum_column, generic `len`) on one entity per length:
+    """The CUDA byte-range hashers (stepwise: k_image_tma; default: k_generic_program's hash_row_range, word-aligned
+    and byte-wise arms) on one entity per length:
     checksum = entity_part(1, 1) ^ seahash(seahash(order 0 ‖ custom)) with custom = the buffer-form vector."""
     from bevy_ggrs_b200.engine import Engine
     from bevy_ggrs_b200.session import SAVE, Request
