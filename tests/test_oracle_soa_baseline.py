@@ -36,3 +36,22 @@ def test_soa_bar_matches_faithful_restatement_synctest_and_p2p():
         assert np.array_equal(salive.astype(bool), m)
         assert np.array_equal(stf.view(np.uint8).reshape(n, 40)[m], otf[m])
         soa.close(); orc.close()
+
+
+def test_soa_bar_matches_faithful_restatement_at_100k_entities():
+    """The size at which tests/test_gpu_baseline_shapes.py starts trusting the SoA bar as a second oracle (C5, 10M):
+    100k entities, the headline window d = 8, entities dying inside the rollback window, every thread count path."""
+    n, d = 100_000, 8
+    tf, vel, ttl = synth_particles(n, 0x5A, 6, 25)
+    orc = OracleWorld(save_threads=4)
+    cols = register_particles(orc)
+    populate(orc, cols, tf, vel, ttl)
+    soa = SoaWorld(tf, vel, ttl, depth=d + 1, threads=7)        # a thread count that does not divide the rows
+    h = _drive(SyncTestSession(2, d, d + 1, input_delay=2), [orc, soa], d + 5)
+    assert h[0] == h[1] and len(h[0]) > 3 * d
+    stf, svel, sttl, salive = soa.columns()
+    m = orc.read_alive(0, n).astype(bool)
+    assert 0 < m.sum() < n and np.array_equal(salive.astype(bool), m)
+    for c, got in zip(cols, (stf.view(np.uint8).reshape(n, 40), svel.view(np.uint8).reshape(n, 12), sttl.view(np.uint8).reshape(n, 8))):
+        assert np.array_equal(got[m], orc.read_component(c, 0, n)[m])
+    soa.close(); orc.close()
