@@ -783,12 +783,53 @@ def run_cpu_soa_sample(n, d, maxp, rollback_ticks=5):
             "seconds_per_tick": total_ns * 1e-9 / rollback_ticks}
 
 
+def try_real_reference(n, d, ticks, seed):
+    """where a Rust toolchain and a bevy_ggrs checkout exist (probed at run time — neither does in
+    this image nor on the GPU box), build oracle/ref_harness against the UNMODIFIED reference crate and time the real
+    Bevy SyncTest path.  Returns the harness' timing dict or None."""
+    import shutil
+    import tempfile
+    ref = os.environ.get("BEVY_GGRS_PATH", "/root/reference")
+    if not shutil.which("cargo") or not os.path.exists(os.path.join(ref, "Cargo.toml")):
+        return None
+    try:
+        tmp = tempfile.mkdtemp()
+        shutil.copytree(os.path.join(ROOT, "oracle", "ref_harness"), os.path.join(tmp, "harness"))
+        man = os.path.join(tmp, "harness", "Cargo.toml")
+        open(man, "w").write(open(man).read().replace('path = "../../../reference"', f'path = "{ref}"'))
+        subprocess.run([sys.executable, os.path.join(ROOT, "tests", "golden", "gen_reference_inputs.py"),
+                        os.path.join(tmp, "p.bin"), str(n), hex(seed), str(300 + d + 100000), str(300 + d + 100000)], check=True)
+        r = subprocess.run(["cargo", "run", "--release", "--quiet", "--manifest-path", man, "--",
+                            os.path.join(tmp, "p.bin"), str(n), str(d), str(ticks)], capture_output=True, text=True, timeout=1500)
+        if r.returncode != 0:
+            return None
+        return json.loads(r.stdout)["timing"]
+    except Exception:
+        return None
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     n, d, maxp = WORKLOADS[args.workload]
     K, W = args.steps, args.warmup
+    real = try_real_reference(min(n, 200_000), d, d + 2 + K + W, SEED) if d > 0 else None
+    if real:  # the unmodified crate ran here: report it (scaled linearly to the metric's entity count — flatters the CPU)
+        e = min(n, 200_000)
+        v = real["rollback_frames_per_s"] * (e / n)
+        line = {"impl": "reference", "metric": "rollback frames/sec at 1M entities x 8-frame window (SyncTest: 1 Load + 8 Save+checksum + 9 Advance per tick)",
+                "value": v, "unit": "rollback frames/s", "n_gpus": args.gpus, "steps": K, "warmup": W,
+                "ms_per_step": real["seconds"] / max(1, real["ticks"]) * 1e3 * (n / e), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "u64 (seahash) + f32 + bytes", "data": "synthetic (same generator and seed as the GPU arm)",
+                "config": {"workload": args.workload, "entities_per_gpu": n, "check_distance": d, "max_prediction": maxp,
+                           "note": f"the UNMODIFIED bevy_ggrs crate through oracle/ref_harness (headless Bevy app), {e} entities "
+                                   f"scaled by {e}/{n}"},
+                "cpu_baseline": {"value": v, "unit": "rollback frames/s", "cores": 1, "kind": "reference",
+                                 "sample": f"{real['ticks']} SyncTest ticks at {e} entities of the real crate"},
+                "e2e": {"value": v, "unit": "rollback frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return
     # bound the whole run to a few minutes: the port needs ~2.6 s per 1M-entity rollback tick with 8 threads and
     # about linear time in the entity count (super-linear in reality — hash maps fall out of cache — so a smaller
     # sample flatters the CPU, never the GPU); d+1 plain ticks fill the ring before the first rollback tick

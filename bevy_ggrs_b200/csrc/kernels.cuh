@@ -127,6 +127,10 @@ struct ProgramParams {
     // MODE 2 (per-entity presence, BGR_STRATEGY_OPTIONAL): absent bits (of the row's mask byte) that take a row out of
     // update_particles' query (Transform | Velocity), despawn_particles' (Ttl) and the two checksum queries
     uint32_t need_tv, need_l, need_t, need_v;
+    // A grid that starts on an idle GPU has every block in the same phase of the same op (all load, then all hash, then
+    // all store): HBM idles while the ALUs work and vice versa until latency noise has dephased them.  Delaying the
+    // second / third resident block of every SM by a fraction of one frame's time starts them out of phase.
+    uint32_t stagger_ns, stagger_div;
     PassiveRun runs[kMaxRuns];
     uint16_t passive[kMaxPassive];
     uint32_t passive_template[kMaxPassive];   // value of each passive word in a freshly spawned row (Transform::default())
@@ -303,6 +307,10 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     // ... while this grid touches no global memory before the previous grid has completed and flushed
     const bool tile_wait = (p.flags & PF_TILE_WAIT) != 0, tile_signal = (p.flags & PF_TILE_SIGNAL) != 0;
     if (!tile_wait) asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (p.stagger_ns) {
+        const unsigned long long until = globaltimer_ns() + (unsigned long long)(blockIdx.x / p.stagger_div) * p.stagger_ns;
+        while (globaltimer_ns() < until) __nanosleep(64);
+    }
 
     const uint32_t i0 = tid * VEC;  // first row of this thread inside the tile
     // Dynamic tile hand-off WITHOUT a block barrier: at the top of a tile thread 0 claims the block's NEXT tile

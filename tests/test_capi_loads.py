@@ -80,3 +80,59 @@ def test_rust_ffi_source_declares_every_engine_symbol():
         body = rs[rs.index("pub struct " + struct):]
         body = body[:body.index("}")]
         assert re.findall(r"pub (\w+):", body) == fields
+
+
+def test_rust_ffi_repr_c_structs_have_the_c_layout():
+    """Without rustc the -sys crate cannot be compiled, but its #[repr(C)] structs can still be checked: parse every
+    struct, lay it out with the C rules (natural alignment) and compare field order, offsets and total size with the
+    ctypes mirror of the header (capi.py) — which test_struct_layouts_match_the_header pins to the header's sizes."""
+    rs = open(os.path.join(ROOT, "rust_shim", "bevy_ggrs_b200_sys", "src", "lib.rs")).read()
+    consts = {k: int(v, 0) for k, v in re.findall(r"pub const (\w+): \w+ = (0x[0-9a-fA-F]+|\d+);", rs)}
+    prim = {"u8": 1, "i8": 1, "u16": 2, "i16": 2, "u32": 4, "i32": 4, "f32": 4, "u64": 8, "i64": 8, "usize": 8,
+            "*mut c_void": 8, "*const c_void": 8}
+
+    def size_align(ty):
+        ty = ty.strip()
+        m = re.fullmatch(r"\[(\w+); (\w+)\]", ty)
+        if m:
+            n = consts[m.group(2)] if not m.group(2).isdigit() else int(m.group(2))
+            return prim[m.group(1)] * n, prim[m.group(1)]
+        return prim[ty], prim[ty]
+
+    mirrors = {"bgr_request": capi.bgr_request, "bgr_session_info": capi.bgr_session_info, "bgr_checksum": capi.bgr_checksum,
+               "bgr_partial": capi.bgr_partial, "bgr_config": capi.bgr_config}
+    found = 0
+    for m in re.finditer(r"#\[repr\(C\)\]\s*(?:#\[derive\([^)]*\)\]\s*)?pub struct (\w+) \{(.*?)\}", rs, re.S):
+        name, body = m.group(1), m.group(2)
+        fields = re.findall(r"pub (\w+): ([^,\n]+),", body)
+        off, max_align, layout = 0, 1, []
+        for fname, ty in fields:
+            sz, al = size_align(ty)
+            off = (off + al - 1) // al * al
+            layout.append((fname, off, sz))
+            off += sz
+            max_align = max(max_align, al)
+        total = (off + max_align - 1) // max_align * max_align
+        cst = mirrors[name]
+        assert [f for f, _, _ in layout] == [f for f, _ in cst._fields_], name
+        for fname, o, sz in layout:
+            assert getattr(cst, fname).offset == o and getattr(cst, fname).size == sz, (name, fname)
+        assert total == C.sizeof(cst), name
+        found += 1
+    assert found == len(mirrors)
+    assert consts["BGR_MAX_PLAYERS"] == capi.BGR_MAX_PLAYERS and consts["BGR_MAX_REQUESTS"] == capi.BGR_MAX_REQUESTS
+    assert consts["BGR_MAX_CHECKSUM_COLUMNS"] == capi.BGR_MAX_CHECKSUM_COLUMNS
+
+
+def test_rust_shim_keeps_the_reference_api_names():
+    """The drop-in crate exposes the reference's RollbackApp / GgrsPlugin names (rollback_app.rs:31-133, lib.rs:198-224),
+    not renamed `_b200` variants."""
+    rs = open(os.path.join(ROOT, "rust_shim", "bevy_ggrs_b200", "src", "lib.rs")).read()
+    for name in ("rollback_component_with_copy", "rollback_component_with_clone", "checksum_component_with_hash",
+                 "checksum_component", "rollback_resource_with_copy", "rollback_resource_with_clone", "checksum_resource_with_hash"):
+        assert re.search(r"fn %s<" % name, rs), name
+    assert "pub struct GgrsPlugin<C: Config>" in rs and "pub trait RollbackApp" in rs
+    assert "_b200::<" not in rs and "fn handle_requests<" in rs and "fn run_ggrs_schedules<" in rs
+    assert "On<Add, Rollback>" in rs and "bgr_spawn" in rs          # Rollback on_add -> engine row (rollback.rs:40-54)
+    for item in ("Rollback", "Session", "GgrsSchedule", "ReadInputs", "LocalInputs", "PlayerInputs", "SyncTestMismatch"):
+        assert re.search(r"pub use bevy_ggrs::\{[^}]*\b%s\b" % item, rs, re.S), item
