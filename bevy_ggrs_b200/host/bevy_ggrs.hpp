@@ -52,10 +52,14 @@ struct SyncTestMismatch { ggrs::Frame current_frame; std::vector<ggrs::Frame> mi
 template <class Input = uint8_t> struct GgrsConfig { using input_type = Input; };
 template <class Config> struct GgrsPlugin {};
 
-struct Session {  // lib.rs:79-86 (SyncTest is the variant the tests and the bench drive)
-    enum Kind { SyncTestKind } kind = SyncTestKind;
+struct Session {  // lib.rs:79-86: enum Session<T> { SyncTest(..), P2P(..), Spectator(..) }
+    enum Kind { SyncTestKind, P2PKind, SpectatorKind } kind = SyncTestKind;
     std::shared_ptr<ggrs::SyncTestSession> synctest;
-    static Session SyncTest(ggrs::SyncTestSession s) { return Session{SyncTestKind, std::make_shared<ggrs::SyncTestSession>(std::move(s))}; }
+    std::shared_ptr<ggrs::P2PTraceSession> p2p;
+    std::shared_ptr<ggrs::SpectatorTraceSession> spectator;
+    static Session SyncTest(ggrs::SyncTestSession s) { Session r; r.kind = SyncTestKind; r.synctest = std::make_shared<ggrs::SyncTestSession>(std::move(s)); return r; }
+    static Session P2P(ggrs::P2PTraceSession s) { Session r; r.kind = P2PKind; r.p2p = std::make_shared<ggrs::P2PTraceSession>(std::move(s)); return r; }
+    static Session Spectator(ggrs::SpectatorTraceSession s) { Session r; r.kind = SpectatorKind; r.spectator = std::make_shared<ggrs::SpectatorTraceSession>(std::move(s)); return r; }
 };
 
 // a compiled-in GgrsSchedule system: id + bound columns + scalar parameters
@@ -90,6 +94,7 @@ public:
     template <class C> App& add_plugins(GgrsPlugin<C>) { return *this; }
     App& insert_resource(RollbackFrameRate r) { cfg_.fps = uint32_t(r.fps); return *this; }
     App& insert_resource(Session s) { session_ = std::move(s); return *this; }
+    App& remove_session() { session_.reset(); return *this; }  // world.remove_resource::<Session<T>>()
     App& insert_resource(LocalInputs li) { local_inputs_ = std::move(li); return *this; }
     App& add_systems(ReadInputs, std::function<void(App&)> f) { read_inputs_.push_back(std::move(f)); return *this; }
     App& add_systems(Startup, std::function<void(App&)> f) { startup_.push_back(std::move(f)); return *this; }
@@ -181,14 +186,27 @@ public:
         first_update_ = false;
         const uint64_t fps_delta = run_slow_ ? 1000000000ull * 11 / (uint64_t(cfg_.fps) * 10) : 1000000000ull / cfg_.fps;
         accumulator_ns_ += delta;
+        if (session_ && session_->kind == Session::P2PKind) session_->p2p->poll_remote_clients();             // :43-53
+        if (session_ && session_->kind == Session::SpectatorKind) session_->spectator->poll_remote_clients();
         while (accumulator_ns_ >= fps_delta) {
             accumulator_ns_ -= fps_delta;
-            if (!session_) { accumulator_ns_ = 0; run_slow_ = false; return; }
-            run_synctest(*session_->synctest);
+            if (!session_) {  // :70-79 "No session has been started yet, reset time data and snapshots"
+                accumulator_ns_ = 0; run_slow_ = false;
+                local_players_.handles.clear();
+                check(bgr_reset_session(engine_));  // RollbackFrameCount(0), ConfirmedFrameCount(-1), MaxPredictionWindow(8)
+                return;
+            }
+            tick();
         }
     }
     // exactly one GGRS tick (benches)
-    void step() { finish(); run_synctest(*session_->synctest); }
+    void step() { finish(); tick(); }
+    uint32_t max_prediction_window() { uint32_t v = 0; check(bgr_max_prediction_window(engine_, &v)); return v; }
+    std::vector<int32_t> snapshot_frames() {
+        int32_t f[128]; uint32_t n = 0;
+        check(bgr_snapshot_frames(engine_, f, 128, &n));
+        return std::vector<int32_t>(f, f + std::min<uint32_t>(n, 128));
+    }
 
 private:
     template <class T> App& register_component(uint32_t strategy) {
@@ -210,6 +228,38 @@ private:
         for (auto& f : startup_) f(*this);
     }
 
+    void tick() {  // :59-69: depending on the session type, doing a single update looks a bit different
+        switch (session_->kind) {
+        case Session::SyncTestKind: run_synctest(*session_->synctest); break;
+        case Session::P2PKind: run_slow_ = session_->p2p->frames_ahead() > 0; run_p2p(*session_->p2p); break;
+        case Session::SpectatorKind: run_spectator(*session_->spectator); break;
+        }
+    }
+
+    // run_p2p (schedule_systems.rs:137-168)
+    void run_p2p(ggrs::P2PTraceSession& sess) {
+        local_players_.handles = sess.local_player_handles();
+        if (sess.current_state() != ggrs::SessionState::Running) return;
+        local_inputs_.reset();
+        for (auto& f : read_inputs_) f(*this);
+        if (!local_inputs_)
+            throw Panic(BGR_ERR_MISSING_RESOURCE, "No local player inputs found. Did you insert systems into the ReadInputs schedule?");
+        for (auto& kv : local_inputs_->inputs) sess.add_local_input(kv.first, kv.second);
+        const auto requests = sess.advance_frame();
+        // the numbers handle_requests reads from a P2P session before every request (:203-206)
+        bgr_session_info info{BGR_SESSION_P2P, uint32_t(sess.max_prediction()), 0, sess.confirmed_frame()};
+        handle_requests(requests, info, [&](ggrs::Frame f, unsigned __int128 c) { sess.save_cell(f, c); });
+    }
+
+    // run_spectator (schedule_systems.rs:120-135): only AdvanceFrame requests, several per tick when catching up
+    void run_spectator(ggrs::SpectatorTraceSession& sess) {
+        if (sess.current_state() != ggrs::SessionState::Running) return;
+        const auto requests = sess.advance_frame();
+        if (requests.empty()) return;  // PredictionThreshold: "Waiting for input from host."
+        bgr_session_info info{BGR_SESSION_SPECTATOR, 0, 0, 0};  // max_prediction forced to 0, confirmed = current frame (:199-201, :209)
+        handle_requests(requests, info, [](ggrs::Frame, unsigned __int128) {});
+    }
+
     // run_synctest (schedule_systems.rs:85-118)
     void run_synctest(ggrs::SyncTestSession& sess) {
         local_players_.handles.clear();
@@ -221,16 +271,18 @@ private:
         for (auto& kv : local_inputs_->inputs) sess.add_local_input(kv.first, kv.second);
         std::vector<ggrs::GgrsRequest> requests;
         ggrs::MismatchedChecksum err;
-        if (sess.advance_frame(requests, err)) handle_requests(requests, sess);
-        else {  // :104-115
+        if (sess.advance_frame(requests, err)) {
+            bgr_session_info info{BGR_SESSION_SYNCTEST, uint32_t(sess.max_prediction()), uint32_t(sess.check_distance()), 0};
+            handle_requests(requests, info, [&](ggrs::Frame f, unsigned __int128 c) { sess.save_cell(f, c); });
+        } else {  // :104-115
             SyncTestMismatch ev{err.current_frame, err.mismatched_frames};
             for (auto& o : observers_) o(ev);
         }
     }
 
     // handle_requests (schedule_systems.rs:170-289): ONE C-ABI call for the whole vector
-    void handle_requests(const std::vector<ggrs::GgrsRequest>& requests, ggrs::SyncTestSession& sess) {
-        bgr_session_info info{BGR_SESSION_SYNCTEST, uint32_t(sess.max_prediction()), uint32_t(sess.check_distance()), 0};
+    void handle_requests(const std::vector<ggrs::GgrsRequest>& requests, const bgr_session_info& info,
+                         const std::function<void(ggrs::Frame, unsigned __int128)>& save_cell) {
         std::vector<bgr_request> reqs(requests.size());
         for (size_t i = 0; i < requests.size(); ++i) {
             bgr_request& q = reqs[i];
@@ -249,7 +301,7 @@ private:
         last_checksums_.resize(n);
         if (!resources_.empty()) handle_resource_requests(requests);
         for (auto& cs : last_checksums_)  // cell.save(frame, None, checksum) (:231-236)
-            sess.save_cell(cs.frame, (static_cast<unsigned __int128>(cs.hi) << 64) | cs.lo);
+            save_cell(cs.frame, (static_cast<unsigned __int128>(cs.hi) << 64) | cs.lo);
     }
 
     // host-side half of handle_requests for resources: the same request vector replayed on a few bytes

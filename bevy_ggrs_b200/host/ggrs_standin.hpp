@@ -6,6 +6,7 @@
 // requests of ggrs 0.11 `SyncTestSession::advance_frame` + `adjust_gamestate`, and the checksum
 // comparison that yields `GgrsError::MismatchedChecksum` (-> SyncTestMismatch, lib.rs:131-137).
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <map>
 #include <optional>
@@ -106,6 +107,98 @@ private:
     std::map<PlayerHandle, uint8_t> local_;
     std::map<Frame, std::optional<unsigned __int128>> history_;
     std::vector<std::optional<std::pair<Frame, std::optional<unsigned __int128>>>> cells_;
+};
+
+// ---- trace-driven stand-ins for the two networked session kinds --------------------------------------------------
+// handle_requests treats the three kinds differently only through the numbers it reads from the session per request
+// (schedule_systems.rs:195-220): P2P -> (max_prediction, confirmed_frame), Spectator -> max_prediction 0 and
+// confirmed = current frame.  The sockets, input exchange and prediction of ggrs stay out of scope; what is restated
+// is the SHAPE of the request vectors those sessions emit, driven by a script instead of a remote peer:
+//   P2P        per tick a rollback depth L (0 = the remote input arrived in time): [Load(f-L), (Adv, Save) x (L-1), Adv,] Save(f), Adv
+//              confirmed_frame() = the last frame for which every "remote" input has arrived (scripted lag)
+//   Spectator  per tick k >= 0 confirmed frames received from the host: Adv x k (k > 1 when catching up), never Save / Load
+enum class SessionState { Synchronizing, Running };
+
+class P2PTraceSession {
+public:
+    P2PTraceSession(size_t num_players, size_t max_prediction, std::vector<int> rollback_depths, int confirm_lag = 2, size_t input_delay = 0)
+        : num_players_(num_players), max_prediction_(max_prediction), depths_(std::move(rollback_depths)), confirm_lag_(confirm_lag),
+          input_delay_(input_delay), queues_(num_players) {}
+    size_t num_players() const { return num_players_; }
+    size_t max_prediction() const { return max_prediction_; }
+    std::vector<PlayerHandle> local_player_handles() const { return {0}; }
+    SessionState current_state() const { return SessionState::Running; }
+    Frame current_frame() const { return current_frame_; }
+    Frame confirmed_frame() const { return current_frame_ - Frame(confirm_lag_) < 0 ? -1 : current_frame_ - Frame(confirm_lag_); }
+    int frames_ahead() const { return 0; }
+    void poll_remote_clients() {}
+    void add_local_input(PlayerHandle handle, uint8_t input) { local_[handle] = input; }
+    void save_cell(Frame, std::optional<unsigned __int128>) {}
+    std::vector<GgrsRequest> advance_frame() {
+        std::vector<GgrsRequest> requests;
+        int depth = tick_ < depths_.size() ? depths_[tick_] : 0;
+        ++tick_;
+        depth = std::min<int>({depth, int(current_frame_), int(max_prediction_), confirm_lag_});  // ggrs never rolls back past a confirmed frame
+        if (depth > 0) {
+            current_frame_ -= depth;
+            requests.push_back({GgrsRequest::LoadGameState, current_frame_, {}});
+            for (int i = 0; i < depth; ++i) {
+                if (i > 0) requests.push_back({GgrsRequest::SaveGameState, current_frame_, {}});
+                requests.push_back(advance_request(InputStatus::Confirmed));
+                ++current_frame_;
+            }
+        }
+        for (auto& kv : local_) queues_[kv.first][current_frame_ + Frame(input_delay_)] = kv.second;
+        local_.clear();
+        requests.push_back({GgrsRequest::SaveGameState, current_frame_, {}});
+        requests.push_back(advance_request(InputStatus::Predicted));
+        ++current_frame_;
+        return requests;
+    }
+
+private:
+    GgrsRequest advance_request(InputStatus remote) const {
+        GgrsRequest r{GgrsRequest::AdvanceFrame, 0, {}};
+        for (size_t p = 0; p < num_players_; ++p) {
+            auto it = queues_[p].find(current_frame_);
+            r.inputs.emplace_back(it == queues_[p].end() ? uint8_t(0) : it->second, p == 0 ? InputStatus::Confirmed : remote);
+        }
+        return r;
+    }
+    size_t num_players_, max_prediction_;
+    std::vector<int> depths_;
+    int confirm_lag_;
+    size_t input_delay_, tick_ = 0;
+    Frame current_frame_ = 0;
+    std::vector<std::map<Frame, uint8_t>> queues_;
+    std::map<PlayerHandle, uint8_t> local_;
+};
+
+class SpectatorTraceSession {
+public:
+    SpectatorTraceSession(size_t num_players, std::vector<int> frames_per_tick) : num_players_(num_players), script_(std::move(frames_per_tick)) {}
+    size_t num_players() const { return num_players_; }
+    SessionState current_state() const { return SessionState::Running; }
+    Frame current_frame() const { return current_frame_; }
+    void poll_remote_clients() {}
+    // Ok(requests); an empty vector models GgrsError::PredictionThreshold ("Waiting for input from host")
+    std::vector<GgrsRequest> advance_frame() {
+        std::vector<GgrsRequest> requests;
+        const int k = tick_ < script_.size() ? script_[tick_] : 1;
+        ++tick_;
+        for (int i = 0; i < k; ++i) {
+            GgrsRequest r{GgrsRequest::AdvanceFrame, 0, {}};
+            for (size_t p = 0; p < num_players_; ++p) r.inputs.emplace_back(uint8_t((current_frame_ + Frame(p)) & 3), InputStatus::Confirmed);
+            requests.push_back(r);
+            ++current_frame_;
+        }
+        return requests;
+    }
+
+private:
+    size_t num_players_, tick_ = 0;
+    std::vector<int> script_;
+    Frame current_frame_ = 0;
 };
 
 }  // namespace ggrs

@@ -276,6 +276,74 @@ static void box_game_synctest_c1() {
     EXPECT(moved);
 }
 
+// tests/p2p.rs:268-304 (p2p_confirmed_frame_advances_and_prunes_snapshots), with the trace-driven P2P stand-in instead
+// of two UDP peers: ConfirmedFrameCount follows the session's confirmed_frame, snapshots older than it are pruned, and
+// the rollbacks the "remote" peer causes resimulate to the same state (score == frame, component_rollback.rs:54-64).
+static void p2p_confirmed_frame_advances_and_prunes_snapshots() {
+    std::printf("p2p_confirmed_frame_advances_and_prunes_snapshots\n");
+    App app(16, 8);
+    std::vector<int> depths;
+    for (int t = 0; t < 60; ++t) depths.push_back((t * 7 + 3) % 5 == 0 ? 0 : (t * 5 + 1) % 4);  // 0..3 frames of misprediction
+    app.insert_resource(Session::P2P(ggrs::P2PTraceSession(2, 8, depths, /*confirm_lag=*/3)))
+        .add_plugins(GgrsPlugin<GgrsConfig<uint8_t>>{})
+        .add_systems(ReadInputs{}, input_system);
+    app.rollback_component_with_copy<Score>().checksum_component_with_hash<Score>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_U32_ADD, {0}, {0, 1}});
+    app.add_systems(Startup{}, [](App& a) { a.write<Score>(a.spawn(1), {Score{0}}); });
+    for (int i = 0; i < 50; ++i) app.update();
+    const int32_t confirmed = app.confirmed_frame_count(), frame = app.rollback_frame_count();
+    EXPECT(confirmed > 0);                                  // advances once the session confirms frames
+    EXPECT(frame == 49 && confirmed == frame - 3);
+    EXPECT(!app.peek<Score>(0, 0, 1).has_value());          // the frame-0 snapshot was pruned (confirm, mod.rs:182-199)
+    const auto frames = app.snapshot_frames();
+    EXPECT(!frames.empty() && frames.size() <= 8);
+    for (int32_t f : frames) EXPECT(f >= confirmed);        // nothing older than the confirmed frame survives
+    EXPECT(app.read<Score>(0, 1)[0].v == uint32_t(frame));  // every rollback resimulated to the same state
+    EXPECT(app.local_players().handles.size() == 1);        // local_player_handles(), not 0..num_players
+    EXPECT(app.max_prediction_window() == 8);
+}
+
+// run_spectator (schedule_systems.rs:120-135) + the spectator arm of handle_requests (:199-201, :209): AdvanceFrame
+// requests only — several per tick when catching up — MaxPredictionWindow 0, ConfirmedFrameCount = the frame in hand.
+static void spectator_session_only_advances() {
+    std::printf("spectator_session_only_advances\n");
+    App app(16, 8);
+    const std::vector<int> script = {1, 1, 3, 0, 2, 1, 0, 0, 4, 1};
+    int total = 0;
+    for (int k : script) total += k;
+    app.insert_resource(Session::Spectator(ggrs::SpectatorTraceSession(2, script)))
+        .add_plugins(GgrsPlugin<GgrsConfig<uint8_t>>{})
+        .add_systems(ReadInputs{}, [](App&) { std::printf("  FAILED: a spectator never reads local inputs\n"); ++g_failed; });
+    app.rollback_component_with_copy<Score>().checksum_component_with_hash<Score>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_U32_ADD, {0}, {0, 1}});
+    app.add_systems(Startup{}, [](App& a) { a.write<Score>(a.spawn(1), {Score{0}}); });
+    for (size_t i = 0; i <= script.size(); ++i) app.update();    // the first update has a zero delta
+    EXPECT(app.rollback_frame_count() == total);
+    EXPECT(app.read<Score>(0, 1)[0].v == uint32_t(total));
+    EXPECT(app.snapshot_frames().empty());                       // no SaveGameState ever reaches a spectator
+    EXPECT(app.max_prediction_window() == 0);
+    EXPECT(app.confirmed_frame_count() == total - 1);            // = RollbackFrameCount when the last request was handled
+    EXPECT(app.last_checksums().empty());
+}
+
+// schedule_systems.rs:70-79: without a session the frame resources are reset
+static void removed_session_resets_frame_resources() {
+    std::printf("removed_session_resets_frame_resources\n");
+    App app(16, 8);
+    base_synctest_app(app, 2);
+    app.rollback_component_with_copy<Score>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_U32_ADD, {0}, {0, 1}});
+    app.add_systems(Startup{}, [](App& a) { a.write<Score>(a.spawn(1), {Score{0}}); });
+    for (int i = 0; i < 12; ++i) app.update();
+    EXPECT(app.rollback_frame_count() == 11 && app.confirmed_frame_count() >= 0);
+    app.remove_session();
+    app.update();
+    EXPECT(app.rollback_frame_count() == 0);
+    EXPECT(app.confirmed_frame_count() == -1);
+    EXPECT(app.max_prediction_window() == 8);
+    EXPECT(app.local_players().handles.empty());
+}
+
 int main(int argc, char** argv) {
     if (argc > 1 && std::string(argv[1]) == "--no-gpu") {
         // the library must refuse loudly (no CPU fallback) when no device is usable
@@ -299,6 +367,9 @@ int main(int argc, char** argv) {
         particles_stress_synctest();
         optional_component_is_reinserted_and_removed_by_rollback();
         box_game_synctest_c1();
+        p2p_confirmed_frame_advances_and_prunes_snapshots();
+        spectator_session_only_advances();
+        removed_session_resets_frame_resources();
     } catch (const std::exception& e) {
         std::printf("unexpected exception: %s\n", e.what());
         return 2;
