@@ -230,6 +230,13 @@ def trace_stats(tr):
 
 
 def run_ours(args):
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        # before torch / NCCL are loaded: the communicator's INIT banner ("... rank r nranks N ...") must stay
+        # reachable — on stderr, see StdoutGuard — so that the rank count of a multi-GPU run can be checked
+        os.environ.setdefault("NCCL_DEBUG", "INFO")
+        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        if os.environ.get("RANK", "0") == "0":
+            print(f"[bench] NCCL_DEBUG={os.environ['NCCL_DEBUG']} NCCL_DEBUG_SUBSYS={os.environ['NCCL_DEBUG_SUBSYS']}", file=sys.stderr, flush=True)
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -249,8 +256,6 @@ def run_ours(args):
     if sharded:
         # the communicator is only the launcher-side plumbing (rendezvous, barriers, max-over-ranks of the timings);
         # its INIT banner stays reachable on stderr so that the rank count can be checked
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         dist.init_process_group("nccl", device_id=dev)
 
     n_total, d, maxp = WORKLOADS[args.workload]
