@@ -102,6 +102,19 @@ uint64_t host_ns() {
     return uint64_t(ts.tv_sec) * 1000000000ULL + uint64_t(ts.tv_nsec);
 }
 
+// The reference's tracing spans as NVTX ranges (no-ops unless a profiler is attached): `HandleRequests` around the
+// whole call (schedule_systems.rs:171) and `SaveWorld` / `LoadWorld` / `AdvanceWorld` per request (:224-253) — around
+// the host half of each request (ring push / rollback, frame resources, GgrsTime) while the vector is compiled, and
+// around each request's kernel launches on the stepwise path.  On the fused paths the device half of all requests is
+// ONE launch, which sits inside the HandleRequests range.
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+inline const char* span_name(uint32_t request_kind) {
+    return request_kind == BGR_REQ_SAVE ? "SaveWorld" : request_kind == BGR_REQ_LOAD ? "LoadWorld" : "AdvanceWorld";
+}
+
 int env_int(const char* name, int dflt) {
     const char* v = std::getenv(name);
     return v && *v ? std::atoi(v) : dflt;
@@ -196,6 +209,7 @@ struct bgr_engine {
     // generic one-launch program (generic_program.cuh): any schema whose tile fits shared memory + the compiled systems
     bool generic_ok = false;
     int generic_bps = 0;            // resident blocks per SM of k_generic_program (occupancy query, cached)
+    int tune_sub = 0;               // 0: 128-row work items for small worlds (auto); 128: always; 512: never
     int tune_stagger_ns = 800;      // start-of-grid phase stagger between the resident blocks of an SM (synchronous launches; measured -1.3 %)
     int tune_generic = 1;
     int tune_bundle = 1;            // 0: never use the specialised particles kernel (A/B tests of the generic program)
@@ -204,7 +218,7 @@ struct bgr_engine {
     int tune_tma = 1;          // stepwise Save/Load through the TMA-staged bulk-copy kernel
     uint32_t tma_stage_tiles = 0;  // one-tile stages of the TMA copy kernel (0: schema too wide for two stages of shared memory)
     unsigned int* d_tma_ticket = nullptr;
-    int occ_cache[3][3][3] = {};
+    int occ_cache[2][3][3][3] = {};
 
     uint8_t* image(uint32_t idx) const { return arena + size_t(idx) * image_bytes; }
     uint32_t image_off256(uint32_t idx) const { return uint32_t((size_t(idx) * image_bytes) >> 8); }
@@ -242,6 +256,7 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
     for (auto& sy : e->systems) n_counter_systems += (sy.id == BGR_SYS_U32_STORE_CALL_COUNT);
     for (uint32_t i = 0; i < n; ++i) {
         const bgr_request& rq = reqs[i];
+        NvtxRange span(span_name(rq.kind));
         // schedule_systems.rs:190-220 — resources recomputed from the session before every request
         const int32_t current_frame = s.frame_count;
         if (sess) {
@@ -369,21 +384,24 @@ int compile_requests(bgr_engine* e, HostState& s, const bgr_session_info* sess, 
 // ---------------------------------------------------------------------------------------------
 // launch: fused bundle kernel
 // ---------------------------------------------------------------------------------------------
-template <int VEC, int MODE, int MINB>
+template <int VEC, int MODE, int MINB, int SUB = int(kTileRows)>
 int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int mi, cudaStream_t stream) {
-    auto kern = k_particles_program<VEC, MODE, MINB>;
-    constexpr int BLOCK = kTileRows / VEC;
+    auto kern = k_particles_program<VEC, MODE, MINB, SUB>;
+    constexpr int BLOCK = SUB / VEC;
+    constexpr uint32_t kSubs = kTileRows / SUB;
+    constexpr int ui = kSubs > 1 ? 1 : 0;
     const size_t smem = (pp.flags & PF_PASSIVE_TMA) ? size_t(2) * pp.passive_bytes : 0;
-    if (e->occ_cache[vi][si][mi] == 0) {
+    if (e->occ_cache[ui][vi][si][mi] == 0) {
         if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int nb = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, BLOCK, smem));
-        e->occ_cache[vi][si][mi] = std::max(1, nb);
+        e->occ_cache[ui][vi][si][mi] = std::max(1, nb);
     }
-    int bps = e->occ_cache[vi][si][mi];
+    int bps = e->occ_cache[ui][vi][si][mi];
     if (e->tune_bps > 0) bps = std::min(e->tune_bps, bps);
-    uint32_t grid = std::max(1u, std::min(pp.n_tiles - pp.tile_begin, uint32_t(e->num_sms * bps)));
+    uint32_t grid = std::max(1u, std::min((pp.n_tiles - pp.tile_begin) * kSubs, uint32_t(e->num_sms * bps)));
     if (e->tune_grid > 0) grid = std::min(grid, uint32_t(e->tune_grid));
+    if (kSubs > 1) grid = std::max(kSubs, grid / kSubs * kSubs);  // the first wave covers whole tiles (per-tile completion counts)
     cudaLaunchConfig_t lc{};
     lc.gridDim = dim3(grid); lc.blockDim = dim3(BLOCK); lc.dynamicSmemBytes = smem; lc.stream = stream;
     cudaLaunchAttribute attr[1];
@@ -430,13 +448,17 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
         pp.spawn_ttl_lo = uint32_t(ttl); pp.spawn_ttl_hi = uint32_t(ttl >> 32);
     }
     if (!pg.has_spawn && simple && e->tune_passive_tma && !e->runs.empty() && 2u * e->passive_bytes <= 96u * 1024u) pp.flags |= PF_PASSIVE_TMA;
+    // small worlds (fewer than three tiles per SM): cut every tile into 128-row work items (kernels.cuh `SUB`)
+    const bool sub_items = e->tune_sub == 128 || (e->tune_sub == 0 && total_tiles < 3u * uint32_t(e->num_sms));
+    if (sub_items && e->tune_vec == 2 && e->n_chains == 1) pp.flags |= PF_SUB_ITEMS;
     const Column& ct = e->cols[e->bt]; const Column& cv = e->cols[e->bv];
     if (ct.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_T; if (ct.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_T; pp.ck_t_slot = uint32_t(ct.ck_slot); }
     if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_V; pp.ck_v_slot = uint32_t(cv.ck_slot); }
     pp.t_off = ct.first_plane * kPlaneBytes; pp.v_off = cv.first_plane * kPlaneBytes;
     pp.l_off = e->cols[e->bl].first_plane * kPlaneBytes; pp.alive_off = e->words * kPlaneBytes;
     pp.need_t = ct.absent; pp.need_v = cv.absent; pp.need_tv = ct.absent | cv.absent; pp.need_l = e->cols[e->bl].absent;
-    pp.n_runs = passive_needed ? uint32_t(e->runs.size()) : 0u; pp.passive_bytes = e->passive_bytes;
+    pp.n_runs = passive_needed ? uint32_t(e->runs.size()) : 0u;
+    pp.passive_bytes = (pp.flags & PF_SUB_ITEMS) ? uint32_t(e->passive.size()) * 128u * 4u : e->passive_bytes;
     for (size_t i = 0; i < e->runs.size(); ++i) pp.runs[i] = e->runs[i];
     pp.n_passive = passive_needed ? uint32_t(e->passive.size()) : 0u;
     for (size_t i = 0; i < e->passive.size(); ++i) {
@@ -507,6 +529,12 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
 int launch_fused_variant(bgr_engine* e, const ProgramParams& pp, cudaStream_t stream) {
     const int v = e->bundle_opt ? 2 : e->tune_vec;
     const bool st = e->bundle_static_ck && !e->bundle_opt;
+    if (pp.flags & PF_SUB_ITEMS) {  // small worlds: 128-row work items, 64-thread blocks, 768 threads per SM
+        constexpr int kSub = 128, kMinbSub = 768 / (kSub / 2);
+        if (e->bundle_opt) return launch_particles<2, 2, kMinbSub, kSub>(e, pp, 1, 2, 1, stream);
+        if (st) return launch_particles<2, 1, kMinbSub, kSub>(e, pp, 1, 1, 1, stream);
+        return launch_particles<2, 0, kMinbSub, kSub>(e, pp, 1, 0, 1, stream);
+    }
     const int mb = e->tune_minb >= 8 ? 2 : (e->tune_minb >= 2 ? 1 : 0);  // launch-bounds tier: 1024 / 768 / unconstrained threads per SM
     if (e->bundle_opt) {  // per-entity presence: one variant (2 rows per thread, 768 threads per SM)
         constexpr int kMidOpt = 768 / int(kTileRows / 2);
@@ -572,6 +600,7 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
     uint8_t* live = e->image(0);
     for (uint32_t i = 0; i < pg.n_ops; ++i) {
         const Op& op = pg.ops[i];
+        NvtxRange span(span_name(op.kind == OP_SAVE ? uint32_t(BGR_REQ_SAVE) : op.kind == OP_LOAD ? uint32_t(BGR_REQ_LOAD) : uint32_t(BGR_REQ_ADVANCE)));
         switch (op.kind) {
         case OP_SAVE: {
             unsigned long long* acc = e->d_accum + size_t(op.save_index) * kAccStride;
@@ -741,11 +770,6 @@ int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
     return BGR_OK;
 }
 
-// the reference's tracing span (schedule_systems.rs:171 `info_span!("ggrs", name = "HandleRequests")`) as an NVTX range
-struct NvtxRange {
-    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
-    ~NvtxRange() { nvtxRangePop(); }
-};
 
 int submit(bgr_engine* e, const bgr_session_info* sess, const bgr_request* reqs, uint32_t n) {
     NvtxRange span("HandleRequests");
@@ -1116,6 +1140,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_grid = env_int("BGR_TUNE_GRID", 0);
     e->tune_tiledep = env_int("BGR_TUNE_TILEDEP", 1);
     e->tune_generic = env_int("BGR_TUNE_GENERIC", 1);
+    e->tune_sub = env_int("BGR_TUNE_SUB", 0);
     e->tune_stagger_ns = env_int("BGR_TUNE_STAGGER_NS", 800);
     e->tune_bundle = env_int("BGR_TUNE_BUNDLE", 1);
     e->n_chains = std::max(1, std::min(int(bgr_engine::kMaxChains), env_int("BGR_TUNE_CHAINS", 1)));

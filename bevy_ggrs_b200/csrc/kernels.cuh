@@ -95,6 +95,7 @@ enum ProgFlags : uint32_t {
     PF_PREFETCH_NEXT = 512u,     // warp 0 pulls the next tile's active planes into L2 while this tile computes
     PF_TILE_SIGNAL = 1024u,      // announce each block's FIRST tile in tile_done[] as soon as its stores are visible, and the
                                  // whole launch in *grid_done: what the next launch's first wave needs to start early
+    PF_SUB_ITEMS = 4096u,        // host: launch the 128-row work-item variant (small worlds)
     PF_TILE_WAIT = 2048u,        // the previous launch on the stream was a PF_TILE_SIGNAL launch: start without waiting for
                                  // its grid (no griddepcontrol.wait) and wait per tile for tile_done[tile] or grid_done >=
                                  // wait_seq instead.  Tile i of tick k+1 only depends on tile i of tick k, so this grid's
@@ -274,9 +275,14 @@ __device__ __forceinline__ void particle_step(uint32_t& tx, uint32_t& ty, uint32
 // byte carries absent bits (BGR_STRATEGY_OPTIONAL), every system and checksum applies the reference's query filter
 // (`Query<(&RollbackId, &T)>`, component_checksum.rs:73-77; `Query<(&mut Transform, &mut Velocity)>`, particles.rs:273)
 // per row, and Save / Load move the mask with the image (= the four-way match of component_snapshot.rs:99-115).
-template <int VEC, int MODE, int MINB>
-__global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(const __grid_constant__ ProgramParams p) {
-    constexpr int BLOCK = kTileRows / VEC;
+// SUB: rows per work item.  SUB == kTileRows: one tile per block iteration (large worlds).  SUB < kTileRows: a tile is cut
+// into kTileRows / SUB row ranges handled by different (smaller) blocks — small worlds: 100k entities are 196 tiles on
+// 148 SMs, so a third of the SMs carried two tiles and set the pace (issue-bound, 17 us); 128-row items spread the
+// same rows as 5-6 items per SM.
+template <int VEC, int MODE, int MINB, int SUB = int(kTileRows)>
+__global__ void __launch_bounds__(SUB / VEC, MINB) k_particles_program(const __grid_constant__ ProgramParams p) {
+    constexpr int BLOCK = SUB / VEC;
+    constexpr uint32_t kSubs = kTileRows / SUB;
     constexpr bool STATIC_CK = MODE == 1;
     constexpr bool OPT = MODE == 2;
     // STATIC_CK: both columns checksummed with the finite assertion (the stress test's registration) —
@@ -296,7 +302,16 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
     // into SM slots as this grid drains (hides launch latency and block ramp-up between back-to-back ticks) ...
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     for (uint32_t i = tid; i < p.n_saves * kAccStride * 2; i += BLOCK) s_acc[i] = 0u;
-    const bool use_tma = (p.flags & PF_PASSIVE_TMA) && p.n_runs > 0;
+    const bool use_tma = (p.flags & PF_PASSIVE_TMA) && (kSubs == 1 ? p.n_runs : p.n_passive) > 0;
+    // the passive planes of one work item as bulk-copy chunks: whole runs of adjacent planes (full tiles), or this
+    // item's row range of every passive plane (sub-tiles); f(offset inside the tile, bytes)
+    auto for_each_passive_chunk = [&](uint32_t sub, auto&& f) {
+        if (kSubs == 1) {
+            for (uint32_t r = 0; r < p.n_runs; ++r) f(p.runs[r].off, p.runs[r].bytes);
+        } else {
+            for (uint32_t k = 0; k < p.n_passive; ++k) f(uint32_t(p.passive[k]) * kPlaneBytes + sub * uint32_t(SUB) * 4u, uint32_t(SUB) * 4u);
+        }
+    };
     if (tid == 0 && use_tma) {
         mbar_init(&s_bar[0], 1);
         mbar_init(&s_bar[1], 1);
@@ -312,7 +327,6 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         while (globaltimer_ns() < until) __nanosleep(64);
     }
 
-    const uint32_t i0 = tid * VEC;  // first row of this thread inside the tile
     // Dynamic tile hand-off WITHOUT a block barrier: at the top of a tile thread 0 claims the block's NEXT tile
     // from a global counter (late binding: one tile ahead, so the tail stays balanced) and publishes it a little
     // later — once the atomic has returned, hidden behind the tile's loads — through a 4-slot ring guarded by
@@ -340,15 +354,18 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         fence_acq_rel_gpu();                      // every thread's stores are visible gpu-wide before its warp arrives
         __syncwarp();
         if (lane == 0) {
-            if (atomicAdd(&p.tile_cnt[t], 1u) == BLOCK / 32 - 1) {  // last warp of the block to announce this tile
+            if (atomicAdd(&p.tile_cnt[t], 1u) == kTileRows / (32 * VEC) - 1) {  // last warp (of all the tile's items) to announce this tile
                 p.tile_cnt[t] = 0u;
                 fence_acq_rel_gpu();
                 st_release_gpu(&p.tile_done[t], p.done_seq);
             }
         }
     };
-    for (uint32_t tile = p.tile_begin + blockIdx.x; tile < p.n_tiles; ++it) {
-        if (dynamic && tid == 0) claimed = p.tile_begin + gridDim.x + atomicAdd(&p.ticket[1], 1u);  // published after the loads below
+    const uint32_t n_items = p.n_tiles * kSubs;
+    for (uint32_t item = p.tile_begin * kSubs + blockIdx.x; item < n_items; ++it) {
+        if (dynamic && tid == 0) claimed = p.tile_begin * kSubs + gridDim.x + atomicAdd(&p.ticket[1], 1u);  // published after the loads below
+        const uint32_t tile = item / kSubs, sub = item % kSubs;
+        const uint32_t i0 = sub * uint32_t(SUB) + tid * VEC;  // first row of this thread inside the tile
         if (tile_wait && tile < p.wait_tiles) {
             // the previous tick's kernel may still be running: this tile's images are complete once it has signalled
             if (lane == 0)
@@ -370,10 +387,10 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
             uint8_t* dst = s_passive + size_t(buf) * p.passive_bytes;
             mbar_arrive_expect_tx(&s_bar[buf], p.passive_bytes);
             uint32_t o = 0;
-            for (uint32_t r = 0; r < p.n_runs; ++r) {
-                tma_load_1d(dst + o, src + p.runs[r].off, p.runs[r].bytes, &s_bar[buf]);
-                o += p.runs[r].bytes;
-            }
+            for_each_passive_chunk(sub, [&](uint32_t off, uint32_t bytes) {
+                tma_load_1d(dst + o, src + off, bytes, &s_bar[buf]);
+                o += bytes;
+            });
         }
 
         // ------------------------------ active words ------------------------------
@@ -423,14 +440,16 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
             // the next tile's first touch is a dependent DRAM read at the top of the tile (20 % of all stall samples in
             // the round-1 profile): pull its active planes (8 word planes + alive = 132 lines) into L2 now
             const uint32_t nxt = __shfl_sync(0xffffffffu, claimed, 0);
-            if (nxt < p.n_tiles) {
-                const uint8_t* img = p.arena + ((p.flags & PF_READ_LIVE) ? size_t(0) : (size_t(p.ops[0].image_off256) << 8)) + size_t(nxt) * p.tile_bytes;
-                for (uint32_t l = lane; l < 8u * (kPlaneBytes / 128u) + kTileRows / 128u; l += 32u) {
-                    const uint32_t plane = l / (kPlaneBytes / 128u), line = l % (kPlaneBytes / 128u);
-                    const size_t off = plane < 3 ? p.t_off + size_t(plane) * kPlaneBytes
-                                     : plane < 6 ? p.v_off + size_t(plane - 3) * kPlaneBytes
-                                     : plane < 8 ? p.l_off + size_t(plane - 6) * kPlaneBytes
-                                                 : size_t(p.alive_off);
+            if (nxt < n_items) {
+                const uint32_t nsub = nxt % kSubs;
+                const uint8_t* img = p.arena + ((p.flags & PF_READ_LIVE) ? size_t(0) : (size_t(p.ops[0].image_off256) << 8)) + size_t(nxt / kSubs) * p.tile_bytes;
+                constexpr uint32_t kLines = uint32_t(SUB) * 4u / 128u, kAliveLines = (uint32_t(SUB) + 127u) / 128u;  // per plane / alive range of one item
+                for (uint32_t l = lane; l < 8u * kLines + kAliveLines; l += 32u) {
+                    const uint32_t plane = l / kLines, line = l % kLines;
+                    const size_t off = plane < 3 ? p.t_off + size_t(plane) * kPlaneBytes + size_t(nsub) * SUB * 4u
+                                     : plane < 6 ? p.v_off + size_t(plane - 3) * kPlaneBytes + size_t(nsub) * SUB * 4u
+                                     : plane < 8 ? p.l_off + size_t(plane - 6) * kPlaneBytes + size_t(nsub) * SUB * 4u
+                                                 : size_t(p.alive_off) + size_t(nsub) * SUB;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(img + off + size_t(line) * 128u));
                 }
             }
@@ -557,12 +576,12 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
                     if (p.ops[i].kind != OP_SAVE || (p.ops[i].flags & (OPF_NO_STORE | OPF_SKIP_PASSIVE))) continue;
                     uint8_t* img = p.arena + (size_t(p.ops[i].image_off256) << 8) + tile_off;
                     uint32_t o = 0;
-                    for (uint32_t r = 0; r < p.n_runs; ++r) { tma_store_1d(img + p.runs[r].off, src + o, p.runs[r].bytes); o += p.runs[r].bytes; }
+                    for_each_passive_chunk(sub, [&](uint32_t off, uint32_t bytes) { tma_store_1d(img + off, src + o, bytes); o += bytes; });
                 }
                 if (p.flags & PF_WRITE_LIVE_PASSIVE) {
                     uint8_t* img = p.arena + tile_off;
                     uint32_t o = 0;
-                    for (uint32_t r = 0; r < p.n_runs; ++r) { tma_store_1d(img + p.runs[r].off, src + o, p.runs[r].bytes); o += p.runs[r].bytes; }
+                    for_each_passive_chunk(sub, [&](uint32_t off, uint32_t bytes) { tma_store_1d(img + off, src + o, bytes); o += bytes; });
                 }
                 tma_commit();
             }
@@ -610,11 +629,11 @@ __global__ void __launch_bounds__(kTileRows / VEC, MINB) k_particles_program(con
         if (dynamic) {
             const uint32_t slot = it % kRing, use = it / kRing;  // entry of iteration it + 1
             mbar_wait(&s_full[slot], use & 1u);
-            tile = s_tile[slot];
+            item = s_tile[slot];
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_empty[slot]);
         } else {
-            tile += gridDim.x;
+            item += gridDim.x;
         }
     }
     if (use_tma && tid == 0) tma_wait_all();  // every bulk store has landed before the results are published

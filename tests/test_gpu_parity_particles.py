@@ -292,3 +292,53 @@ def test_particles_world_on_the_generic_program_matches_oracle(monkeypatch, n, d
     assert r["fused"] and r["launches"] == ticks
     assert r["checksums_equal"] and r["state_equal"] and r["peek_equal"]
     assert r["ring"][0] == r["ring"][1] and r["active"][0] == r["active"][1] < n
+
+
+@pytest.mark.parametrize("sub", ["128", "512"])
+@pytest.mark.parametrize("n,d,spawn", [(700, 3, 0), (20_000, 8, 0), (3000, 6, 40)])
+def test_both_work_item_sizes_match_the_oracle(monkeypatch, sub, n, d, spawn):
+    """BGR_TUNE_SUB forces the fused kernel's work-item size: 128-row items (the small-world default: every tile is cut
+    into four row ranges handled by different 64-thread blocks, passive planes moved as per-plane bulk copies) and
+    whole 512-row tiles (the large-world default) must both match the oracle — despawns, spawns inside the window,
+    snapshots of every frame."""
+    monkeypatch.setenv("BGR_TUNE_SUB", sub)
+    r = run_particles_synctest_pair(n, d, 16, seed=31, ttl_lo=3, ttl_hi=30, peek_check=True, z_fraction=0.25,
+                                    spawn_rate=spawn, spawn_ttl=9, startup_burst=bool(spawn))
+    assert r["fused"] and r["launches"] == 16
+    assert r["checksums_equal"] and r["state_equal"] and r["peek_equal"]
+    assert r["ring"][0] == r["ring"][1] and r["active"][0] == r["active"][1]
+
+
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("sub", ["128", "512"])
+def test_pipelined_overlap_with_both_work_item_sizes(monkeypatch, sub):
+    """Tile dependencies count announcements per TILE: with 128-row items four blocks complete one tile together."""
+    from bevy_ggrs_b200.session import SAVE, SyncTestSession
+    from bevy_ggrs_b200.stress import populate, register_particles, synth_particles
+    from oracle_backend import OracleWorld
+    monkeypatch.setenv("BGR_TUNE_SUB", sub)
+    monkeypatch.setenv("BGR_TUNE_TILEDEP", "2")
+    n, d, maxp, n_ticks = 60_000, 3, 8, 24
+    eng, orc = Engine(max_entities=n, max_depth=maxp), OracleWorld()
+    for w in (eng, orc):
+        cols = register_particles(w)
+        w.build()
+        populate(w, cols, *synth_particles(n, 77, 3, 40))
+    sess = SyncTestSession(2, d, maxp, input_delay=2)
+    got, want, inflight = [], [], 0
+    for t in range(n_ticks):
+        sess.add_local_input(0, 0); sess.add_local_input(1, (1 << 5) if t % 3 == 0 else 0)
+        reqs = sess.advance_frame()
+        for r in reqs:
+            if r.kind == SAVE:
+                sess.save_cell(r.frame, 0)
+        eng.submit_requests(sess.info(), reqs)
+        inflight += 1
+        if inflight == 4:
+            got += eng.collect(); inflight -= 1
+        want += orc.handle_requests(sess.info(), reqs)
+    while inflight:
+        got += eng.collect(); inflight -= 1
+    assert got == want
+    assert compare_state(eng, orc, cols, n)
+    eng.close(); orc.close()
