@@ -9,15 +9,21 @@ One step = one SyncTest tick of the stress-test world at steady state: the reque
 [Load(f-8), Adv, Save, Adv, ..., Save(f), Adv] = 1 LoadGameState + 8 SaveGameState (each with its
 desync checksum) + 9 AdvanceFrame, i.e. 9 rollback frames per step.
 
-    value        device throughput: K ticks enqueued back to back (state resident in HBM), CUDA events
-    e2e          the same metric through the synchronous C-ABI call a user makes
-                 (bgr_handle_requests: host request array in, host checksums out, every tick)
-    roofline     the fused kernel k_particles_program against the measured HBM copy bandwidth
+    e2e          THE HEADLINE: the metric through the synchronous C-ABI call a user makes — one bgr_handle_requests per
+                 tick from a compiled caller (tools/e2e_caller.c), host request array in, host checksums out, every tick
+                 (`e2e_python_caller`: the same loop driven through ctypes)
+    value        device throughput with PIPELINED submits (bgr_submit_requests / bgr_collect, K ticks enqueued back to
+                 back, CUDA events on the engine's stream); explains the kernel, not reachable through the reference's
+                 synchronous contract
+    roofline     the fused kernel against the measured HBM copy bandwidth: pipelined / sync (device trace) / e2e / isolated
+    timeline     device-side [first block start, last block end, published] of consecutive launches in both modes
     cpu_baseline the oracle port (faithful restatement of the reference's data structures) on host cores
 
-N > 1 (torchrun): entity-range shards, one engine per GPU, 1M entities PER GPU (weak scaling);
-the only exchange is an NCCL all_gather of the per-save checksum partials (XOR has no NCCL reduce op).
-value = N x ticks/s x 9 = 1M-entity rollback frames per second summed over the shards.
+N > 1 (torchrun): entity-range shards, one engine per GPU.  --scaling weak (default): the workload's entity count PER
+GPU; --scaling strong: the workload's entity count split over the GPUs (BASELINE C5: 10M total, d=32).  The cross-shard
+checksum fold happens inside the engine (bgr_shard_group_join: result pairs in a shared host segment); torch.distributed /
+NCCL is launcher plumbing only (rendezvous, barriers, max over ranks).  Rank 0 verifies the folded checksums against one
+unsharded engine (`sharded_parity`).
 """
 from __future__ import annotations
 

@@ -209,7 +209,7 @@ struct bgr_engine {
     // generic one-launch program (generic_program.cuh): any schema whose tile fits shared memory + the compiled systems
     bool generic_ok = false;
     int generic_bps = 0;            // resident blocks per SM of k_generic_program (occupancy query, cached)
-    int tune_sub = 0;               // 0: 128-row work items for small worlds (auto); 128: always; 512: never
+    int tune_sub = 0;               // 128: the 128-row work-item variant of the fused kernel (experiment; default: whole tiles)
     int tune_stagger_ns = 800;      // start-of-grid phase stagger between the resident blocks of an SM (synchronous launches; measured -1.3 %)
     int tune_generic = 1;
     int tune_bundle = 1;            // 0: never use the specialised particles kernel (A/B tests of the generic program)
@@ -448,8 +448,11 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
         pp.spawn_ttl_lo = uint32_t(ttl); pp.spawn_ttl_hi = uint32_t(ttl >> 32);
     }
     if (!pg.has_spawn && simple && e->tune_passive_tma && !e->runs.empty() && 2u * e->passive_bytes <= 96u * 1024u) pp.flags |= PF_PASSIVE_TMA;
-    // small worlds (fewer than three tiles per SM): cut every tile into 128-row work items (kernels.cuh `SUB`)
-    const bool sub_items = e->tune_sub == 128 || (e->tune_sub == 0 && total_tiles < 3u * uint32_t(e->num_sms));
+    // Opt-in experiment (BGR_TUNE_SUB=128): cut every tile into 128-row work items handled by 64-thread blocks
+    // (kernels.cuh `SUB`).  Meant to balance small worlds (100k entities = 196 tiles on 148 SMs); measured SLOWER there
+    // (21.2 vs 17.2 us per tick): the better balance is paid for with fewer warps per scheduler on the busy SMs and
+    // per-plane bulk copies, and the tick is issue-latency-bound on the hash, not imbalance-bound.  Kept for A/B runs.
+    const bool sub_items = e->tune_sub == 128;
     if (sub_items && e->tune_vec == 2 && e->n_chains == 1) pp.flags |= PF_SUB_ITEMS;
     const Column& ct = e->cols[e->bt]; const Column& cv = e->cols[e->bv];
     if (ct.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_T; if (ct.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_T; pp.ck_t_slot = uint32_t(ct.ck_slot); }

@@ -455,6 +455,25 @@ __global__ void __launch_bounds__(SUB / VEC, MINB) k_particles_program(const __g
             }
         }
 
+        // ---- passive planes, TMA path: stream them out NOW, while the frames below are computed — they do not depend on any
+        // frame, and issued at the end of the tile (round 1) their completion sat on every tile's (and the grid's) tail ----
+        if (use_tma && tid == 0) {
+            mbar_wait(&s_bar[buf], (it >> 1) & 1u);
+            const uint8_t* src = s_passive + size_t(buf) * p.passive_bytes;
+            for (uint32_t i = 0; i < p.n_ops; ++i) {
+                if (p.ops[i].kind != OP_SAVE || (p.ops[i].flags & (OPF_NO_STORE | OPF_SKIP_PASSIVE))) continue;
+                uint8_t* img = p.arena + (size_t(p.ops[i].image_off256) << 8) + tile_off;
+                uint32_t o = 0;
+                for_each_passive_chunk(sub, [&](uint32_t off, uint32_t bytes) { tma_store_1d(img + off, src + o, bytes); o += bytes; });
+            }
+            if (p.flags & PF_WRITE_LIVE_PASSIVE) {
+                uint8_t* img = p.arena + tile_off;
+                uint32_t o = 0;
+                for_each_passive_chunk(sub, [&](uint32_t off, uint32_t bytes) { tma_store_1d(img + off, src + o, bytes); o += bytes; });
+            }
+            tma_commit();
+        }
+
         uint32_t pend[6] = {0, 0, 0, 0, 0, 0};
         uint32_t pend_row = 0;
         bool pend_valid = false;
@@ -569,22 +588,7 @@ __global__ void __launch_bounds__(SUB / VEC, MINB) k_particles_program(const __g
 
         // ------------------------------ passive planes ------------------------------
         if (use_tma) {
-            if (tid == 0) {
-                mbar_wait(&s_bar[buf], (it >> 1) & 1u);
-                const uint8_t* src = s_passive + size_t(buf) * p.passive_bytes;
-                for (uint32_t i = 0; i < p.n_ops; ++i) {
-                    if (p.ops[i].kind != OP_SAVE || (p.ops[i].flags & (OPF_NO_STORE | OPF_SKIP_PASSIVE))) continue;
-                    uint8_t* img = p.arena + (size_t(p.ops[i].image_off256) << 8) + tile_off;
-                    uint32_t o = 0;
-                    for_each_passive_chunk(sub, [&](uint32_t off, uint32_t bytes) { tma_store_1d(img + off, src + o, bytes); o += bytes; });
-                }
-                if (p.flags & PF_WRITE_LIVE_PASSIVE) {
-                    uint8_t* img = p.arena + tile_off;
-                    uint32_t o = 0;
-                    for_each_passive_chunk(sub, [&](uint32_t off, uint32_t bytes) { tma_store_1d(img + off, src + o, bytes); o += bytes; });
-                }
-                tma_commit();
-            }
+            // (bulk stores were issued at the top of the tile, right after the passive load landed)
         } else {
             // generic fallback (several LOADs in one program): the same program per passive plane,
             // a value is only ever loaded and stored, never computed on

@@ -22,11 +22,16 @@
 //   move_cube_system / increase_frame    examples/box_game/box_game.rs:146-206
 //   increment_score / decrease_health    tests/component_rollback.rs:25-29, tests/synctest.rs:38-45
 //
-// PARITY STATUS: ring semantics and RollbackOrdered are pinned by the reference's own unit
-// tests (ported in tests/); seahash is pinned by the crate's documented vectors; the
-// composition of per-entity hashes, the dt sequence and particle trajectories are
-// "parity unpinned" — the reference holds no numeric golden for them and no Rust toolchain
-// exists here to produce one.
+// PARITY STATUS: ring semantics and RollbackOrdered are pinned by the reference's own unit tests (ported in tests/);
+// the third-party arithmetic is pinned by vectors that do not come from this restatement (tests/golden/
+// third_party_kats.json, seahash_buffer_mode.json; tests/test_third_party_kats.py): seahash 4.1 by the crate's
+// documented vector + 97 lengths of a buffer-form restatement, SplitMix64 / xoshiro256++ by the published reference
+// vectors, Duration::as_secs_f32 (the dt sequence) by IEEE binary32 evaluation of the std formula, rand's f32 range by
+// proof that its retry branch is unreachable for the example's range.  What remains "PARITY UNPINNED" in the strict
+// sense is the COMPOSITION — how component_checksum.rs:67-108 / particles.rs combine those primitives, and therefore
+// the numeric frame checksums and trajectories: the reference holds no numeric golden for them and no Rust toolchain
+// exists here to produce one.  oracle/ref_harness + scripts/gen_reference_goldens.sh generate such
+// goldens from the UNMODIFIED crate on any box with cargo; tests/test_reference_goldens.py consumes them.
 //
 // Build with -ffp-contract=off: Rust/glam scalar Vec3 math rounds every mul and add.
 #pragma once

@@ -61,11 +61,19 @@ def run(w, ticks):
     for info, arr, n in vecs[:12]:
         w.submit_prepared(info, arr, n); w.collect()
     l0 = w.launch_count()
+    traced = w.last_path_fused()
+    if traced:
+        w.trace_enable(ticks + 4)
     t0 = time.perf_counter()
     for info, arr, n in vecs[12:]:
         w.submit_prepared(info, arr, n); w.collect()
     dt = (time.perf_counter() - t0) / ticks
-    return {"sync_us_per_tick": dt * 1e6, "launches_per_tick": (w.launch_count() - l0) / ticks, "one_launch": w.last_path_fused()}
+    out = {"sync_us_per_tick": dt * 1e6, "launches_per_tick": (w.launch_count() - l0) / ticks, "one_launch": w.last_path_fused()}
+    if traced:
+        tr = w.trace_read(ticks + 4)
+        out["kernel_us_median"] = float(np.median((tr[:, 1].astype(np.int64) - tr[:, 0].astype(np.int64)) / 1e3))
+        w.trace_enable(0)
+    return out
 
 
 def main():
