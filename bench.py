@@ -293,7 +293,10 @@ def run_ours(args):
     BT = min(BT, capi.BGR_MAX_REQUESTS // (2 * d + 2)) if d > 0 else 0                          # ... that fit one call
     K3 = (min(K, 400) // BT) * BT if BT > 1 else 0
     KT = 64                            # ticks of each traced leg (pipelined / synchronous)
-    ticks = pregenerate_ticks(fill + W + K + K + K + K2 + K3 + 2 * KT, d, maxp)
+    # A short K (the driver's 20) makes one timed region ~2 ms: time EXACTLY K steps several times and report the median
+    # region, so that one clock / scheduling hiccup cannot set the number.  Every region is bracketed as the contract says.
+    R = max(1, min(5, 400 // max(1, K)))
+    ticks = pregenerate_ticks(fill + W + 2 * R * K + K + K2 + K3 + 2 * KT, d, maxp)
     pos = [0]
 
     def take(k):
@@ -334,28 +337,37 @@ def run_ours(args):
 
     run_pipelined(take(fill + W))           # ring fill + warm-up (>= 3 steady-state ticks)
     barrier()
-    # ---------------- value: device-timed, K ticks back to back ----------------
-    timed = take(K)
-    adv_total = sum(t[2] for t in timed)
-    adv_per_tick = adv_total / K
+    # ---------------- value: device-timed, K ticks back to back (median of R such regions) ----------------
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = eng.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    run_pipelined(timed)
-    ev1.record(stream)
-    barrier()
-    ms = max_over_ranks(ev0.elapsed_time(ev1))
-    launches = eng.launch_count() - l0
+    regions = []
+    for _ in range(R):
+        tk = take(K)
+        l0 = eng.launch_count()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        run_pipelined(tk)
+        ev1.record(stream)
+        barrier()
+        regions.append((max_over_ranks(ev0.elapsed_time(ev1)), tk, eng.launch_count() - l0))
+    regions.sort(key=lambda r: r[0] / sum(t[2] for t in r[1]))
+    ms, timed, launches = regions[len(regions) // 2]
+    ms_all = [r[0] for r in regions]
+    adv_total = sum(t[2] for t in timed)
+    adv_per_tick = adv_total / K
     # ---------------- e2e: ONE synchronous bgr_handle_requests per tick, host arrays in / host checksums out ----------------
-    e2e_ticks = take(K)
-    batch = CallerBatch(e2e_ticks)
-    barrier()
-    e2e_s = max_over_ranks(batch.run(caller, eng))
-    history.extend(batch.checksums())
+    e2e_regions = []
+    for _ in range(R):
+        tk = take(K)
+        b = CallerBatch(tk)
+        barrier()
+        e2e_regions.append((max_over_ranks(b.run(caller, eng)), tk, b))
+        history.extend(b.checksums())
+    e2e_regions.sort(key=lambda r: r[0] / sum(t[2] for t in r[1]))
+    e2e_s, e2e_ticks, batch = e2e_regions[len(e2e_regions) // 2]
+    e2e_all = [r[0] for r in e2e_regions]
     clocks = sampler.stop() if rank == 0 else None
     e2e_p50_us = float(np.median(batch.per_tick) * 1e6)
     h2d = sum(C.sizeof(capi.bgr_request) * t[1] + C.sizeof(capi.bgr_session_info) for t in e2e_ticks) / K
@@ -538,7 +550,11 @@ def run_ours(args):
             "config": {"workload": args.workload, "entities_per_gpu": n, "entities_total": sum(shard_rows), "check_distance": d,
                        "max_prediction": maxp,
                        "columns": "Transform40+Velocity12+Ttl8+alive1 = 61 B/entity/slot", "checksum": "every saved frame",
-                       "advances_per_step": adv_per_tick, "l2": "inputs larger than L2: each tick reads 1 slot and writes 9 images of "
+                       "advances_per_step": adv_per_tick,
+                       "timed_regions": {"count": R, "reported": "median region", "value_ms": ms_all, "e2e_s": e2e_all,
+                                         "why": "each region times exactly K steps between barrier + synchronize; a short K is "
+                                                "repeated so that one hiccup cannot set the number"},
+                       "l2": "inputs larger than L2: each tick reads 1 slot and writes 9 images of "
                        f"{slot_bytes/1e6:.0f} MB (ring {maxp} slots)", "path": "fused" if fused else "stepwise",
                        "value_is": "device-timed PIPELINED submits (bgr_submit_requests / bgr_collect, consecutive launches overlap); "
                                    "the synchronous per-tick contract of the reference is `e2e`",

@@ -209,6 +209,7 @@ struct bgr_engine {
     // generic one-launch program (generic_program.cuh): any schema whose tile fits shared memory + the compiled systems
     bool generic_ok = false;
     int generic_bps = 0;            // resident blocks per SM of k_generic_program (occupancy query, cached)
+    int tune_passive_early = -1;    // -1: early passive stores for single-wave grids (auto); 0 never; 1 always
     int tune_sub = 0;               // 128: the 128-row work-item variant of the fused kernel (experiment; default: whole tiles)
     int tune_stagger_ns = 800;      // start-of-grid phase stagger between the resident blocks of an SM (synchronous launches; measured -1.3 %)
     int tune_generic = 1;
@@ -454,6 +455,8 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
     // per-plane bulk copies, and the tick is issue-latency-bound on the hash, not imbalance-bound.  Kept for A/B runs.
     const bool sub_items = e->tune_sub == 128;
     if (sub_items && e->tune_vec == 2 && e->n_chains == 1) pp.flags |= PF_SUB_ITEMS;
+    // one wave of blocks (every block runs one or two tiles): the tile's tail is the grid's tail
+    if (e->tune_passive_early == 1 || (e->tune_passive_early < 0 && total_tiles <= 3u * uint32_t(e->num_sms))) pp.flags |= PF_PASSIVE_EARLY;
     const Column& ct = e->cols[e->bt]; const Column& cv = e->cols[e->bv];
     if (ct.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_T; if (ct.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_T; pp.ck_t_slot = uint32_t(ct.ck_slot); }
     if (cv.hash_kind != BGR_HASH_NONE) { pp.flags |= PF_CK_V; if (cv.hash_flags & BGR_HASH_FLAG_ASSERT_FINITE_F32) pp.flags |= PF_FIN_V; pp.ck_v_slot = uint32_t(cv.ck_slot); }
@@ -1144,6 +1147,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_tiledep = env_int("BGR_TUNE_TILEDEP", 1);
     e->tune_generic = env_int("BGR_TUNE_GENERIC", 1);
     e->tune_sub = env_int("BGR_TUNE_SUB", 0);
+    e->tune_passive_early = env_int("BGR_TUNE_PASSIVE_EARLY", -1);
     e->tune_stagger_ns = env_int("BGR_TUNE_STAGGER_NS", 800);
     e->tune_bundle = env_int("BGR_TUNE_BUNDLE", 1);
     e->n_chains = std::max(1, std::min(int(bgr_engine::kMaxChains), env_int("BGR_TUNE_CHAINS", 1)));

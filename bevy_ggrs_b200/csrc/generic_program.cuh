@@ -58,6 +58,14 @@ static_assert(sizeof(GenericParams) <= 4000, "kernel parameter block must fit 4 
 __device__ __forceinline__ uint64_t hash_row_range(const uint32_t* col, uint32_t off, uint32_t len) {
     if (((off | len) & 3u) == 0u) {  // word-aligned range (every POD of u32 / f32 / u64 fields): no byte shuffling
         const uint32_t* w = col + size_t(off >> 2) * kTileRows;
+        // the common element sizes without a loop (warp-uniform switch: every row of a column has the same range)
+        switch (len) {
+        case 4: return sea_diffuse(sea_diffuse(kSeaA ^ uint64_t(w[0])) ^ kSeaB ^ kSeaC ^ kSeaD ^ 4ULL);
+        case 8: return sea_hash_u64(uint64_t(w[0]) | (uint64_t(w[kTileRows]) << 32));
+        case 12: return sea_hash_12(uint64_t(w[0]) | (uint64_t(w[kTileRows]) << 32), w[2 * kTileRows]);
+        case 16: return sea_hash_2xu64(uint64_t(w[0]) | (uint64_t(w[kTileRows]) << 32), uint64_t(w[2 * kTileRows]) | (uint64_t(w[3 * kTileRows]) << 32));
+        default: break;
+        }
         uint64_t a = kSeaA, b = kSeaB, c = kSeaC, d = kSeaD;
         uint32_t i = 0;
         for (; i + 8 <= len; i += 8) {

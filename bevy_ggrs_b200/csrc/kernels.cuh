@@ -95,6 +95,7 @@ enum ProgFlags : uint32_t {
     PF_PREFETCH_NEXT = 512u,     // warp 0 pulls the next tile's active planes into L2 while this tile computes
     PF_TILE_SIGNAL = 1024u,      // announce each block's FIRST tile in tile_done[] as soon as its stores are visible, and the
                                  // whole launch in *grid_done: what the next launch's first wave needs to start early
+    PF_PASSIVE_EARLY = 8192u,    // single-wave grid: issue the passive planes' bulk stores at the top of a tile
     PF_SUB_ITEMS = 4096u,        // host: launch the 128-row work-item variant (small worlds)
     PF_TILE_WAIT = 2048u,        // the previous launch on the stream was a PF_TILE_SIGNAL launch: start without waiting for
                                  // its grid (no griddepcontrol.wait) and wait per tile for tile_done[tile] or grid_done >=
@@ -455,9 +456,12 @@ __global__ void __launch_bounds__(SUB / VEC, MINB) k_particles_program(const __g
             }
         }
 
-        // ---- passive planes, TMA path: stream them out NOW, while the frames below are computed — they do not depend on any
-        // frame, and issued at the end of the tile (round 1) their completion sat on every tile's (and the grid's) tail ----
-        if (use_tma && tid == 0) {
+        // ---- passive planes, TMA path: one bulk store per SAVE (+ live) out of the staged copy.  They depend on no frame.
+        // Single-wave grids (small worlds, PF_PASSIVE_EARLY) issue them NOW, while the frames below are computed: issued
+        // after the last frame their completion sits on the tile's — and with one tile per block the grid's — tail
+        // (100k entities: 17.2 -> 15.7 us per tick).  Multi-wave grids keep them behind the frames: up front the 140 KB
+        // burst queues ahead of the tile's own loads and the HBM-bound steady state gets slower (1M: +2.5 us per tick). ----
+        auto issue_passive_stores = [&]() {
             mbar_wait(&s_bar[buf], (it >> 1) & 1u);
             const uint8_t* src = s_passive + size_t(buf) * p.passive_bytes;
             for (uint32_t i = 0; i < p.n_ops; ++i) {
@@ -472,7 +476,9 @@ __global__ void __launch_bounds__(SUB / VEC, MINB) k_particles_program(const __g
                 for_each_passive_chunk(sub, [&](uint32_t off, uint32_t bytes) { tma_store_1d(img + off, src + o, bytes); o += bytes; });
             }
             tma_commit();
-        }
+        };
+        const bool passive_early = (p.flags & PF_PASSIVE_EARLY) != 0;
+        if (use_tma && tid == 0 && passive_early) issue_passive_stores();
 
         uint32_t pend[6] = {0, 0, 0, 0, 0, 0};
         uint32_t pend_row = 0;
@@ -588,7 +594,7 @@ __global__ void __launch_bounds__(SUB / VEC, MINB) k_particles_program(const __g
 
         // ------------------------------ passive planes ------------------------------
         if (use_tma) {
-            // (bulk stores were issued at the top of the tile, right after the passive load landed)
+            if (tid == 0 && !passive_early) issue_passive_stores();
         } else {
             // generic fallback (several LOADs in one program): the same program per passive plane,
             // a value is only ever loaded and stored, never computed on
