@@ -52,3 +52,25 @@ def test_stdout_guard_keeps_the_json_line_alone_on_stdout():
 def test_synctest_consistency_check():
     assert bench.check_synctest_consistency([(1, 5), (2, 6), (1, 5)])
     assert not bench.check_synctest_consistency([(1, 5), (1, 7)])
+
+
+def test_reference_arm_prints_the_contract_line_on_a_cpu_box():
+    """`bench.py --impl reference` = the reference's CPU path (the oracle port here: no cargo, no checkout on the GPU box)
+    on host cores, same metric / unit / config keys as our arm, bounded sample, no GPU needed."""
+    import json
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "stress_100k_d8",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "rollback frames/s" and line["higher_is_better"] is True
+    assert line["config"]["workload"] == "stress_100k_d8" and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] in ("port", "reference") and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "rollback frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["value"] > 0
+
+
+def test_reference_arm_is_silent_on_other_ranks():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"], capture_output=True,
+                       text=True, timeout=120, env=env)
+    assert r.returncode == 0 and r.stdout.strip() == ""
