@@ -55,7 +55,9 @@ struct GenericParams {
 static_assert(sizeof(GenericParams) <= 4000, "kernel parameter block must fit 4 KB");
 
 // seahash of bytes [off, off+len) of one row's element whose words are `col[w * kTileRows]` (a column of the shared tile)
-__device__ __forceinline__ uint64_t hash_row_range(const uint32_t* col, uint32_t off, uint32_t len) {
+// (__noinline__: inlined per checksummed column and per row the interpreter grew to 11k instructions — 176 KB of code,
+// more than the SM's instruction cache — and ran 2.7x slower per frame than the specialised bundle kernel)
+__device__ __noinline__ uint64_t hash_row_range(const uint32_t* col, uint32_t off, uint32_t len) {
     if (((off | len) & 3u) == 0u) {  // word-aligned range (every POD of u32 / f32 / u64 fields): no byte shuffling
         const uint32_t* w = col + size_t(off >> 2) * kTileRows;
         // the common element sizes without a loop (warp-uniform switch: every row of a column has the same range)
@@ -168,7 +170,7 @@ __global__ void __launch_bounds__(kGenericBlock) k_generic_program(const __grid_
                 const float dt = __uint_as_float(op.dt_bits);
                 const uint8_t* al_cur = alive_ptr(cur);
                 uint8_t* al_new = alive_ptr(nb);
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < kGenericRowsPerThread; ++k) {
                     const uint32_t r = tid + k * kGenericBlock;
                     const uint32_t m = al_cur[r];   // the schedule's systems all see the entity as it was before the frame:
@@ -225,37 +227,32 @@ __global__ void __launch_bounds__(kGenericBlock) k_generic_program(const __grid_
                 // the bulk store streams the tile to the frame's slot while the threads hash their rows out of it
                 if (!(op.flags & OPF_NO_STORE)) store_tile(p.arena + (size_t(op.image_off256) << 8), tile);
                 const uint8_t* al = alive_ptr(cur);
-                uint64_t hx[kMaxHashCols];
-#pragma unroll
-                for (int c = 0; c < kMaxHashCols; ++c) hx[c] = 0;
+                uint32_t m[kGenericRowsPerThread];
+                uint64_t t0[kGenericRowsPerThread];
                 uint32_t n_alive = 0, bad = 0;
 #pragma unroll
                 for (int k = 0; k < kGenericRowsPerThread; ++k) {
                     const uint32_t r = tid + k * kGenericBlock;
-                    const uint32_t m = al[r];
-                    if (!(m & 1u)) continue;
-                    ++n_alive;
-                    const uint64_t t0 = sea_order_lane(p.order_base + size_t(tile) * kTileRows + r);
-#pragma unroll
-                    for (int c = 0; c < kMaxHashCols; ++c) {
-                        if (c < p.n_hash) {
-                            const HashSpec hs = p.hash[c];
-                            if (m & hs.absent) continue;  // Query<(&RollbackId, &T)> does not match this entity
-                            const uint32_t* col = reinterpret_cast<const uint32_t*>(tile_ptr(cur)) + size_t(hs.first_plane) * kTileRows + r;
-                            if (hs.finite)
-                                for (uint32_t q = 0; q + 4 <= hs.len; q += 4) bad |= f32_bits_nonfinite(col[size_t((hs.off + q) >> 2) * kTileRows]);
-                            hx[c] ^= sea_hash_entity(t0, hash_row_range(col, hs.off, hs.len));
-                        }
-                    }
+                    m[k] = al[r];
+                    n_alive += m[k] & 1u;
+                    t0[k] = sea_order_lane(p.order_base + size_t(tile) * kTileRows + r);
                 }
                 const unsigned full = 0xffffffffu;
                 unsigned int* a = &s_acc[op.save_index * kAccStride * 2];
+#pragma unroll 1
+                for (uint32_t c = 0; c < p.n_hash; ++c) {  // one checksummed column at a time: one copy of the hash code
+                    const HashSpec hs = p.hash[c];
+                    uint64_t hx = 0;
 #pragma unroll
-                for (int c = 0; c < kMaxHashCols; ++c) {
-                    if (c < p.n_hash) {
-                        const uint32_t lo = __reduce_xor_sync(full, uint32_t(hx[c])), hi = __reduce_xor_sync(full, uint32_t(hx[c] >> 32));
-                        if (lane == 0) { atomicXor(&a[2 * p.hash[c].slot], lo); atomicXor(&a[2 * p.hash[c].slot + 1], hi); }
+                    for (int k = 0; k < kGenericRowsPerThread; ++k) {
+                        if (!row_matches(m[k], hs.absent)) continue;  // Query<(&RollbackId, &T)>: exists and has the component
+                        const uint32_t* col = reinterpret_cast<const uint32_t*>(tile_ptr(cur)) + size_t(hs.first_plane) * kTileRows + tid + k * kGenericBlock;
+                        if (hs.finite)
+                            for (uint32_t q = 0; q + 4 <= hs.len; q += 4) bad |= f32_bits_nonfinite(col[size_t((hs.off + q) >> 2) * kTileRows]);
+                        hx ^= sea_hash_entity(t0[k], hash_row_range(col, hs.off, hs.len));
                     }
+                    const uint32_t lo = __reduce_xor_sync(full, uint32_t(hx)), hi = __reduce_xor_sync(full, uint32_t(hx >> 32));
+                    if (lane == 0) { atomicXor(&a[2 * hs.slot], lo); atomicXor(&a[2 * hs.slot + 1], hi); }
                 }
                 const uint32_t cnt = __reduce_add_sync(full, n_alive);
                 const uint32_t anybad = __reduce_or_sync(full, bad);
