@@ -208,7 +208,8 @@ struct bgr_engine {
     bool bundle_static_ck = false;  // both columns checksummed with the finite assertion: fully specialised kernel
     // generic one-launch program (generic_program.cuh): any schema whose tile fits shared memory + the compiled systems
     bool generic_ok = false;
-    int generic_bps = 0;            // resident blocks per SM of k_generic_program (occupancy query, cached)
+    int generic_bps[2] = {0, 0};    // resident blocks per SM of k_generic_program<256> / <512> (occupancy query, cached)
+    int tune_generic_block = 0;     // 0 auto, 256 / 512 force
     int tune_passive_early = -1;    // -1: early passive stores for single-wave grids (auto); 0 never; 1 always
     int tune_sub = 0;               // 128: the 128-row work-item variant of the fused kernel (experiment; default: whole tiles)
     int tune_stagger_ns = 800;      // start-of-grid phase stagger between the resident blocks of an SM (synchronous launches; measured -1.3 %)
@@ -763,14 +764,23 @@ int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
     }
     std::memcpy(gp.ops, pg.ops, sizeof(Op) * pg.n_ops);
     const size_t smem = 2 * size_t((e->tile_bytes + 127u) & ~127u);  // two tile buffers (ping-pong)
-    if (e->generic_bps == 0) {
-        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(k_generic_program, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    if (e->generic_bps[0] == 0) {
+        if (smem > 48 * 1024) {
+            CUDA_TRY(cudaFuncSetAttribute(k_generic_program<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+            CUDA_TRY(cudaFuncSetAttribute(k_generic_program<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        }
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_generic_program, kGenericBlock, smem));
-        e->generic_bps = std::max(1, nb);
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_generic_program<256>, 256, smem));
+        e->generic_bps[0] = std::max(1, nb);
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_generic_program<512>, 512, smem));
+        e->generic_bps[1] = std::max(1, nb);
     }
-    const uint32_t grid = std::max(1u, std::min(gp.n_tiles, uint32_t(e->num_sms * e->generic_bps)));
-    k_generic_program<<<grid, kGenericBlock, smem, e->stream>>>(gp);
+    // few tiles per SM: one row per thread (512 threads per tile) doubles the warps that hide each other's latency
+    const bool wide = e->tune_generic_block == 512 || (e->tune_generic_block == 0 && gp.n_tiles < 4u * uint32_t(e->num_sms));
+    const int bps = e->generic_bps[wide ? 1 : 0];
+    const uint32_t grid = std::max(1u, std::min(gp.n_tiles, uint32_t(e->num_sms * bps)));
+    if (wide) k_generic_program<512><<<grid, 512, smem, e->stream>>>(gp);
+    else k_generic_program<256><<<grid, 256, smem, e->stream>>>(gp);
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
     return BGR_OK;
@@ -1147,6 +1157,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_tiledep = env_int("BGR_TUNE_TILEDEP", 1);
     e->tune_generic = env_int("BGR_TUNE_GENERIC", 1);
     e->tune_sub = env_int("BGR_TUNE_SUB", 0);
+    e->tune_generic_block = env_int("BGR_TUNE_GENERIC_BLOCK", 0);
     e->tune_passive_early = env_int("BGR_TUNE_PASSIVE_EARLY", -1);
     e->tune_stagger_ns = env_int("BGR_TUNE_STAGGER_NS", 800);
     e->tune_bundle = env_int("BGR_TUNE_BUNDLE", 1);

@@ -28,8 +28,9 @@
 namespace bgr {
 
 constexpr int kMaxGenericSys = 8;
-constexpr int kGenericBlock = 256;
-constexpr int kGenericRowsPerThread = kTileRows / kGenericBlock;
+// threads per block: 256 (two rows per thread) for worlds with many tiles per SM, 512 (one row per thread, twice the
+// warps per tile) for small worlds, where a tick is one wave of blocks and latency-bound per warp (ncu, 100k entities:
+// 2.6 warps per scheduler, issue slots 24 % busy)
 
 struct SysSpec {
     uint32_t id;      // bgr_system
@@ -86,7 +87,9 @@ __device__ __noinline__ uint64_t hash_row_range(const uint32_t* col, uint32_t of
     return sea_hash_stream(len, byte_at);
 }
 
+template <int kGenericBlock>
 __global__ void __launch_bounds__(kGenericBlock) k_generic_program(const __grid_constant__ GenericParams p) {
+    constexpr int kGenericRowsPerThread = kTileRows / kGenericBlock;
     extern __shared__ __align__(128) uint8_t s_buf[];  // TWO tile buffers (ping-pong), each tile_bytes rounded up to 128
     __shared__ unsigned int s_acc[kMaxSaves * kAccStride * 2];
     __shared__ __align__(8) uint64_t s_bar;
