@@ -239,10 +239,16 @@ def run_ours(args):
     if int(os.environ.get("WORLD_SIZE", "1")) > 1:
         # before torch / NCCL are loaded: the communicator's INIT banner ("... rank r nranks N ...") must stay
         # reachable — on stderr, see StdoutGuard — so that the rank count of a multi-GPU run can be checked
-        os.environ.setdefault("NCCL_DEBUG", "INFO")
-        os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
+        # (the image exports NCCL_DEBUG=VERSION, which prints no rank count: raise it to INFO / INIT unless the caller
+        # asked for something specific through BENCH_NCCL_DEBUG)
+        want = os.environ.get("BENCH_NCCL_DEBUG")
+        if want:
+            os.environ["NCCL_DEBUG"] = want
+        elif os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
+            os.environ["NCCL_DEBUG"] = "INFO"
+            os.environ.setdefault("NCCL_DEBUG_SUBSYS", "INIT")
         if os.environ.get("RANK", "0") == "0":
-            print(f"[bench] NCCL_DEBUG={os.environ['NCCL_DEBUG']} NCCL_DEBUG_SUBSYS={os.environ['NCCL_DEBUG_SUBSYS']}", file=sys.stderr, flush=True)
+            print(f"[bench] NCCL_DEBUG={os.environ.get('NCCL_DEBUG')} NCCL_DEBUG_SUBSYS={os.environ.get('NCCL_DEBUG_SUBSYS')}", file=sys.stderr, flush=True)
     import numpy as np
     import torch
     import torch.distributed as dist

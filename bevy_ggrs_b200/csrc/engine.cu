@@ -411,11 +411,6 @@ int launch_particles(bgr_engine* e, const ProgramParams& pp, int vi, int si, int
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     const bool pdl = e->tune_pdl || (pp.flags & PF_TILE_WAIT);
     lc.attrs = attr; lc.numAttrs = pdl ? 1 : 0;
-    if (e->tune_stagger_ns > 0 && !(pp.flags & PF_TILE_WAIT) && grid >= 2u * uint32_t(e->num_sms)) {
-        ProgramParams ps = pp;  // only launches that start on an idle GPU: overlapping launches arrive dephased already
-        ps.stagger_ns = uint32_t(e->tune_stagger_ns); ps.stagger_div = uint32_t(e->num_sms);
-        CUDA_TRY(cudaLaunchKernelEx(&lc, kern, ps));
-    } else
     CUDA_TRY(cudaLaunchKernelEx(&lc, kern, pp));
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
@@ -506,6 +501,11 @@ int run_fused(bgr_engine* e, const Program& pg, uint32_t buf, uint32_t* chains_o
         pp.tile_done = e->d_tile_done; pp.tile_cnt = e->d_tile_cnt;
         pp.done_seq = uint32_t(e->seq);
         if (e->tiledep_chain) { pp.flags |= PF_TILE_WAIT; pp.wait_seq = e->tiledep_seq; pp.wait_tiles = e->tiledep_tiles; }
+    }
+    // start stagger: only launches that start on an idle GPU with at least two resident blocks per SM (overlapping
+    // launches arrive dephased already)
+    if (e->tune_stagger_ns > 0 && !(pp.flags & PF_TILE_WAIT) && total_tiles / chains >= 2u * uint32_t(e->num_sms)) {
+        pp.stagger_ns = uint32_t(e->tune_stagger_ns); pp.stagger_div = uint32_t(e->num_sms);
     }
     for (uint32_t c = 0; c < chains; ++c) {
         pp.tile_begin = uint32_t(uint64_t(total_tiles) * c / chains);

@@ -19,6 +19,7 @@ done
 [ -s gpurun_out/r02_generic_world.json ] && cp gpurun_out/r02_generic_world.json profiles/r02_generic_world.json
 [ -s gpurun_out/r02_prof_fused.ncu-rep ] && python tools/ncu_summary.py gpurun_out/r02_prof_fused.ncu-rep profiles/r02_k_particles_program stress_1m_d8
 [ -s gpurun_out/r02_prof_fused.ncu-rep ] && python tools/ncu_timeline.py gpurun_out/r02_prof_fused.ncu-rep profiles/r02_k_particles_program.timeline.csv 0
+[ -s gpurun_out/r02_prof_fused_100k.ncu-rep ] && python tools/ncu_summary.py gpurun_out/r02_prof_fused_100k.ncu-rep profiles/r02_k_particles_program_100k stress_100k_d8
 [ -s gpurun_out/r02_prof_tma.ncu-rep ] && python tools/ncu_summary.py gpurun_out/r02_prof_tma.ncu-rep profiles/r02_k_image_tma
 [ -s gpurun_out/r02_prof_generic.ncu-rep ] && python tools/ncu_summary.py gpurun_out/r02_prof_generic.ncu-rep profiles/r02_k_generic_program
 ls -la profiles | tail -30

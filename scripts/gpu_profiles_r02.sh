@@ -10,8 +10,9 @@ done
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 120 --csv --log-file gpurun_out/r02_launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-snapshot-bench > gpurun_out/r02_ncu_launches.log 2>&1; echo "launch list rc=$?"
 # full captures: fused kernel (headline workload), TMA copy at 10M (out of L2), generic program (presence world)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_particles_program -s 16 -c 2 -f -o gpurun_out/r02_prof_fused python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-snapshot-bench > gpurun_out/r02_ncu_fused.log 2>&1; echo "fused rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_particles_program -s 16 -c 2 -f -o gpurun_out/r02_prof_fused_100k python bench.py --workload stress_100k_d8 --steps 5 --warmup 3 --no-cpu-baseline --no-snapshot-bench > gpurun_out/r02_ncu_fused_100k.log 2>&1; echo "fused 100k rc=$?"
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_image_tma -s 6 -c 4 -f -o gpurun_out/r02_prof_tma python -c "import bench; bench.snapshot_bench(10_000_000, 9, 0, iters=3)" > gpurun_out/r02_ncu_tma.log 2>&1; echo "tma rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_generic_program -s 4 -c 2 -f -o gpurun_out/r02_prof_generic python scripts/generic_world_bench.py 100000 12 > gpurun_out/r02_ncu_generic.log 2>&1; echo "generic rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_generic_program -s 20 -c 2 -f -o gpurun_out/r02_prof_generic python scripts/generic_world_bench.py 100000 24 > gpurun_out/r02_ncu_generic.log 2>&1; echo "generic rc=$?"
 timeout 600 python scripts/generic_world_bench.py 100000 200 > gpurun_out/r02_generic_world.json 2> gpurun_out/r02_generic_world.err; echo "generic bench rc=$?"; cat gpurun_out/r02_generic_world.json
 python - <<'PY'
 import json,glob
