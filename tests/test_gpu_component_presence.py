@@ -198,3 +198,53 @@ def test_particles_bundle_with_optional_columns_stays_on_the_one_launch_path(n):
     assert np.array_equal(vals[ho.astype(bool)], vo[ho.astype(bool)])
     for w in (eng, orc, stp):
         w.close()
+
+
+@pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])
+def test_load_shrinks_a_world_that_grew_between_ticks_on_the_generic_program(flags):
+    """Entities spawned by the host between ticks (`commands.spawn((…, Rollback))` outside GgrsSchedule) after a
+    snapshot was taken: loading that snapshot takes them out again (EntitySnapshotPlugin::load despawns entities the
+    snapshot does not know, entity.rs:55-99) — across a tile boundary, on the one-launch generic program and stepwise."""
+    n0, extra = 700, 900          # 700 rows = 2 tiles, 1600 rows = 4 tiles
+    worlds = []
+    for w in (Engine(max_entities=n0 + extra, max_depth=8, flags=flags), OracleWorld()):
+        s_ = w.rollback_component("Score", 4, capi.BGR_STRATEGY_COPY | OPT)
+        h_ = w.rollback_component("Health", 4, capi.BGR_STRATEGY_CLONE | OPT)
+        t_ = w.rollback_component("Tag", 12, capi.BGR_STRATEGY_COPY)
+        for c, ln in ((s_, 4), (t_, 12), (h_, 4)):
+            w.checksum_component(c, 0, ln)
+        w.add_system(capi.BGR_SYS_U32_ADD, [s_], [0, 1])
+        w.add_system(capi.BGR_SYS_U32_SATSUB_DESPAWN, [h_], [0, 1])
+        w.build()
+        w.spawn(n0)
+        rng = np.random.default_rng(3)
+        w.write_component(s_, 0, rng.integers(0, 1000, n0, dtype=np.uint32))
+        w.write_component(h_, 0, rng.integers(3, 40, n0, dtype=np.uint32))
+        w.write_component(t_, 0, rng.integers(0, 2**32, (n0, 3), dtype=np.uint32))
+        worlds.append(w)
+        cols = (s_, h_, t_)
+    eng, orc = worlds
+    score, health, tag = cols
+    both = lambda f, *a: [getattr(w, f)(*a) for w in (eng, orc)]
+    a, b = both("handle_requests", NOSESS, [Request(SAVE, 0), Request(ADVANCE, 0, [0])])
+    assert a == b
+    rng = np.random.default_rng(4)
+    new_score, new_health = rng.integers(0, 99, extra, dtype=np.uint32), rng.integers(5, 50, extra, dtype=np.uint32)
+    new_tag = rng.integers(0, 2**32, (extra, 3), dtype=np.uint32)
+    for w in (eng, orc):
+        first = w.spawn(extra)
+        assert first == n0
+        w.write_component(score, first, new_score); w.write_component(health, first, new_health); w.write_component(tag, first, new_tag)
+    a, b = both("handle_requests", NOSESS, [Request(SAVE, 1), Request(ADVANCE, 0, [0]), Request(SAVE, 2), Request(ADVANCE, 0, [0])])
+    assert a == b and eng.row_count() == orc.row_count() == n0 + extra
+    _same(eng, orc, cols, n0 + extra)
+    l0 = eng.launch_count()
+    a, b = both("handle_requests", NOSESS, [Request(LOAD, 0), Request(ADVANCE, 0, [0]), Request(SAVE, 1), Request(ADVANCE, 0, [0])])
+    assert a == b
+    assert (eng.launch_count() - l0 == 1) == (flags == 0)
+    assert eng.row_count() == orc.row_count() == n0           # RollbackOrdered was rolled back with the snapshot
+    assert eng.active_count() == orc.active_count() <= n0
+    _same(eng, orc, cols, n0)
+    a, b = both("handle_requests", NOSESS, [Request(SAVE, 2), Request(ADVANCE, 0, [0])])   # and the world keeps working
+    assert a == b
+    eng.close(); orc.close()
