@@ -7,9 +7,9 @@
 //     seahash(active_sum, total_sum) ^ XOR_c seahash(XOR_shards xor_c)            (entity_checksum.rs:35-43, checksum.rs:88-99)
 // The consumer of that value is the HOST of every rank, so the exchange medium is host memory that all ranks map:
 // one POSIX shared-memory segment, page-locked and mapped into every rank's GPU address space (cudaHostRegister).
-// The last block of a rank's fused kernel already publishes its result rows with plain stores to host-mapped memory
-// followed by a sequence word (kernels.cuh); in a group those stores land in the shared segment, every rank's CPU
-// polls the sequence words of all ranks and folds.  No extra kernel, no copy, no collective library call, no
+// The last block of a rank's fused kernel already publishes its result words with plain stores to host-mapped memory,
+// each as a self-validating pair (v, v ^ tag(seq, i)) (kernels.cuh publish_pair); in a group those stores land in the
+// shared segment, every rank's CPU polls the pairs of all ranks' blocks and folds.  No extra kernel, no copy, no collective library call, no
 // Python between two ticks: the exchange costs what the single-GPU completion poll costs.  (NCCL has no XOR
 // reduction, and an all_gather of 64 B per frame through NCCL + a D2H copy is ~40 us of launch latency per tick —
 // the round-1 design, which capped weak scaling at 0.78.)
@@ -56,7 +56,7 @@ struct alignas(64) GroupHeader {
 };
 struct alignas(64) GroupRank {
     std::atomic<uint64_t> consumed;  // last group sequence number this rank has folded (its peers may reuse that buffer)
-    std::atomic<uint64_t> seq_base;  // engine sequence number at join: flag value of group sequence g is seq_base + g
+    std::atomic<uint64_t> seq_base;  // engine sequence number at join: the kernel of group sequence g tags its pairs with seq_base + g
 };
 struct alignas(64) GroupMeta {  // host-written at submit time, one per (rank, buffer)
     std::atomic<uint64_t> gseq;  // written last (release)

@@ -75,7 +75,7 @@ def main():
         t[workload] = sum(vals) / len(vals)
         t[workload + "_source"] = out + ".metrics.csv"
         du = hdr.index("gpu__time_duration.sum")
-        us = {"usecond": 1.0, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}
+        us = {"usecond": 1.0, "us": 1.0, "msecond": 1e3, "ms": 1e3, "nsecond": 1e-3, "ns": 1e-3, "second": 1e6, "s": 1e6}
         iso = t.setdefault("isolated_launch_us", {})
         iso[workload] = sum(float(r[du]) * us[units[du]] for r in data) / len(data)   # serialised, cold-cache launches under ncu
         json.dump(t, open(path, "w"), indent=1)
