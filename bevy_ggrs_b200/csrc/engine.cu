@@ -147,7 +147,7 @@ struct bgr_engine {
 
     HostState st;
 
-    static constexpr int kBufs = 8;  // result / spawn buffers = max un-collected submits
+    static constexpr int kBufs = 8;  // result / spawn buffers = max un-collected submits (== PendingRing capacity)
     static constexpr int kMaxChains = 8;
     // Chains: the entity range is cut into n_chains contiguous tile ranges, each with its own stream, accumulators
     // and result block.  Entities are independent, so chain A's kernel of tick i+1 only depends on chain A's kernel
@@ -169,7 +169,18 @@ struct bgr_engine {
     unsigned long long* h_out[kBufs] = {};
     unsigned long long* d_out[kBufs] = {};
     cudaEvent_t ev[kBufs] = {};
-    std::deque<Pending> pending;
+    // un-collected request vectors, oldest first: a fixed ring (a std::deque allocated a chunk per push — the hot path
+    // allocates nothing)
+    struct PendingRing {
+        Pending slot[8];
+        uint32_t head = 0, count = 0;
+        bool empty() const { return count == 0; }
+        size_t size() const { return count; }
+        void push_back(const Pending& p) { slot[(head + count) % 8u] = p; ++count; }
+        Pending& front() { return slot[head]; }
+        void pop_front() { head = (head + 1u) % 8u; --count; }
+        template <class F> void for_each(F f) { for (uint32_t i = 0; i < count; ++i) f(slot[(head + i) % 8u]); }
+    } pending;
     uint32_t next_buf = 0;
     std::vector<bgr_partial> last_partials;
 
@@ -941,7 +952,7 @@ int drain(bgr_engine* e) {
     e->tiledep_chain = false;  // callers enqueue ordinary (fully ordered) work next
     if (e->pending.empty()) return BGR_OK;
     CUDA_TRY(cudaStreamSynchronize(e->stream));  // every chain stream is joined into the main stream by an event
-    for (Pending& pd : e->pending) pd.finished = true;
+    e->pending.for_each([](Pending& pd) { pd.finished = true; });
     return BGR_OK;
 }
 

@@ -47,6 +47,26 @@ def particles_world(n, flags):
     return w
 
 
+def particles_world_optional(n, flags):
+    """the particles bundle with Velocity and Ttl registered optional (fused kernel MODE 2), a few components removed"""
+    OPT = capi.BGR_STRATEGY_OPTIONAL
+    w = Engine(max_entities=n, max_depth=9, flags=flags)
+    t = w.rollback_component("Transform", 40, capi.BGR_STRATEGY_CLONE)
+    v = w.rollback_component("Velocity", 12, capi.BGR_STRATEGY_COPY | OPT)
+    l = w.rollback_component("Ttl", 8, capi.BGR_STRATEGY_COPY | OPT)
+    w.checksum_component(v, 0, 12, capi.BGR_HASH_FLAG_ASSERT_FINITE_F32)
+    w.checksum_component(t, 0, 12, capi.BGR_HASH_FLAG_ASSERT_FINITE_F32)
+    w.add_system(capi.BGR_SYS_PARTICLES_UPDATE, [t, v])
+    w.add_system(capi.BGR_SYS_PARTICLES_DESPAWN, [l])
+    w.build()
+    tf, vel, ttl = synth_particles(n, 1, 100000, 100000)
+    w.spawn(n)
+    w.write_component(t, 0, tf); w.write_component(v, 0, vel); w.write_component(l, 0, ttl)
+    for r in range(0, min(n, 2000), 7):
+        w.remove_component(v if r % 2 else l, r)
+    return w
+
+
 def run(w, ticks):
     sess = SyncTestSession(2, 8, 9, input_delay=2)
     vecs = []
@@ -81,10 +101,12 @@ def main():
     out = {"entities": n, "ticks": ticks, "check_distance": 8}
     for name, make, flags in (("presence_world_generic_program", presence_world, 0),
                               ("presence_world_stepwise", presence_world, capi.BGR_CFG_FORCE_STEPWISE),
-                              ("particles_bundle", particles_world, 0)):
+                              ("particles_bundle", particles_world, 0),
+                              ("particles_bundle_with_optional_columns", particles_world_optional, 0)):
         w = make(n, flags)
         out[name] = run(w, ticks)
         w.close()
+    out["optional_bundle_vs_bundle"] = out["particles_bundle_with_optional_columns"]["sync_us_per_tick"] / out["particles_bundle"]["sync_us_per_tick"]
     out["generic_vs_bundle"] = out["presence_world_generic_program"]["sync_us_per_tick"] / out["particles_bundle"]["sync_us_per_tick"]
     print(json.dumps(out))
 
