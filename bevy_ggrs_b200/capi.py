@@ -34,6 +34,7 @@ BGR_SYS_U32_ADD = 4
 BGR_SYS_U32_SATSUB_DESPAWN = 5
 BGR_SYS_U32_STORE_CALL_COUNT = 6
 BGR_SYS_PARTICLES_SPAWN = 7
+BGR_SYS_DESPAWN_ON_INPUT = 8
 BGR_INPUT_SPAWN = 0x10
 # bgr_request_kind
 BGR_REQ_SAVE, BGR_REQ_LOAD, BGR_REQ_ADVANCE = 0, 1, 2

@@ -694,6 +694,14 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
                     break;
                 case BGR_SYS_PARTICLES_SPAWN:
                     continue;  // Commands: applied after the schedule (below)
+                case BGR_SYS_DESPAWN_ON_INPUT: {
+                    const uint32_t player = sy.params[0], n_players = (op.flags >> 8) & 0xFu;
+                    const uint32_t input = player < n_players ? op.inputs[player] : 0u;
+                    if (input != sy.params[1]) continue;  // the run condition is host-known: no launch on other frames
+                    k_sys_despawn_having<<<grid, 256, 0, e->stream>>>(live, e->words, n, e->d_kill, need);
+                    any_despawn = true;
+                    break;
+                }
                 case BGR_SYS_BOX_MOVE: {
                     unsigned long long packed = 0;
                     for (int k = 0; k < 8; ++k) packed |= (unsigned long long)(op.inputs[k]) << (8 * k);
@@ -768,6 +776,7 @@ int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
         case BGR_SYS_U32_ADD:
         case BGR_SYS_U32_SATSUB_DESPAWN: sp.plane0 += sy.params[0] / 4; sp.param = sy.params[1]; break;
         case BGR_SYS_U32_STORE_CALL_COUNT: sp.plane0 += sy.params[0] / 4; sp.param = counter_index++; break;
+        case BGR_SYS_DESPAWN_ON_INPUT: sp.param = sy.params[0] | (sy.params[1] << 8); break;
         case BGR_SYS_PARTICLES_UPDATE:
         case BGR_SYS_BOX_MOVE: sp.plane1 = e->cols[sy.cols[1]].first_plane; break;
         default: break;
@@ -1303,6 +1312,10 @@ BGR_API int bgr_add_system(bgr_engine* e, uint32_t system, const uint32_t* colum
         if (!need(2, 0) || eb(0) != 40 || eb(1) != 12)
             return fail(BGR_ERR_INVALID_ARGUMENT, "move_cube_system binds {Transform(40B), Velocity(12B)}");
         break;
+    case BGR_SYS_DESPAWN_ON_INPUT:
+        if (!need(1, 2) || s.params[0] >= BGR_MAX_PLAYERS || s.params[1] > 0xFF)
+            return fail(BGR_ERR_INVALID_ARGUMENT, "despawn_on_input binds {C} with params {player_handle < 8, value <= 255}");
+        break;
     default: return fail(BGR_ERR_INVALID_ARGUMENT, "unknown system id");
     }
     e->systems.push_back(std::move(s));
@@ -1380,7 +1393,8 @@ BGR_API int bgr_build(bgr_engine* e) {
         bool ok = e->systems.size() <= size_t(kMaxGenericSys) && e->tile_bytes <= 100u * 1024u;  // two tile buffers per block in <= 200 KB
         for (const SystemReg& sy : e->systems)
             ok = ok && (sy.id == BGR_SYS_U32_ADD || sy.id == BGR_SYS_U32_SATSUB_DESPAWN || sy.id == BGR_SYS_U32_STORE_CALL_COUNT ||
-                        sy.id == BGR_SYS_PARTICLES_UPDATE || sy.id == BGR_SYS_PARTICLES_DESPAWN || sy.id == BGR_SYS_BOX_MOVE);
+                        sy.id == BGR_SYS_PARTICLES_UPDATE || sy.id == BGR_SYS_PARTICLES_DESPAWN || sy.id == BGR_SYS_BOX_MOVE ||
+                        sy.id == BGR_SYS_DESPAWN_ON_INPUT);
         e->generic_ok = ok;
     }
     {   // TMA copy kernel: up to six one-tile stages in ~200 KB of shared memory, at least two

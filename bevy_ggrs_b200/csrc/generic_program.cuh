@@ -195,6 +195,12 @@ __global__ void __launch_bounds__(kGenericBlock) k_generic_program(const __grid_
                             break;
                         }
                         case BGR_SYS_U32_STORE_CALL_COUNT: w0[0] = op.call_count + sy.param; break;
+                        case BGR_SYS_DESPAWN_ON_INPUT: {  // param = player handle | value << 8
+                            const uint32_t player = sy.param & 0xFFu, n_players = (op.flags >> 8) & 0xFu;
+                            const uint32_t input = player < n_players && player < 8 ? op.inputs[player] : 0u;
+                            kill = kill || input == (sy.param >> 8);
+                            break;
+                        }
                         case BGR_SYS_PARTICLES_UPDATE: {
                             uint32_t* v = row + size_t(sy.plane1) * kTileRows;
                             uint32_t tx = w0[0], ty = w0[kTileRows], tz = w0[2 * kTileRows], vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];

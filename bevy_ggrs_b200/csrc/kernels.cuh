@@ -859,6 +859,13 @@ __global__ void __launch_bounds__(256) k_sys_u32_satsub_despawn(uint8_t* img, ui
     }
 }
 
+// commands.entity(e).despawn() for every entity that has the bound component (tests/hierarchy.rs:36-45; launched only
+// on frames whose input matches)
+__global__ void __launch_bounds__(256) k_sys_despawn_having(const uint8_t* img, uint32_t words, uint32_t n_rows, uint8_t* kill, uint32_t need) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
+        if (row_matches(img[alive_offset(words, r)], need)) kill[r] = 1;
+}
+
 // c.0 = count  (the deliberately non-deterministic system of tests/synctest.rs:92-97)
 __global__ void __launch_bounds__(256) k_sys_u32_store(uint8_t* img, uint32_t words, uint32_t plane, uint32_t n_rows, uint32_t value, uint32_t need) {
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)

@@ -100,7 +100,13 @@ typedef enum bgr_system {
      * keeps host-side and rolls back with every snapshot (rollback_resource_with_clone::<ParticleRng>, :200).
      * Commands are deferred: the new rows exist from the end of the frame on and are not updated in it.
      * cols = {Transform(40B), Velocity(12B), Ttl(8B)}; params = {rate, ttl, seed_lo, seed_hi} */
-    BGR_SYS_PARTICLES_SPAWN = 7
+    BGR_SYS_PARTICLES_SPAWN = 7,
+    /* `if inputs[player].0 == value { commands.entity(e).despawn() }` for every entity that has component C — the
+     * shape of tests/hierarchy.rs:36-45 delete_child_system (there the child is reached through the parent's `Children`;
+     * here C is the child's own `ChildOf`, an optional 8-byte column holding the parent's RollbackOrdered index: row
+     * indices are stable across rollback, so the hierarchy needs neither ChildOfSnapshotPlugin's remapping
+     * (childof_snapshot.rs) nor MapEntities (component_map.rs)).  cols = {C}; params = {player_handle, value} */
+    BGR_SYS_DESPAWN_ON_INPUT = 8
 } bgr_system;
 #define BGR_INPUT_SPAWN 0x10u /* INPUT_SPAWN, particles.rs:75 */
 

@@ -637,6 +637,14 @@ struct World {
             }
             break;
         }
+        case BGR_SYS_DESPAWN_ON_INPUT: {  // tests/hierarchy.rs:36-45 delete_child_system, keyed on the entity's own component
+            uint32_t c = s.cols[0], player = s.params[0], value = s.params[1];
+            uint8_t input = player < n_players ? player_inputs[player] : 0;
+            if (input == value)
+                for (size_t r = 0; r < rows(); ++r)
+                    if (has[c][r]) despawn.push_back(r);
+            break;
+        }
         case BGR_SYS_U32_STORE_CALL_COUNT: {  // tests/synctest.rs:92-97
             uint32_t c = s.cols[0], off = s.params[0], eb = columns[c].elem_bytes;
             uint32_t count = call_count++;

@@ -26,6 +26,7 @@ pub const BGR_SYS_U32_ADD: u32 = 4;
 pub const BGR_SYS_U32_SATSUB_DESPAWN: u32 = 5;
 pub const BGR_SYS_U32_STORE_CALL_COUNT: u32 = 6;
 pub const BGR_SYS_PARTICLES_SPAWN: u32 = 7;
+pub const BGR_SYS_DESPAWN_ON_INPUT: u32 = 8;
 
 pub const BGR_REQ_SAVE: u32 = 0;
 pub const BGR_REQ_LOAD: u32 = 1;

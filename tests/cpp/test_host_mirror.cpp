@@ -326,6 +326,46 @@ static void spectator_session_only_advances() {
     EXPECT(app.last_checksums().empty());
 }
 
+// tests/hierarchy.rs:125-188 (hierarchy): parent + child, both Rollback, linked by ChildOf; the child is despawned inside
+// GgrsSchedule on one frame (delete_child_system, :36-45), rollbacks re-simulate that frame; afterwards the child is gone
+// and the parent still exists.  ChildOf is an optional POD column holding the parent's RollbackOrdered index.
+struct ParentEntity { uint8_t tag; };
+struct ChildEntity { uint8_t tag; };
+struct ChildOf { uint64_t parent; };
+static void hierarchy_child_deleted_inside_the_schedule() {
+    std::printf("hierarchy_child_deleted_inside_the_schedule\n");
+    App app(8, 8);
+    bool send_delete = false;
+    app.insert_resource(Session::SyncTest(ggrs::SyncTestSession(1, 2)))
+        .add_plugins(GgrsPlugin<GgrsConfig<uint8_t>>{})
+        .add_systems(ReadInputs{}, [&](App& a) {
+            LocalInputs li;
+            li.inputs[0] = send_delete ? 1 : 0;   // hierarchy.rs:17-27
+            send_delete = false;
+            a.insert_resource(li);
+        });
+    app.rollback_optional_component_with_copy<ParentEntity>().rollback_optional_component_with_copy<ChildEntity>()
+        .rollback_optional_component_with_copy<ChildOf>();
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_DESPAWN_ON_INPUT, {app.col<ChildOf>()}, {0, 1}});
+    app.add_systems(Startup{}, [](App& a) {
+        const uint32_t first = a.spawn(2);
+        a.remove<ChildEntity>(first); a.remove<ChildOf>(first);       // the parent
+        a.remove<ParentEntity>(first + 1);                            // the child ...
+        a.write<ChildOf>(first + 1, {ChildOf{first}});               // ... of the parent
+    });
+    bool mismatch = false;
+    app.add_observer([&](const SyncTestMismatch&) { mismatch = true; });
+    app.update();
+    EXPECT(app.active_count() == 2 && app.has<ChildOf>(0, 2)[1] == 1 && app.read<ChildOf>(1, 1)[0].parent == 0);
+    app.update();
+    send_delete = true;
+    for (int i = 0; i < 5; ++i) app.update();
+    EXPECT(!mismatch);
+    EXPECT(app.active_count() == 1);                                  // the child is gone ...
+    EXPECT(app.has<ChildEntity>(0, 2)[1] == 0 && app.has<ChildOf>(0, 2)[1] == 0);
+    EXPECT(app.has<ParentEntity>(0, 2)[0] == 1);                      // ... the parent still exists
+}
+
 // schedule_systems.rs:70-79: without a session the frame resources are reset
 static void removed_session_resets_frame_resources() {
     std::printf("removed_session_resets_frame_resources\n");
@@ -370,6 +410,7 @@ int main(int argc, char** argv) {
         p2p_confirmed_frame_advances_and_prunes_snapshots();
         spectator_session_only_advances();
         removed_session_resets_frame_resources();
+        hierarchy_child_deleted_inside_the_schedule();
     } catch (const std::exception& e) {
         std::printf("unexpected exception: %s\n", e.what());
         return 2;
