@@ -96,3 +96,37 @@ def run_hierarchy_with_deletion(backend):
     assert (has_marker[1] & alive).sum() == 0 and (has_link & alive).sum() == 0
     assert has_marker[0][0]
     return app
+
+
+def run_reference_survives_despawn_and_restore(world):
+    """What MapEntities exists for (component_map.rs:1-5): "After a rollback, some entities may have been recreated with
+    new Entity IDs" — so components holding an Entity must be remapped.  Here a reference is the target's
+    RollbackOrdered index (its row), and a Load brings a despawned entity back AS THE SAME ROW: the reference is valid
+    again without any fix-up.  Parent (row 0) is despawned on frame 1, a Load of frame 0 restores it; the child's ChildOf
+    still names row 0, which is alive again with its own data."""
+    from bevy_ggrs_b200.session import ADVANCE, LOAD, SAVE, Request
+    NOSESS = (capi.BGR_SESSION_NONE, 0, 0, 0)
+    parent = world.rollback_component("ParentEntity", 4, capi.BGR_STRATEGY_COPY | capi.BGR_STRATEGY_OPTIONAL)
+    child_of = world.rollback_component("ChildOf", 8, capi.BGR_STRATEGY_COPY | capi.BGR_STRATEGY_OPTIONAL)
+    world.checksum_component(parent, 0, 4)
+    world.checksum_component(child_of, 0, 8)
+    world.add_system(capi.BGR_SYS_DESPAWN_ON_INPUT, [parent], [0, 1])     # despawn the PARENT when player 0 presses 1
+    world.build()
+    first = world.spawn(3)
+    world.write_component(parent, first, np.array([0xAAAA], dtype=np.uint32))
+    for row in (first + 1, first + 2):
+        world.remove_component(parent, row)
+        world.write_component(child_of, row, np.array([first], dtype=np.uint64))
+    world.remove_component(child_of, first)
+    cs = []
+    cs += world.handle_requests(NOSESS, [Request(SAVE, 0), Request(ADVANCE, 0, [1]), Request(SAVE, 1), Request(ADVANCE, 0, [0])])
+    assert world.read_alive(0, 3).tolist() == [0, 1, 1]                   # the parent is gone, its children dangle
+    cs += world.handle_requests(NOSESS, [Request(LOAD, 0)])
+    assert world.read_alive(0, 3).tolist() == [1, 1, 1]                   # restored as the SAME row ...
+    assert world.read_component(parent, 0, 1).view(np.uint32)[0, 0] == 0xAAAA
+    link = world.read_component(child_of, 0, 3).view(np.uint64)[:, 0]
+    assert link[1] == first and link[2] == first                          # ... so the references are valid again as they are
+    assert world.has_component(child_of, 0, 3).tolist() == [0, 1, 1]
+    cs += world.handle_requests(NOSESS, [Request(ADVANCE, 0, [0]), Request(SAVE, 1)])
+    assert cs[1][0] == cs[2][0] == 1 and cs[1][1] != cs[2][1]            # frame 1 without / with the parent: different checksums
+    return cs

@@ -33,3 +33,11 @@ def test_hierarchy_checksums_match_the_oracle_tick_for_tick():
         assert eng_app.last_checksums == orc_app.last_checksums, i
         total += len(eng_app.last_checksums)
     assert total > 12 and eng_app.world.active_count() == orc_app.world.active_count() == 1
+
+
+@pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])
+def test_entity_reference_survives_despawn_and_restore_without_mapping(flags):
+    from hierarchy_util import run_reference_survives_despawn_and_restore
+    got = run_reference_survives_despawn_and_restore(Engine(max_entities=8, max_depth=8, flags=flags))
+    want = run_reference_survives_despawn_and_restore(OracleWorld())
+    assert got == want and len(got) == 3

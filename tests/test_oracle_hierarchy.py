@@ -9,3 +9,9 @@ def test_recursive_hierarchy_is_preserved_through_rollback():
 
 def test_hierarchy_child_deleted_inside_the_schedule_stays_deleted():
     run_hierarchy_with_deletion(OracleWorld())
+
+
+def test_entity_reference_survives_despawn_and_restore_without_mapping():
+    from hierarchy_util import run_reference_survives_despawn_and_restore
+    cs = run_reference_survives_despawn_and_restore(OracleWorld())
+    assert len(cs) == 3
