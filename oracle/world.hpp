@@ -272,7 +272,9 @@ struct World {
 
     // commands.spawn((components..., Rollback)): on_add hook -> RollbackId + RollbackOrdered.push (rollback.rs:40-54)
     uint32_t spawn(uint32_t count) {
-        uint32_t first = uint32_t(rows());
+        // the caller addresses entities by RollbackOrdered index (== engine row): the first new one gets the next index.
+        // (rows() — the dense table's length — is smaller once entities have been despawned; found by the request fuzz.)
+        uint32_t first = uint32_t(rollback_ordered.len());
         for (uint32_t k = 0; k < count; ++k) {
             uint64_t e = next_entity++;
             rollback_id.push_back(e);
