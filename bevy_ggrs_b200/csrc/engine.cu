@@ -783,7 +783,7 @@ int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
         }
     }
     std::memcpy(gp.ops, pg.ops, sizeof(Op) * pg.n_ops);
-    const size_t smem = 2 * size_t((e->tile_bytes + 127u) & ~127u);  // two tile buffers (ping-pong)
+    const size_t smem = size_t((e->tile_bytes + 127u) & ~127u);
     if (e->generic_bps[0] == 0) {
         if (smem > 48 * 1024) {
             CUDA_TRY(cudaFuncSetAttribute(k_generic_program<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
@@ -1390,7 +1390,7 @@ BGR_API int bgr_build(bgr_engine* e) {
         }
     detect_bundles(e);
     {   // generic one-launch program: every registered system has a shared-memory implementation, the tile fits twice per SM
-        bool ok = e->systems.size() <= size_t(kMaxGenericSys) && e->tile_bytes <= 100u * 1024u;  // two tile buffers per block in <= 200 KB
+        bool ok = e->systems.size() <= size_t(kMaxGenericSys) && e->tile_bytes <= 100u * 1024u;  // at least two blocks per SM
         for (const SystemReg& sy : e->systems)
             ok = ok && (sy.id == BGR_SYS_U32_ADD || sy.id == BGR_SYS_U32_SATSUB_DESPAWN || sy.id == BGR_SYS_U32_STORE_CALL_COUNT ||
                         sy.id == BGR_SYS_PARTICLES_UPDATE || sy.id == BGR_SYS_PARTICLES_DESPAWN || sy.id == BGR_SYS_BOX_MOVE ||

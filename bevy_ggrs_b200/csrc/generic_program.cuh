@@ -87,10 +87,36 @@ __device__ __noinline__ uint64_t hash_row_range(const uint32_t* col, uint32_t of
     return sea_hash_stream(len, byte_at);
 }
 
+// One checksummed column whose element is NW whole words (4 * NW bytes, word-aligned) for the thread's R rows:
+// `col` points at the first word of the thread's first row, rows are `B` words apart, words of an element kTileRows apart.
+// Branch-free per row (a row without the component contributes 0), so the rows' hash chains interleave.
+template <int NW, int R, int B>
+__device__ __forceinline__ void hash_words_column(const uint32_t* col, const uint32_t (&m)[R], uint32_t absent, uint32_t finite,
+                                                  const uint64_t (&t0)[R], uint64_t& hx, uint32_t& bad) {
+#pragma unroll
+    for (int k = 0; k < R; ++k) {
+        uint32_t w[NW];
+#pragma unroll
+        for (int j = 0; j < NW; ++j) w[j] = col[k * B + j * kTileRows];
+        const bool has = row_matches(m[k], absent);  // Query<(&RollbackId, &T)>: exists and has the component
+        uint32_t nonfinite = 0;
+#pragma unroll
+        for (int j = 0; j < NW; ++j) nonfinite |= f32_bits_nonfinite(w[j]);
+        bad |= (has && finite) ? nonfinite : 0u;
+        uint64_t h;
+        if (NW == 1) h = sea_diffuse(sea_diffuse(kSeaA ^ uint64_t(w[0])) ^ kSeaB ^ kSeaC ^ kSeaD ^ 4ULL);
+        else if (NW == 2) h = sea_hash_u64(uint64_t(w[0]) | (uint64_t(w[1 % NW]) << 32));
+        else if (NW == 3) h = sea_hash_12(uint64_t(w[0]) | (uint64_t(w[1 % NW]) << 32), w[2 % NW]);
+        else h = sea_hash_2xu64(uint64_t(w[0]) | (uint64_t(w[1 % NW]) << 32), uint64_t(w[2 % NW]) | (uint64_t(w[3 % NW]) << 32));
+        const uint64_t e = sea_hash_entity(t0[k], h);
+        hx ^= has ? e : 0ULL;
+    }
+}
+
 template <int kGenericBlock>
 __global__ void __launch_bounds__(kGenericBlock) k_generic_program(const __grid_constant__ GenericParams p) {
-    constexpr int kGenericRowsPerThread = kTileRows / kGenericBlock;
-    extern __shared__ __align__(128) uint8_t s_buf[];  // TWO tile buffers (ping-pong), each tile_bytes rounded up to 128
+    constexpr int kRows = kTileRows / kGenericBlock;  // rows of a tile per thread
+    extern __shared__ __align__(128) uint8_t s_buf[];  // one tile
     __shared__ unsigned int s_acc[kMaxSaves * kAccStride * 2];
     __shared__ __align__(8) uint64_t s_bar;
     __shared__ uint32_t s_next;
@@ -102,46 +128,39 @@ __global__ void __launch_bounds__(kGenericBlock) k_generic_program(const __grid_
     if (tid == 0) { mbar_init(&s_bar, 1); fence_mbar_init(); }
     __syncthreads();
 
-    // Ping-pong: an ADVANCE reads the current buffer and writes the other one, so the bulk store a SAVE issued from the
-    // current buffer keeps reading it while the next frame is already being computed — with ONE buffer every frame waited
-    // for its predecessor's store to finish reading shared memory (measured: 4.5 us per frame instead of ~2).
-    const uint32_t buf_stride = (p.tile_bytes + 127u) & ~127u;
-    uint32_t cur = 0;                       // buffer holding the tile's current state (block-uniform)
+    // ONE tile buffer.  (A ping-pong pair — ADVANCE reading one buffer and writing the other so that a SAVE's bulk store
+    // could keep reading — was measured: no faster, the store has long finished reading when the next ADVANCE starts,
+    // and it costs a copy of every word per frame and half the resident blocks.)
+    uint8_t* const s_tile = s_buf;
+    uint8_t* const s_alive = s_tile + size_t(p.words) * kPlaneBytes;
+    uint32_t* const tile_w = reinterpret_cast<uint32_t*>(s_tile);  // word (plane, row) = tile_w[plane * kTileRows + row]
     uint32_t phase = 0;
-    uint32_t n_stores = 0;                  // bulk stores committed so far by thread 0 (block-uniform count)
-    uint32_t last_store[2] = {0, 0};        // n_stores right after the last store that reads each buffer (0: none)
-    auto tile_ptr = [&](uint32_t b) { return s_buf + size_t(b) * buf_stride; };
-    auto alive_ptr = [&](uint32_t b) { return tile_ptr(b) + size_t(p.words) * kPlaneBytes; };
+    bool store_pending = false;  // a bulk store may still be reading the shared tile (block-uniform)
 
-    // buffer b is about to be overwritten: every bulk store that reads it must be done reading, and every thread must be
-    // done with its previous content
-    auto before_write = [&](uint32_t b) {
-        if (last_store[b] != 0) {
-            if (tid == 0) {
-                if (n_stores - last_store[b] == 0) tma_wait_read<0>();   // the most recent store reads b
-                else tma_wait_read<1>();                                  // at least one newer store exists: all but the newest are done
-            }
-            last_store[b] = 0;
+    // the shared tile is about to be modified: pending bulk stores must have read it
+    auto before_write = [&]() {
+        if (store_pending) {
+            if (tid == 0) tma_wait_read<0>();
+            __syncthreads();
+            store_pending = false;
         }
-        __syncthreads();
     };
-    // bring tile `t` of image `img` into the OTHER buffer and make it current; rows the image never contained come back dead
+    // bring tile `t` of image `img` into shared memory; rows the image never contained come back dead
     auto load_tile = [&](const uint8_t* img, uint32_t t, uint32_t n_rows_src) {
-        const uint32_t nb = cur ^ 1u;
-        before_write(nb);
+        __syncthreads();  // every thread is done with the previous content
         if (tid == 0) {
+            tma_wait_read<0>();
             mbar_arrive_expect_tx(&s_bar, p.tile_bytes);
-            tma_load_1d(tile_ptr(nb), img + size_t(t) * p.tile_bytes, p.tile_bytes, &s_bar);
+            tma_load_1d(s_tile, img + size_t(t) * p.tile_bytes, p.tile_bytes, &s_bar);
         }
         mbar_wait(&s_bar, phase);
         phase ^= 1u;
-        cur = nb;
+        store_pending = false;
         if (size_t(t + 1) * kTileRows > n_rows_src) {
-            uint8_t* al = alive_ptr(cur);
 #pragma unroll
-            for (int k = 0; k < kGenericRowsPerThread; ++k) {
+            for (int k = 0; k < kRows; ++k) {
                 const uint32_t r = tid + k * kGenericBlock;
-                if (t * kTileRows + r >= n_rows_src) al[r] = 0;
+                if (t * kTileRows + r >= n_rows_src) s_alive[r] = 0;
             }
         }
     };
@@ -149,11 +168,10 @@ __global__ void __launch_bounds__(kGenericBlock) k_generic_program(const __grid_
         fence_proxy_async();  // generic-proxy writes of this thread are visible to the bulk (async-proxy) store
         __syncthreads();
         if (tid == 0) {
-            tma_store_1d(img + size_t(t) * p.tile_bytes, tile_ptr(cur), p.tile_bytes);
+            tma_store_1d(img + size_t(t) * p.tile_bytes, s_tile, p.tile_bytes);
             tma_commit();
         }
-        n_stores += 1;
-        last_store[cur] = n_stores;
+        store_pending = true;
     };
 
     const uint8_t* first_img = p.arena + ((p.flags & PF_READ_LIVE) ? size_t(0) : (size_t(p.ops[0].image_off256) << 8));
@@ -164,101 +182,138 @@ __global__ void __launch_bounds__(kGenericBlock) k_generic_program(const __grid_
         if (tid == 0) s_next = gridDim.x + atomicAdd(&p.ticket[1], 1u);  // the block's next tile (read after the barrier in load_tile)
         load_tile(first_img, tile, first_rows);
         const uint32_t next_tile = s_next;
+        // first lane of the per-entity hash: only depends on the RollbackOrdered index — once per tile, not per SAVE
+        const unsigned long long row0 = p.order_base + size_t(tile) * kTileRows + tid;
+        uint64_t t0[kRows];
+#pragma unroll
+        for (int k = 0; k < kRows; ++k) t0[k] = sea_order_lane(row0 + uint32_t(k * kGenericBlock));
 
         for (uint32_t i = (p.flags & PF_READ_LIVE) ? 0u : 1u; i < p.n_ops; ++i) {
             const Op& op = p.ops[i];
             if (op.kind == OP_ADVANCE) {
-                const uint32_t nb = cur ^ 1u;
-                before_write(nb);
+                before_write();
                 const float dt = __uint_as_float(op.dt_bits);
-                const uint8_t* al_cur = alive_ptr(cur);
-                uint8_t* al_new = alive_ptr(nb);
+                // systems outside, the thread's rows inside: a system's spec is decoded once for all of them.  A row still
+                // sees the schedule's systems in order, every system sees the entity's presence as it was before the frame,
+                // and despawn commands are applied after the last system.
+                uint32_t m[kRows];
+                bool kill[kRows];
+#pragma unroll
+                for (int k = 0; k < kRows; ++k) { m[k] = s_alive[tid + k * kGenericBlock]; kill[k] = false; }
 #pragma unroll 1
-                for (int k = 0; k < kGenericRowsPerThread; ++k) {
-                    const uint32_t r = tid + k * kGenericBlock;
-                    const uint32_t m = al_cur[r];   // the schedule's systems all see the entity as it was before the frame:
-                    bool kill = false;              // despawn commands are applied after the last system
-                    const uint32_t* old_row = reinterpret_cast<const uint32_t*>(tile_ptr(cur)) + r;
-                    uint32_t* row = reinterpret_cast<uint32_t*>(tile_ptr(nb)) + r;
-                    for (uint32_t w = 0; w < p.words; ++w) row[size_t(w) * kTileRows] = old_row[size_t(w) * kTileRows];
-                    for (uint32_t s = 0; s < p.n_sys; ++s) {
-                        const SysSpec sy = p.sys[s];
-                        if (!row_matches(m, sy.need)) continue;
-                        uint32_t* w0 = row + size_t(sy.plane0) * kTileRows;
-                        switch (sy.id) {
-                        case BGR_SYS_U32_ADD: w0[0] += sy.param; break;
-                        case BGR_SYS_U32_SATSUB_DESPAWN: {
-                            uint32_t v = w0[0];
-                            v = v > sy.param ? v - sy.param : 0u;
-                            w0[0] = v;
-                            kill = kill || v == 0u;
-                            break;
-                        }
-                        case BGR_SYS_U32_STORE_CALL_COUNT: w0[0] = op.call_count + sy.param; break;
-                        case BGR_SYS_DESPAWN_ON_INPUT: {  // param = player handle | value << 8
-                            const uint32_t player = sy.param & 0xFFu, n_players = (op.flags >> 8) & 0xFu;
-                            const uint32_t input = player < n_players && player < 8 ? op.inputs[player] : 0u;
-                            kill = kill || input == (sy.param >> 8);
-                            break;
-                        }
-                        case BGR_SYS_PARTICLES_UPDATE: {
-                            uint32_t* v = row + size_t(sy.plane1) * kTileRows;
-                            uint32_t tx = w0[0], ty = w0[kTileRows], tz = w0[2 * kTileRows], vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
-                            particle_step(tx, ty, tz, vx, vy, vz, dt);
-                            w0[0] = tx; w0[kTileRows] = ty; w0[2 * kTileRows] = tz; v[0] = vx; v[kTileRows] = vy; v[2 * kTileRows] = vz;
-                            break;
-                        }
-                        case BGR_SYS_PARTICLES_DESPAWN: {
-                            uint64_t ttl = (uint64_t(w0[kTileRows]) << 32) | w0[0];
-                            ttl -= 1;
-                            w0[0] = uint32_t(ttl); w0[kTileRows] = uint32_t(ttl >> 32);
-                            kill = kill || ttl == 0;
-                            break;
-                        }
-                        case BGR_SYS_BOX_MOVE: {
-                            float* t = reinterpret_cast<float*>(w0);
-                            float* v = reinterpret_cast<float*>(row + size_t(sy.plane1) * kTileRows);
-                            float tx = t[0], ty = t[kTileRows], tz = t[2 * kTileRows], vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
-                            const unsigned long long handle = p.order_base + size_t(tile) * kTileRows + r;
-                            const uint32_t n_players = (op.flags >> 8) & 0xFu;
-                            const uint32_t input = handle < n_players && handle < 8 ? op.inputs[handle] : 0u;
-                            box_move_step(tx, ty, tz, vx, vy, vz, dt, input);
-                            t[0] = tx; t[kTileRows] = ty; t[2 * kTileRows] = tz; v[0] = vx; v[kTileRows] = vy; v[2 * kTileRows] = vz;
-                            break;
-                        }
-                        default: break;
-                        }
+                for (uint32_t s = 0; s < p.n_sys; ++s) {
+                    const SysSpec sy = p.sys[s];
+                    uint32_t* w0 = tile_w + sy.plane0 * uint32_t(kTileRows) + tid;
+                    switch (sy.id) {
+                    case BGR_SYS_U32_ADD:
+#pragma unroll
+                        for (int k = 0; k < kRows; ++k)
+                            if (row_matches(m[k], sy.need)) w0[k * kGenericBlock] += sy.param;
+                        break;
+                    case BGR_SYS_U32_SATSUB_DESPAWN:
+#pragma unroll
+                        for (int k = 0; k < kRows; ++k)
+                            if (row_matches(m[k], sy.need)) {
+                                uint32_t v = w0[k * kGenericBlock];
+                                v = v > sy.param ? v - sy.param : 0u;
+                                w0[k * kGenericBlock] = v;
+                                kill[k] = kill[k] || v == 0u;
+                            }
+                        break;
+                    case BGR_SYS_U32_STORE_CALL_COUNT:
+#pragma unroll
+                        for (int k = 0; k < kRows; ++k)
+                            if (row_matches(m[k], sy.need)) w0[k * kGenericBlock] = op.call_count + sy.param;
+                        break;
+                    case BGR_SYS_DESPAWN_ON_INPUT: {  // param = player handle | value << 8
+                        const uint32_t player = sy.param & 0xFFu, n_players = (op.flags >> 8) & 0xFu;
+                        const uint32_t input = player < n_players && player < 8 ? op.inputs[player] : 0u;
+                        const bool hit = input == (sy.param >> 8);
+#pragma unroll
+                        for (int k = 0; k < kRows; ++k) kill[k] = kill[k] || (hit && row_matches(m[k], sy.need));
+                        break;
                     }
-                    al_new[r] = kill ? uint8_t(0) : uint8_t(m);
+                    case BGR_SYS_PARTICLES_UPDATE: {
+                        uint32_t* v0 = tile_w + sy.plane1 * uint32_t(kTileRows) + tid;
+#pragma unroll
+                        for (int k = 0; k < kRows; ++k)
+                            if (row_matches(m[k], sy.need)) {
+                                uint32_t* t = w0 + k * kGenericBlock;
+                                uint32_t* v = v0 + k * kGenericBlock;
+                                uint32_t tx = t[0], ty = t[kTileRows], tz = t[2 * kTileRows], vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
+                                particle_step(tx, ty, tz, vx, vy, vz, dt);
+                                t[0] = tx; t[kTileRows] = ty; t[2 * kTileRows] = tz; v[0] = vx; v[kTileRows] = vy; v[2 * kTileRows] = vz;
+                            }
+                        break;
+                    }
+                    case BGR_SYS_PARTICLES_DESPAWN:
+#pragma unroll
+                        for (int k = 0; k < kRows; ++k)
+                            if (row_matches(m[k], sy.need)) {
+                                uint32_t* t = w0 + k * kGenericBlock;
+                                uint64_t ttl = (uint64_t(t[kTileRows]) << 32) | t[0];
+                                ttl -= 1;
+                                t[0] = uint32_t(ttl); t[kTileRows] = uint32_t(ttl >> 32);
+                                kill[k] = kill[k] || ttl == 0;
+                            }
+                        break;
+                    case BGR_SYS_BOX_MOVE: {
+                        uint32_t* v0 = tile_w + sy.plane1 * uint32_t(kTileRows) + tid;
+                        const uint32_t n_players = (op.flags >> 8) & 0xFu;
+#pragma unroll
+                        for (int k = 0; k < kRows; ++k)
+                            if (row_matches(m[k], sy.need)) {
+                                float* t = reinterpret_cast<float*>(w0 + k * kGenericBlock);
+                                float* v = reinterpret_cast<float*>(v0 + k * kGenericBlock);
+                                float tx = t[0], ty = t[kTileRows], tz = t[2 * kTileRows], vx = v[0], vy = v[kTileRows], vz = v[2 * kTileRows];
+                                const unsigned long long handle = row0 + uint32_t(k * kGenericBlock);
+                                const uint32_t input = handle < n_players && handle < 8 ? op.inputs[handle] : 0u;
+                                box_move_step(tx, ty, tz, vx, vy, vz, dt, input);
+                                t[0] = tx; t[kTileRows] = ty; t[2 * kTileRows] = tz; v[0] = vx; v[kTileRows] = vy; v[2 * kTileRows] = vz;
+                            }
+                        break;
+                    }
+                    default: break;
+                    }
                 }
-                cur = nb;
+#pragma unroll
+                for (int k = 0; k < kRows; ++k)
+                    if (kill[k]) s_alive[tid + k * kGenericBlock] = 0;
             } else if (op.kind == OP_SAVE) {
                 // the bulk store streams the tile to the frame's slot while the threads hash their rows out of it
                 if (!(op.flags & OPF_NO_STORE)) store_tile(p.arena + (size_t(op.image_off256) << 8), tile);
-                const uint8_t* al = alive_ptr(cur);
-                uint32_t m[kGenericRowsPerThread];
-                uint64_t t0[kGenericRowsPerThread];
+                uint32_t m[kRows];
                 uint32_t n_alive = 0, bad = 0;
 #pragma unroll
-                for (int k = 0; k < kGenericRowsPerThread; ++k) {
-                    const uint32_t r = tid + k * kGenericBlock;
-                    m[k] = al[r];
+                for (int k = 0; k < kRows; ++k) {
+                    m[k] = s_alive[tid + k * kGenericBlock];
                     n_alive += m[k] & 1u;
-                    t0[k] = sea_order_lane(p.order_base + size_t(tile) * kTileRows + r);
                 }
                 const unsigned full = 0xffffffffu;
                 unsigned int* a = &s_acc[op.save_index * kAccStride * 2];
 #pragma unroll 1
-                for (uint32_t c = 0; c < p.n_hash; ++c) {  // one checksummed column at a time: one copy of the hash code
+                for (uint32_t c = 0; c < p.n_hash; ++c) {  // one checksummed column at a time
                     const HashSpec hs = p.hash[c];
+                    const uint32_t* col = tile_w + (hs.first_plane + (hs.off >> 2)) * uint32_t(kTileRows) + tid;
                     uint64_t hx = 0;
+                    // the common element shapes (whole u32 / f32 / u64 fields, 4..16 bytes) inline and branch-free per
+                    // row; anything else through the one out-of-line copy of the general hash.  The switch is uniform.
+                    const uint32_t shape = ((hs.off | hs.len) & 3u) == 0u ? hs.len >> 2 : 0u;
+                    switch (shape) {
+                    case 1: hash_words_column<1, kRows, kGenericBlock>(col, m, hs.absent, hs.finite, t0, hx, bad); break;
+                    case 2: hash_words_column<2, kRows, kGenericBlock>(col, m, hs.absent, hs.finite, t0, hx, bad); break;
+                    case 3: hash_words_column<3, kRows, kGenericBlock>(col, m, hs.absent, hs.finite, t0, hx, bad); break;
+                    case 4: hash_words_column<4, kRows, kGenericBlock>(col, m, hs.absent, hs.finite, t0, hx, bad); break;
+                    default: {
+                        const uint32_t* base = tile_w + hs.first_plane * uint32_t(kTileRows) + tid;
 #pragma unroll
-                    for (int k = 0; k < kGenericRowsPerThread; ++k) {
-                        if (!row_matches(m[k], hs.absent)) continue;  // Query<(&RollbackId, &T)>: exists and has the component
-                        const uint32_t* col = reinterpret_cast<const uint32_t*>(tile_ptr(cur)) + size_t(hs.first_plane) * kTileRows + tid + k * kGenericBlock;
-                        if (hs.finite)
-                            for (uint32_t q = 0; q + 4 <= hs.len; q += 4) bad |= f32_bits_nonfinite(col[size_t((hs.off + q) >> 2) * kTileRows]);
-                        hx ^= sea_hash_entity(t0[k], hash_row_range(col, hs.off, hs.len));
+                        for (int k = 0; k < kRows; ++k) {
+                            if (!row_matches(m[k], hs.absent)) continue;  // Query<(&RollbackId, &T)>: exists and has the component
+                            if (hs.finite)
+                                for (uint32_t q = 0; q + 4 <= hs.len; q += 4) bad |= f32_bits_nonfinite(base[k * kGenericBlock + ((hs.off + q) >> 2) * uint32_t(kTileRows)]);
+                            hx ^= sea_hash_entity(t0[k], hash_row_range(base + k * kGenericBlock, hs.off, hs.len));
+                        }
+                    }
                     }
                     const uint32_t lo = __reduce_xor_sync(full, uint32_t(hx)), hi = __reduce_xor_sync(full, uint32_t(hx >> 32));
                     if (lane == 0) { atomicXor(&a[2 * hs.slot], lo); atomicXor(&a[2 * hs.slot + 1], hi); }
