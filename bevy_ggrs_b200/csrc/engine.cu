@@ -219,8 +219,8 @@ struct bgr_engine {
     bool bundle_static_ck = false;  // both columns checksummed with the finite assertion: fully specialised kernel
     // generic one-launch program (generic_program.cuh): any schema whose tile fits shared memory + the compiled systems
     bool generic_ok = false;
-    int generic_bps[2] = {0, 0};    // resident blocks per SM of k_generic_program<256> / <512> (occupancy query, cached)
-    int tune_generic_block = 0;     // 0 auto, 256 / 512 force
+    int generic_bps[4] = {0, 0, 0, 0};  // resident blocks per SM of k_generic_program<64 | 128 | 256 | 512> (occupancy query, cached)
+    int tune_generic_block = 0;     // 0 = 128; 64 / 256 / 512 force
     int tune_passive_early = -1;    // -1: early passive stores for single-wave grids (auto); 0 never; 1 always
     int tune_sub = 0;               // 128: the 128-row work-item variant of the fused kernel (experiment; default: whole tiles)
     int tune_stagger_ns = 800;      // start-of-grid phase stagger between the resident blocks of an SM (synchronous launches; measured -1.3 %)
@@ -784,23 +784,21 @@ int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
     }
     std::memcpy(gp.ops, pg.ops, sizeof(Op) * pg.n_ops);
     const size_t smem = size_t((e->tile_bytes + 127u) & ~127u);
-    if (e->generic_bps[0] == 0) {
-        if (smem > 48 * 1024) {
-            CUDA_TRY(cudaFuncSetAttribute(k_generic_program<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-            CUDA_TRY(cudaFuncSetAttribute(k_generic_program<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
-        }
+    // rows of a tile per thread: 8 (64 threads per tile), 4 (128), 2 (256) or 1 (512).  More rows per thread = more
+    // independent hash chains interleaved in one warp; measured (scripts/gpu_generic_block.sh): see DESIGN.md
+    const int block = e->tune_generic_block == 64 || e->tune_generic_block == 256 || e->tune_generic_block == 512 ? e->tune_generic_block : 128;
+    const int vi = block == 64 ? 0 : block == 128 ? 1 : block == 256 ? 2 : 3;
+    const void* fn = vi == 0 ? (const void*)k_generic_program<64> : vi == 1 ? (const void*)k_generic_program<128>
+                   : vi == 2 ? (const void*)k_generic_program<256> : (const void*)k_generic_program<512>;
+    if (e->generic_bps[vi] == 0) {
+        if (smem > 48 * 1024) CUDA_TRY(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_generic_program<256>, 256, smem));
-        e->generic_bps[0] = std::max(1, nb);
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_generic_program<512>, 512, smem));
-        e->generic_bps[1] = std::max(1, nb);
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, block, smem));
+        e->generic_bps[vi] = std::max(1, nb);
     }
-    // few tiles per SM: one row per thread (512 threads per tile) doubles the warps that hide each other's latency
-    const bool wide = e->tune_generic_block == 512 || (e->tune_generic_block == 0 && gp.n_tiles < 4u * uint32_t(e->num_sms));
-    const int bps = e->generic_bps[wide ? 1 : 0];
-    const uint32_t grid = std::max(1u, std::min(gp.n_tiles, uint32_t(e->num_sms * bps)));
-    if (wide) k_generic_program<512><<<grid, 512, smem, e->stream>>>(gp);
-    else k_generic_program<256><<<grid, 256, smem, e->stream>>>(gp);
+    const uint32_t grid = std::max(1u, std::min(gp.n_tiles, uint32_t(e->num_sms * e->generic_bps[vi])));
+    void* args[] = {&gp};
+    CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, e->stream));
     CUDA_TRY(cudaGetLastError());
     e->launches += 1;
     return BGR_OK;

@@ -282,14 +282,14 @@ def test_pipelined_submits_overlap_without_observable_change(monkeypatch, tilede
             assert np.array_equal(pe[1].astype(bool), m) and np.array_equal(pe[0][m], po[0][m])
 
 
-@pytest.mark.parametrize("block", ["256", "512"])
+@pytest.mark.parametrize("block", ["64", "128", "256", "512"])
 @pytest.mark.parametrize("n,d,ticks", [(257, 3, 14), (10_000, 8, 12)])
 def test_particles_world_on_the_generic_program_matches_oracle(monkeypatch, n, d, ticks, block):
     """BGR_TUNE_BUNDLE=0 takes the specialised particles kernel out: the same world runs on the generic one-launch
     program (shared-memory tile, systems and hashes driven by the registration) and must match the oracle bit for bit,
     including despawns inside the window and the passive Transform planes of every snapshot."""
     monkeypatch.setenv("BGR_TUNE_BUNDLE", "0")
-    monkeypatch.setenv("BGR_TUNE_GENERIC_BLOCK", block)   # two rows per thread (large worlds) / one row per thread (small worlds)
+    monkeypatch.setenv("BGR_TUNE_GENERIC_BLOCK", block)   # 8 / 4 (default) / 2 / 1 rows of a tile per thread
     r = run_particles_synctest_pair(n, d, ticks, seed=5, ttl_lo=3, ttl_hi=40, peek_check=True, z_fraction=0.3)
     assert r["fused"] and r["launches"] == ticks
     assert r["checksums_equal"] and r["state_equal"] and r["peek_equal"]
