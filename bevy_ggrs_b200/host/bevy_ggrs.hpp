@@ -16,6 +16,7 @@
 // A Rust panic becomes a C++ exception carrying the same text (`Panic`).  The "World" is the engine:
 // columns and the snapshot ring live in HBM, this layer holds no component data.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <functional>
@@ -104,7 +105,31 @@ public:
 
     // ---- RollbackApp (rollback_app.rs:31-248) ----
     template <class T> App& rollback_component_with_copy() { return register_component<T>(BGR_STRATEGY_COPY); }
-    template <class T> App& rollback_component_with_clone() { return register_component<T>(BGR_STRATEGY_CLONE); }
+    // Clone of plain bytes -> an HBM column.  Clone of anything else (bevy's Sprite holds an Arc asset handle,
+    // particles.rs:191) -> the type stays on the host in a side table keyed by row (= RollbackOrdered index, never
+    // reused) and is rolled back there by the same request vectors: Save clones the table into a per-frame snapshot
+    // (component_snapshot.rs:66-90), Load replaces it by a clone of the frame's snapshot = the four-way match of
+    // component_snapshot.rs:99-115 for every entity at once; whether the entity exists is the alive mask in HBM.
+    template <class T> App& rollback_component_with_clone() {
+        if constexpr (std::is_trivially_copyable<T>::value) return register_component<T>(BGR_STRATEGY_CLONE);
+        else { host_cols_[std::type_index(typeid(T))] = std::make_unique<HostColumn<T>>(); return *this; }
+    }
+    // commands.entity(row).insert(value) / .remove::<T>() / Query<&T> for a host-side component
+    template <class T> void host_insert(uint32_t row, T value) {
+        if (!entity_exists(row)) throw Panic(BGR_ERR_INVALID_ARGUMENT, "entity of row " + std::to_string(row) + " does not exist");
+        host_col<T>().live.insert_or_assign(row, std::move(value));
+    }
+    template <class T> void host_remove(uint32_t row) { host_col<T>().live.erase(row); }
+    template <class T> const T* host_get(uint32_t row) {
+        auto& live = host_col<T>().live;
+        auto it = live.find(row);
+        return it != live.end() && entity_exists(row) ? &it->second : nullptr;
+    }
+    template <class T> std::vector<ggrs::Frame> host_snapshot_frames() {
+        std::vector<ggrs::Frame> f;
+        for (auto& kv : host_col<T>().snaps) f.push_back(kv.first);
+        return f;
+    }
     // a component single entities may lose / regain inside the window: Option<&mut T> in ComponentSnapshotPlugin::load
     // (component_snapshot.rs:99-115); see remove<T>() / insert<T>() below
     template <class T> App& rollback_optional_component_with_copy() { return register_component<T>(BGR_STRATEGY_COPY | BGR_STRATEGY_OPTIONAL); }
@@ -300,6 +325,7 @@ private:
         check(bgr_handle_requests(engine_, &info, reqs.data(), uint32_t(reqs.size()), last_checksums_.data(), BGR_MAX_REQUESTS, &n));
         last_checksums_.resize(n);
         if (!resources_.empty()) handle_resource_requests(requests);
+        if (!host_cols_.empty()) handle_host_component_requests(requests);
         for (auto& cs : last_checksums_)  // cell.save(frame, None, checksum) (:231-236)
             save_cell(cs.frame, (static_cast<unsigned __int128>(cs.hi) << 64) | cs.lo);
     }
@@ -330,6 +356,65 @@ private:
             it = alive ? std::next(it) : res_store_.erase(it);
         }
     }
+
+    // host-side half of handle_requests for non-POD components (see rollback_component_with_clone)
+    struct HostColumnBase {
+        virtual ~HostColumnBase() = default;
+        virtual void save(ggrs::Frame f) = 0;
+        virtual void load(ggrs::Frame f) = 0;
+        virtual void prune(const std::vector<uint8_t>& alive, const std::vector<int32_t>& kept_frames) = 0;
+        virtual bool empty() const = 0;
+    };
+    template <class T> struct HostColumn : HostColumnBase {
+        std::map<uint32_t, T> live;
+        std::map<ggrs::Frame, std::map<uint32_t, T>> snaps;
+        void save(ggrs::Frame f) override { snaps[f] = live; }  // T's copy constructor is its Clone
+        void load(ggrs::Frame f) override {
+            auto it = snaps.find(f);
+            if (it == snaps.end())  // mod.rs:209-212
+                throw Panic(BGR_ERR_NO_SNAPSHOT, "Could not rollback to " + std::to_string(f) + ": no snapshot at that moment could be found.");
+            live = it->second;
+        }
+        void prune(const std::vector<uint8_t>& alive, const std::vector<int32_t>& kept) override {
+            for (auto it = live.begin(); it != live.end();)  // the components of despawned entities are gone with them
+                it = it->first < alive.size() && alive[it->first] ? std::next(it) : live.erase(it);
+            for (auto it = snaps.begin(); it != snaps.end();)  // what the engine's ring discarded (mod.rs:144-199)
+                it = std::find(kept.begin(), kept.end(), it->first) != kept.end() ? std::next(it) : snaps.erase(it);
+        }
+        bool empty() const override { return live.empty(); }
+    };
+    template <class T> HostColumn<T>& host_col() {
+        auto it = host_cols_.find(std::type_index(typeid(T)));
+        if (it == host_cols_.end()) throw Panic(BGR_ERR_INVALID_ARGUMENT, std::string("not registered for rollback: ") + typeid(T).name());
+        return static_cast<HostColumn<T>&>(*it->second);
+    }
+    bool entity_exists(uint32_t row) {
+        finish();
+        uint32_t rows = 0;
+        check(bgr_row_count(engine_, &rows));
+        if (row >= rows) return false;
+        uint8_t a = 0;
+        check(bgr_read_alive(engine_, row, 1, &a));
+        return a != 0;
+    }
+    void handle_host_component_requests(const std::vector<ggrs::GgrsRequest>& requests) {
+        for (const auto& r : requests) {
+            if (r.kind == ggrs::GgrsRequest::SaveGameState) for (auto& c : host_cols_) c.second->save(r.frame);
+            else if (r.kind == ggrs::GgrsRequest::LoadGameState) for (auto& c : host_cols_) c.second->load(r.frame);
+        }
+        std::vector<uint8_t> alive;
+        bool any = false;
+        for (auto& c : host_cols_) any = any || !c.second->empty();
+        if (any) {
+            uint32_t rows = 0;
+            check(bgr_row_count(engine_, &rows));
+            alive.resize(rows);
+            if (rows) check(bgr_read_alive(engine_, 0, rows, alive.data()));
+        }
+        const std::vector<int32_t> kept = snapshot_frames();
+        for (auto& c : host_cols_) c.second->prune(alive, kept);
+    }
+    std::map<std::type_index, std::unique_ptr<HostColumnBase>> host_cols_;
 
     struct PendingCol { std::type_index type; std::string name; uint32_t bytes, strategy; };
     using ResourceMap = std::map<std::type_index, std::vector<uint8_t>>;

@@ -29,6 +29,7 @@ from dataclasses import dataclass, field
 from typing import Callable, Dict, List, Optional, Sequence
 
 from . import capi
+from .host_components import HostComponents
 from .session import (ADVANCE, LOAD, SAVE, GgrsError, MismatchedChecksum, P2PTraceSession, Request,
                       SyncTestSession)
 
@@ -137,6 +138,8 @@ class App:
         self._res_systems: List[Callable] = []
         self._res_store: Dict[int, Dict[str, bytes]] = {}
         self._res_frame = 0
+        # host-side side table for rollback components that are not plain bytes (Sprite: particles.rs:191)
+        self.host_components = HostComponents(backend)
 
     # ---- App ----
     def add_plugins(self, plugin) -> "App":
@@ -186,7 +189,12 @@ class App:
     def rollback_component_with_copy(self, type_name: str, size_of: int) -> int:
         return self.world.rollback_component(type_name, size_of, capi.BGR_STRATEGY_COPY)
 
-    def rollback_component_with_clone(self, type_name: str, size_of: int) -> int:
+    def rollback_component_with_clone(self, type_name: str, size_of: Optional[int] = None, clone=None):
+        """``size_of`` bytes of plain data -> an HBM column (returns its index).  ``size_of=None``: the type is Clone but
+        not plain bytes (``Sprite`` holds an ``Arc`` handle, particles.rs:191) -> it stays on the host in the side table
+        (host_components.py) and is rolled back there by the same request vectors; returns the ``HostColumn``."""
+        if size_of is None:
+            return self.host_components.register(type_name, **({"clone": clone} if clone else {}))
         return self.world.rollback_component(type_name, size_of, capi.BGR_STRATEGY_CLONE)
 
     def rollback_optional_component_with_copy(self, type_name: str, size_of: int) -> int:
@@ -291,6 +299,8 @@ class App:
         checksums = self.world.handle_requests(inner.info(), requests)
         if self._res_registered:
             checksums = self._handle_resource_requests(requests, checksums)
+        if self.host_components.columns:
+            self.host_components.handle_requests(requests)
         # cell.save(frame, None, checksum) (:236)
         for frame, cs in checksums:
             inner.save_cell(frame, cs)

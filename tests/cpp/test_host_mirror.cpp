@@ -384,6 +384,48 @@ static void removed_session_resets_frame_resources() {
     EXPECT(app.local_players().handles.empty());
 }
 
+// particles.rs:191 `rollback_component_with_clone::<Sprite>()`: Sprite holds an Arc asset handle — Clone, not plain
+// bytes.  It stays on the host (side table) and is rolled back by the same request vectors as the HBM columns.
+struct Sprite {
+    std::shared_ptr<int> image;  // the Arc
+    int id;
+};
+static void non_pod_component_rolls_back_on_the_host_side_table() {
+    std::printf("non_pod_component_rolls_back_on_the_host_side_table\n");
+    App app(16, 8);
+    base_synctest_app(app, 2);
+    app.rollback_component_with_copy<Health>().checksum_component_with_hash<Health>();
+    app.rollback_component_with_clone<Sprite>();   // not trivially copyable -> host side table
+    app.add_systems(GgrsSchedule{}, System{BGR_SYS_U32_SATSUB_DESPAWN, {0}, {0, 1}});
+    auto image = std::make_shared<int>(7);
+    app.add_systems(Startup{}, [&](App& a) {
+        a.write<Health>(a.spawn(3), {Health{1000}, Health{1000}, Health{9}});   // row 2 dies in frame 9
+        for (uint32_t r = 0; r < 3; ++r) a.host_insert<Sprite>(r, Sprite{image, int(10 + r)});
+    });
+    bool mismatch = false;
+    app.add_observer([&](const SyncTestMismatch&) { mismatch = true; });
+    for (int i = 0; i < 6; ++i) app.update();
+    EXPECT(!mismatch);
+    EXPECT(app.host_get<Sprite>(0) && app.host_get<Sprite>(0)->id == 10 && app.host_get<Sprite>(2)->id == 12);
+    EXPECT(app.host_get<Sprite>(1)->image.get() == image.get());      // clones share the asset
+    EXPECT(image.use_count() > 4);                                     // ... and the snapshots hold clones
+    EXPECT(app.host_snapshot_frames<Sprite>() == [&] { auto f = app.snapshot_frames(); std::sort(f.begin(), f.end()); return f; }());
+    // an edit outside GgrsSchedule is undone by the next tick's Load of an older frame (any rollback component behaves so)
+    app.host_remove<Sprite>(1);
+    app.host_insert<Sprite>(0, Sprite{image, 99});
+    EXPECT(!app.host_get<Sprite>(1) && app.host_get<Sprite>(0)->id == 99);
+    app.update();
+    EXPECT(app.host_get<Sprite>(1) && app.host_get<Sprite>(1)->id == 11 && app.host_get<Sprite>(0)->id == 10);
+    // the entity of row 2 despawns inside the schedule (Health runs out): its Sprite goes with it
+    for (int i = 0; i < 8; ++i) app.update();
+    EXPECT(app.active_count() == 2);
+    EXPECT(!app.host_get<Sprite>(2) && app.host_get<Sprite>(0) && app.host_get<Sprite>(1));
+    bool threw = false;
+    try { app.host_insert<Sprite>(2, Sprite{image, 1}); } catch (const Panic&) { threw = true; }
+    EXPECT(threw);                                                      // no such entity any more
+    EXPECT(!mismatch);
+}
+
 int main(int argc, char** argv) {
     if (argc > 1 && std::string(argv[1]) == "--no-gpu") {
         // the library must refuse loudly (no CPU fallback) when no device is usable
@@ -411,6 +453,7 @@ int main(int argc, char** argv) {
         spectator_session_only_advances();
         removed_session_resets_frame_resources();
         hierarchy_child_deleted_inside_the_schedule();
+        non_pod_component_rolls_back_on_the_host_side_table();
     } catch (const std::exception& e) {
         std::printf("unexpected exception: %s\n", e.what());
         return 2;
