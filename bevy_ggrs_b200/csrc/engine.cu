@@ -205,7 +205,7 @@ struct bgr_engine {
     unsigned int* d_tile_cnt = nullptr;
     bool tiledep_chain = false;   // the last operation enqueued on the main stream was a PF_TILE_SIGNAL launch
     uint32_t tiledep_seq = 0, tiledep_tiles = 0;
-    int tune_grid = 0;            // experiment: cap the fused kernel's grid (0 = SMs x resident blocks)
+    int tune_grid = 0;            // experiment / tests: cap the one-launch kernels' grid (0 = SMs x resident blocks)
     int tune_prefetch = 1;        // L2 prefetch of the next tile's active planes
     int tune_pdl = 0;             // programmatic dependent launch between consecutive fused kernels (measured: +0.8 % at 1M, -14 % at 100k -> off)
     int tune_dynamic = 1;         // dynamic tile scheduling in the fused kernel (measured +5% over a static stride)
@@ -796,7 +796,8 @@ int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, fn, block, smem));
         e->generic_bps[vi] = std::max(1, nb);
     }
-    const uint32_t grid = std::max(1u, std::min(gp.n_tiles, uint32_t(e->num_sms * e->generic_bps[vi])));
+    uint32_t grid = std::max(1u, std::min(gp.n_tiles, uint32_t(e->num_sms * e->generic_bps[vi])));
+    if (e->tune_grid > 0) grid = std::min(grid, uint32_t(e->tune_grid));  // tests: several tiles per block on small worlds
     void* args[] = {&gp};
     CUDA_TRY(cudaLaunchKernel(fn, dim3(grid), dim3(block), args, smem, e->stream));
     CUDA_TRY(cudaGetLastError());

@@ -116,6 +116,35 @@ def test_synctest_shaped_run_with_presence_changes_between_ticks(flags):
     assert 0 < orc.read_alive(0, n).sum() < n  # Health ran out for some entities inside the run
 
 
+@pytest.mark.parametrize("grid", ["2", "5"])
+def test_presence_world_with_many_tiles_per_block(monkeypatch, grid):
+    """40 tiles on 2 / 5 blocks of the generic program (BGR_TUNE_GRID): the per-row presence bits, the optional columns'
+    checksums and the despawns must come out like the oracle's when a block walks through many tiles."""
+    monkeypatch.setenv("BGR_TUNE_GRID", grid)
+    n, d = 20_000, 3
+    SESS = (capi.BGR_SESSION_SYNCTEST, 8, d, 0)
+    eng, orc, cols = _pair(n)
+    score, health, tag = cols
+    both = lambda f, *a: [getattr(w, f)(*a) for w in (eng, orc)]
+    for r in range(0, n, 37):
+        both("remove_component", score, r)
+    frame = 0
+    for tick in range(9):
+        reqs = []
+        if tick >= d:
+            reqs.append(Request(LOAD, frame - d))
+            for k in range(d):
+                reqs += [Request(ADVANCE, 0, [0]), Request(SAVE, frame - d + k + 1)] if k < d - 1 else [Request(ADVANCE, 0, [0])]
+        reqs += [Request(SAVE, frame), Request(ADVANCE, 0, [0])]
+        l0 = eng.launch_count()
+        a, b = both("handle_requests", SESS, reqs)
+        assert a == b, f"tick {tick}"
+        assert eng.launch_count() - l0 == 1 and eng.last_path_fused()
+        frame += 1
+    _same(eng, orc, cols, n)
+    assert 0 < orc.read_alive(0, n).sum() < n
+
+
 def test_presence_api_errors():
     eng, orc, (score, health, tag) = _pair(10)
     with pytest.raises(BgrError):
