@@ -128,6 +128,7 @@ PROTOTYPES = {
     "bgr_launch_count": (C.c_int, [C.c_void_p, u64p]),
     "bgr_slot_bytes": (C.c_int, [C.c_void_p, u64p]),
     "bgr_last_path": (C.c_int, [C.c_void_p, u32p]),
+    "bgr_generic_specialised": (C.c_int, [C.c_void_p, u32p]),
     "bgr_synchronize": (C.c_int, [C.c_void_p]),
     "bgr_stream": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "bgr_trace_enable": (C.c_int, [C.c_void_p, C.c_uint32]),

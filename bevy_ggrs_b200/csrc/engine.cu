@@ -26,6 +26,7 @@
 #include "shard_group.hpp"
 #include "tma_copy.cuh"
 #include "generic_program.cuh"
+#include "jit.hpp"
 
 using namespace bgr;
 
@@ -220,6 +221,9 @@ struct bgr_engine {
     // generic one-launch program (generic_program.cuh): any schema whose tile fits shared memory + the compiled systems
     bool generic_ok = false;
     int generic_bps[4] = {0, 0, 0, 0};  // resident blocks per SM of k_generic_program<64 | 128 | 256 | 512> (occupancy query, cached)
+    int tune_jit = 1;               // 0 never, 1 worlds of >= 16k entities, 2 always: NVRTC-specialised generic program (jit.hpp)
+    int tune_jit_rows = 4;          // rows of a tile per thread in the specialised kernel (1, 2, 4; measured: scripts/gpu_jit.sh)
+    JitKernel jit;                  // fn == nullptr: the interpreter kernel runs
     int tune_generic_block = 0;     // 0 = 128; 64 / 256 / 512 force
     int tune_passive_early = -1;    // -1: early passive stores for single-wave grids (auto); 0 never; 1 always
     int tune_sub = 0;               // 128: the 128-row work-item variant of the fused kernel (experiment; default: whole tiles)
@@ -738,27 +742,10 @@ int run_stepwise(bgr_engine* e, const Program& pg, uint32_t buf) {
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// launch: generic one-launch program (any schema, compiled systems; generic_program.cuh)
-// ---------------------------------------------------------------------------------------------
-int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
-    e->main_dirty = true;
-    e->tiledep_chain = false;
-    GenericParams gp;
-    std::memset(&gp, 0, sizeof gp);
-    gp.arena = e->arena;
-    gp.order_base = e->cfg.order_base;
-    gp.accum = e->d_accum_c[0];
-    gp.ticket = e->d_ticket_c[0];
-    gp.out = e->d_out[buf];
-    gp.seq = e->seq;
-    if (e->d_trace && e->seq - e->trace_first_seq < e->trace_cap) gp.trace = e->d_trace + (e->seq - e->trace_first_seq) * 4;
-    gp.words = e->words; gp.tile_bytes = e->tile_bytes;
-    gp.n_ops = pg.n_ops; gp.n_saves = pg.n_saves;
-    gp.n_tiles = std::max(1u, e->tiles_for(pg.max_rows));
-    gp.live_rows = pg.live_rows;
-    if (!pg.first_is_load) gp.flags |= PF_READ_LIVE;
-    if (pg.has_load || pg.has_advance) gp.flags |= PF_WRITE_LIVE_ACTIVE;
+// the registration as the generic program's spec tables (parameter block of the interpreter, prelude of the JIT kernel)
+void fill_generic_specs(const bgr_engine* e, GenericParams& gp) {
+    gp.n_hash = 0;
+    gp.n_sys = 0;
     for (const Column& c : e->cols)
         if (c.hash_kind != BGR_HASH_NONE) {
             HashSpec& h = gp.hash[gp.n_hash++];
@@ -782,7 +769,80 @@ int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
         default: break;
         }
     }
+}
+
+// NVRTC specialisation of the generic program for this registration (jit.hpp, generic_program_jit.cuh); called by bgr_build
+void jit_specialise(bgr_engine* e) {
+    e->jit = JitKernel{};
+    if (!e->generic_ok || e->tune_jit == 0 || (e->bundle_particles && e->tune_bundle)) return;  // the bundle has its own kernel
+    if (e->tune_jit == 1 && e->cfg.max_entities < 16384) return;  // small worlds: a tick is launch latency, not worth a compile
+    GenericParams gp;
+    std::memset(&gp, 0, sizeof gp);
+    fill_generic_specs(e, gp);
+    if (e->words < 1 || e->words > 24) return;  // the row has to fit the register file
+    for (uint32_t c = 0; c < gp.n_hash; ++c)   // whole-word byte ranges only (every POD of u32 / f32 / u64 fields)
+        if (((gp.hash[c].off | gp.hash[c].len) & 3u) != 0u || gp.hash[c].len < 4 || gp.hash[c].len > 64) return;
+    const int rows = e->tune_jit_rows == 1 || e->tune_jit_rows == 2 ? e->tune_jit_rows : 4;
+    const int threads = int(kTileRows) / rows;
+    std::string pre;
+    auto def = [&](const char* name, unsigned long long v) { pre += "#define " + std::string(name) + " " + std::to_string(v) + "\n"; };
+    def("BGR_SYS_PARTICLES_UPDATE", BGR_SYS_PARTICLES_UPDATE); def("BGR_SYS_PARTICLES_DESPAWN", BGR_SYS_PARTICLES_DESPAWN);
+    def("BGR_SYS_BOX_MOVE", BGR_SYS_BOX_MOVE); def("BGR_SYS_U32_ADD", BGR_SYS_U32_ADD);
+    def("BGR_SYS_U32_SATSUB_DESPAWN", BGR_SYS_U32_SATSUB_DESPAWN); def("BGR_SYS_U32_STORE_CALL_COUNT", BGR_SYS_U32_STORE_CALL_COUNT);
+    def("BGR_SYS_PARTICLES_SPAWN", BGR_SYS_PARTICLES_SPAWN); def("BGR_SYS_DESPAWN_ON_INPUT", BGR_SYS_DESPAWN_ON_INPUT);
+    def("BGR_TILE_ROWS", kTileRows);
+    def("BGR_JIT_WORDS", e->words); def("BGR_JIT_ROWS", rows);
+    def("BGR_JIT_MINB", rows == 1 ? 1 : rows == 2 ? (e->words <= 8 ? 3 : 2) : (e->words <= 8 ? 4 : 2));
+    def("BGR_JIT_NSYS", gp.n_sys); def("BGR_JIT_NHASH", gp.n_hash);
+    auto u = [](uint32_t v) { return std::to_string(v) + "u"; };
+    pre += "#define BGR_JIT_SYS_LIST ";
+    for (uint32_t i = 0; i < gp.n_sys; ++i) {
+        const SysSpec& y = gp.sys[i];
+        pre += "{" + u(y.id) + "," + u(y.plane0) + "," + u(y.plane1) + "," + u(y.need) + "," + u(y.param) + "}, ";
+    }
+    pre += "{0u,0u,0u,0u,0u}\n#define BGR_JIT_HASH_LIST ";
+    for (uint32_t i = 0; i < gp.n_hash; ++i) {
+        const HashSpec& h = gp.hash[i];
+        pre += "{" + u(h.first_plane) + "," + u(h.off) + "," + u(h.len) + "," + u(h.finite) + "," + u(h.slot) + "," + u(h.absent) + "}, ";
+    }
+    pre += "{0u,0u,0u,0u,0u,0u}\n";
+    std::string why;
+    if (!jit_generic_program(pre, threads, reinterpret_cast<const void*>(&bgr_abi_version), &e->jit, &why) && std::getenv("BGR_JIT_VERBOSE"))
+        std::fprintf(stderr, "[bevy_ggrs_b200] generic program not specialised, the interpreter kernel runs: %s\n", why.c_str());
+}
+
+// ---------------------------------------------------------------------------------------------
+// launch: generic one-launch program (any schema, compiled systems; generic_program.cuh)
+// ---------------------------------------------------------------------------------------------
+int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
+    e->main_dirty = true;
+    e->tiledep_chain = false;
+    GenericParams gp;
+    std::memset(&gp, 0, sizeof gp);
+    gp.arena = e->arena;
+    gp.order_base = e->cfg.order_base;
+    gp.accum = e->d_accum_c[0];
+    gp.ticket = e->d_ticket_c[0];
+    gp.out = e->d_out[buf];
+    gp.seq = e->seq;
+    if (e->d_trace && e->seq - e->trace_first_seq < e->trace_cap) gp.trace = e->d_trace + (e->seq - e->trace_first_seq) * 4;
+    gp.words = e->words; gp.tile_bytes = e->tile_bytes;
+    gp.n_ops = pg.n_ops; gp.n_saves = pg.n_saves;
+    gp.n_tiles = std::max(1u, e->tiles_for(pg.max_rows));
+    gp.live_rows = pg.live_rows;
+    if (!pg.first_is_load) gp.flags |= PF_READ_LIVE;
+    if (pg.has_load || pg.has_advance) gp.flags |= PF_WRITE_LIVE_ACTIVE;
+    fill_generic_specs(e, gp);
     std::memcpy(gp.ops, pg.ops, sizeof(Op) * pg.n_ops);
+    if (e->jit.fn) {  // the registration's own register-resident kernel
+        uint32_t grid = std::max(1u, std::min(gp.n_tiles, uint32_t(e->num_sms * e->jit.bps)));
+        if (e->tune_grid > 0) grid = std::min(grid, uint32_t(e->tune_grid));
+        void* args[] = {&gp};
+        CUDA_TRY(cudaLaunchKernel(e->jit.fn, dim3(grid), dim3(e->jit.threads), args, 0, e->stream));
+        CUDA_TRY(cudaGetLastError());
+        e->launches += 1;
+        return BGR_OK;
+    }
     const size_t smem = size_t((e->tile_bytes + 127u) & ~127u);
     // rows of a tile per thread: 8 (64 threads per tile), 4 (128), 2 (256) or 1 (512).  More rows per thread = more
     // independent hash chains interleaved in one warp; measured (scripts/gpu_generic_block.sh): see DESIGN.md
@@ -1177,6 +1237,8 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_generic = env_int("BGR_TUNE_GENERIC", 1);
     e->tune_sub = env_int("BGR_TUNE_SUB", 0);
     e->tune_generic_block = env_int("BGR_TUNE_GENERIC_BLOCK", 0);
+    e->tune_jit = env_int("BGR_TUNE_JIT", 1);
+    e->tune_jit_rows = env_int("BGR_TUNE_JIT_ROWS", 4);
     e->tune_passive_early = env_int("BGR_TUNE_PASSIVE_EARLY", -1);
     e->tune_stagger_ns = env_int("BGR_TUNE_STAGGER_NS", 800);
     e->tune_bundle = env_int("BGR_TUNE_BUNDLE", 1);
@@ -1396,6 +1458,7 @@ BGR_API int bgr_build(bgr_engine* e) {
                         sy.id == BGR_SYS_DESPAWN_ON_INPUT);
         e->generic_ok = ok;
     }
+    jit_specialise(e);
     {   // TMA copy kernel: up to six one-tile stages in ~200 KB of shared memory, at least two
         uint32_t st = uint32_t(std::min<size_t>((200u * 1024u) / e->tile_bytes, size_t(kTmaMaxStages)));
         if (env_int("BGR_TUNE_TMA_STAGES", 0) > 0) st = std::min(st, uint32_t(env_int("BGR_TUNE_TMA_STAGES", 0)));
@@ -1737,6 +1800,11 @@ BGR_API int bgr_launch_count(bgr_engine* e, uint64_t* out) {
 BGR_API int bgr_slot_bytes(bgr_engine* e, uint64_t* out) {
     if (!e || !out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
     *out = uint64_t(e->st.n_rows) * (uint64_t(e->words) * 4u + 1u); return BGR_OK;
+}
+BGR_API int bgr_generic_specialised(bgr_engine* e, uint32_t* specialised_out) {
+    if (!e || !specialised_out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");
+    *specialised_out = e->jit.fn ? 1u : 0u;
+    return BGR_OK;
 }
 BGR_API int bgr_last_path(bgr_engine* e, uint32_t* fused_out) {
     if (!e || !fused_out) return fail(BGR_ERR_INVALID_ARGUMENT, "null argument");

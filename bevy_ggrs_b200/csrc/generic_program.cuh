@@ -17,10 +17,16 @@
 // Reference semantics: handle_requests (schedule_systems.rs:170-289) over ComponentSnapshotPlugin::save / load
 // (component_snapshot.rs:66-123), the checksum plugins, and the systems listed in include/bevy_ggrs_b200.h.
 #pragma once
+#ifdef __CUDACC_RTC__  // NVRTC (the engine's run-time specialisation, generic_program_jit.cuh): no host headers
+#include "rtc_prelude.cuh"
+#else
 #include <cuda_runtime.h>
 #include <cstdint>
+#endif
 
+#ifndef __CUDACC_RTC__
 #include "../../include/bevy_ggrs_b200.h"
+#endif  // NVRTC: the engine's generated prelude defines the BGR_SYS_* ids (host function declarations cannot be parsed there)
 #include "kernels.cuh"
 #include "seahash.cuh"
 #include "tma_copy.cuh"

@@ -23,8 +23,12 @@
 //   cksum : component_checksum.rs:67-108, entity_checksum.rs:29-52 (XOR of per-entity seahashes; count of live rows)
 //   systems: examples/stress_tests/particles.rs:272-289 (update_particles, despawn_particles)
 #pragma once
+#ifdef __CUDACC_RTC__  // NVRTC (the engine's run-time specialisation, generic_program_jit.cuh): no host headers
+#include "rtc_prelude.cuh"
+#else
 #include <cuda_runtime.h>
 #include <cstdint>
+#endif
 
 #include "seahash.cuh"
 
@@ -682,6 +686,7 @@ __global__ void __launch_bounds__(SUB / VEC, MINB) k_particles_program(const __g
 // =============================================================================================
 // Stepwise (generic) path: one kernel per request, any registered schema / system list.
 // =============================================================================================
+#ifndef __CUDACC_RTC__  // the run-time specialisation (generic_program_jit.cuh) only needs the structs and helpers
 
 // flat copy of tiles [0, n_tiles) of an image (fallback when the TMA kernel cannot be used);
 // alive bytes of rows >= n_rows_src are forced to 0 (a Load that shrinks the world).
@@ -892,6 +897,8 @@ __global__ void __launch_bounds__(256) k_sys_particles_spawn(uint8_t* img, uint3
     }
 }
 
+#endif  // !__CUDACC_RTC__
+
 // move_cube_system (box_game.rs:154-206), BASELINE config C1.  player handle == RollbackOrdered index.
 // `FRICTION.powf(dt)` is libm on the CPU and CUDA powf here: this is the one system of the path whose f32
 // results are only guaranteed within a tolerance (|d| <= 1e-5 * max(1, |x|), tested), not bit-exact.
@@ -918,6 +925,7 @@ __device__ __forceinline__ void box_move_step(float& tx, float& ty, float& tz, f
     tx = tx < -hw ? -hw : (tx > hw ? hw : tx);
     tz = tz < -hw ? -hw : (tz > hw ? hw : tz);
 }
+#ifndef __CUDACC_RTC__
 __global__ void k_sys_box_move(uint8_t* img, uint32_t words, uint32_t t_plane, uint32_t v_plane, uint32_t n_rows,
                                uint32_t dt_bits, unsigned long long inputs_packed, uint32_t n_players, unsigned long long order_base,
                                uint32_t need) {
@@ -941,5 +949,7 @@ __global__ void __launch_bounds__(256) k_apply_despawns(uint8_t* img, uint32_t w
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += gridDim.x * blockDim.x)
         if (kill[r]) { img[alive_offset(words, r)] = 0; kill[r] = 0; }
 }
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace bgr

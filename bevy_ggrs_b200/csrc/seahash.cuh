@@ -9,7 +9,11 @@
 //   hash of 16 bytes = (order:u64, custom:u64)    (per-entity hash, component_checksum.rs:85-86)
 //   generic byte stream                           (derive(Hash) PODs on the stepwise path)
 #pragma once
+#ifdef __CUDACC_RTC__
+#include "rtc_prelude.cuh"
+#else
 #include <cstdint>
+#endif
 
 #if defined(__CUDACC__)
 #define BGR_HD __host__ __device__ __forceinline__ constexpr

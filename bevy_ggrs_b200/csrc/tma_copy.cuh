@@ -19,8 +19,12 @@
 // systems of SaveWorld (component_checksum.rs:67-108, entity_checksum.rs:29-52) in ONE launch;
 // ComponentSnapshotPlugin::load (component_snapshot.rs:95-123) as the reverse copy.
 #pragma once
+#ifdef __CUDACC_RTC__  // NVRTC (the engine's run-time specialisation, generic_program_jit.cuh): no host headers
+#include "rtc_prelude.cuh"
+#else
 #include <cuda_runtime.h>
 #include <cstdint>
+#endif
 
 #include "kernels.cuh"
 #include "seahash.cuh"
@@ -53,6 +57,7 @@ struct TmaCopyParams {
     HashSpec hash[kMaxHashCols];
 };
 
+#ifndef __CUDACC_RTC__
 __global__ void __launch_bounds__(kTmaBlock, 1) k_image_tma(const __grid_constant__ TmaCopyParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ __align__(8) uint64_t full[kTmaMaxStages], hashed[kTmaMaxStages];
@@ -204,5 +209,7 @@ __global__ void __launch_bounds__(kTmaBlock, 1) k_image_tma(const __grid_constan
     __syncthreads();
     if (s_last && tid == 0) { p.ticket[0] = 0u; p.ticket[1] = 0u; }
 }
+
+#endif  // !__CUDACC_RTC__
 
 }  // namespace bgr

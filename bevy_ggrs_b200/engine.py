@@ -241,6 +241,12 @@ class Engine:
         self._check(self._lib.bgr_last_path(self._h, C.byref(v)))
         return bool(v.value)
 
+    def generic_specialised(self) -> bool:
+        """True if bgr_build compiled this registration's own kernel (NVRTC, csrc/generic_program_jit.cuh)."""
+        v = C.c_uint32()
+        self._check(self._lib.bgr_generic_specialised(self._h, C.byref(v)))
+        return bool(v.value)
+
     def synchronize(self) -> None:
         self._check(self._lib.bgr_synchronize(self._h))
 

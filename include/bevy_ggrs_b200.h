@@ -328,6 +328,10 @@ BGR_API uint32_t bgr_ggrs_time_delta_bits(uint32_t fps, int32_t frame);
 BGR_API int bgr_launch_count(bgr_engine* e, uint64_t* kernels_launched_out);
 BGR_API int bgr_slot_bytes(bgr_engine* e, uint64_t* bytes_out);  /* algorithmic bytes of one frame slot at the current row count */
 BGR_API int bgr_last_path(bgr_engine* e, uint32_t* fused_out);   /* 1 if the last handle_requests used the fused program kernel */
+/* 1 if bgr_build compiled this registration's own kernel (NVRTC specialisation of the generic one-launch program,
+ * csrc/generic_program_jit.cuh): every non-bundle request vector then runs on it; 0 = the interpreter kernel (same results).
+ * Env BGR_TUNE_JIT: 0 never, 1 (default) engines created for >= 16384 entities, 2 always. */
+BGR_API int bgr_generic_specialised(bgr_engine* e, uint32_t* specialised_out);
 BGR_API int bgr_synchronize(bgr_engine* e);
 BGR_API int bgr_stream(bgr_engine* e, void** stream_out);        /* the cudaStream_t the engine launches on (timing events) */
 /* device-side launch trace: 4 x u64 per fused launch after the call, up to `capacity` launches (GPU globaltimer ns):

@@ -143,6 +143,7 @@ extern "C" {
     pub fn bgr_launch_count(e: *mut bgr_engine, kernels_launched_out: *mut u64) -> c_int;
     pub fn bgr_slot_bytes(e: *mut bgr_engine, bytes_out: *mut u64) -> c_int;
     pub fn bgr_last_path(e: *mut bgr_engine, fused_out: *mut u32) -> c_int;
+    pub fn bgr_generic_specialised(e: *mut bgr_engine, specialised_out: *mut u32) -> c_int;
     pub fn bgr_synchronize(e: *mut bgr_engine) -> c_int;
     pub fn bgr_stream(e: *mut bgr_engine, stream_out: *mut *mut c_void) -> c_int;
     pub fn bgr_trace_enable(e: *mut bgr_engine, capacity: u32) -> c_int;

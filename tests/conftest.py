@@ -17,3 +17,14 @@ def pytest_configure(config):
 def oracle_lib():
     from oracle_backend import load_oracle
     return load_oracle()
+
+
+# Worlds that are not the particles bundle run on the generic one-launch program, which exists twice: the interpreter
+# kernel (csrc/generic_program.cuh, schema read from the parameter block, tile in shared memory) and the registration's own
+# kernel compiled by NVRTC at bgr_build (csrc/generic_program_jit.cuh, schema as compile-time constants, rows in
+# registers).  GPU test modules of the generic path opt in with `pytestmark = pytest.mark.usefixtures("generic_kernel")`
+# and then run every test on both.
+@pytest.fixture(params=["interpreter", "jit"])
+def generic_kernel(request, monkeypatch):
+    monkeypatch.setenv("BGR_TUNE_JIT", "0" if request.param == "interpreter" else "2")
+    return request.param

@@ -14,7 +14,7 @@ from bevy_ggrs_b200.plugin import (App, GgrsPlugin, GgrsSchedule, LocalInputs, R
 from bevy_ggrs_b200.session import SyncTestSession
 from oracle_backend import ORC_SYS_RESOURCE_U32_ADD, OracleWorld
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("generic_kernel")]
 SEQ = [0b0001, 0b1000, 0b0101, 0, 0b0010, 0b1010, 0b0100, 0b1001]
 
 

@@ -10,7 +10,7 @@ from bevy_ggrs_b200.engine import Engine
 from bevy_ggrs_b200.session import ADVANCE, LOAD, SAVE, Request
 from oracle_backend import OracleWorld
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("generic_kernel")]
 NOSESS = (capi.BGR_SESSION_NONE, 0, 0, 0)
 OPT = capi.BGR_STRATEGY_OPTIONAL
 
@@ -143,6 +143,23 @@ def test_presence_world_with_many_tiles_per_block(monkeypatch, grid):
         frame += 1
     _same(eng, orc, cols, n)
     assert 0 < orc.read_alive(0, n).sum() < n
+
+
+def test_build_compiles_the_registrations_own_kernel(generic_kernel):
+    """BGR_TUNE_JIT=2: bgr_build hands the registration to NVRTC (csrc/jit.hpp) and every request vector then runs on
+    that kernel; =0: the interpreter kernel.  A registration the specialised kernel does not cover (a checksum over a byte
+    range that is not whole words) keeps the interpreter without failing."""
+    eng, orc, cols = _pair(600)
+    assert eng.generic_specialised() == (generic_kernel == "jit")
+    a, b = [w.handle_requests(NOSESS, [Request(SAVE, 0), Request(ADVANCE, 0, [0]), Request(SAVE, 1)]) for w in (eng, orc)]
+    assert a == b and eng.last_path_fused()
+    eng.close(); orc.close()
+    odd = Engine(max_entities=64, max_depth=4)
+    c = odd.rollback_component("Odd", 7, capi.BGR_STRATEGY_COPY)
+    odd.checksum_component(c, 1, 5)
+    odd.build()
+    assert not odd.generic_specialised()
+    odd.close()
 
 
 def test_presence_api_errors():

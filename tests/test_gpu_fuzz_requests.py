@@ -13,7 +13,7 @@ from bevy_ggrs_b200.engine import Engine
 from bevy_ggrs_b200.session import ADVANCE, LOAD, SAVE, Request
 from oracle_backend import OracleError, OracleWorld
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300), pytest.mark.usefixtures("generic_kernel")]
 NOSESS = (capi.BGR_SESSION_NONE, 0, 0, 0)
 OPT = capi.BGR_STRATEGY_OPTIONAL
 

@@ -7,7 +7,7 @@ from bevy_ggrs_b200.engine import Engine
 from hierarchy_util import build_app, run_hierarchy_with_deletion, run_recursive_hierarchy
 from oracle_backend import OracleWorld
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("generic_kernel")]
 
 
 @pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])

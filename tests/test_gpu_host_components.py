@@ -8,7 +8,7 @@ from bevy_ggrs_b200.engine import Engine
 from bevy_ggrs_b200.host_components import HostComponents
 from host_components_util import Sprite, make_world, run_side_table_against_handle_column
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("generic_kernel")]
 
 
 @pytest.mark.parametrize("flags", [0, capi.BGR_CFG_FORCE_STEPWISE])

@@ -284,12 +284,13 @@ def test_pipelined_submits_overlap_without_observable_change(monkeypatch, tilede
 
 @pytest.mark.parametrize("block", ["64", "128", "256", "512"])
 @pytest.mark.parametrize("n,d,ticks", [(257, 3, 14), (10_000, 8, 12)])
-def test_particles_world_on_the_generic_program_matches_oracle(monkeypatch, n, d, ticks, block):
+def test_particles_world_on_the_generic_program_matches_oracle(monkeypatch, generic_kernel, n, d, ticks, block):
     """BGR_TUNE_BUNDLE=0 takes the specialised particles kernel out: the same world runs on the generic one-launch
     program (shared-memory tile, systems and hashes driven by the registration) and must match the oracle bit for bit,
     including despawns inside the window and the passive Transform planes of every snapshot."""
     monkeypatch.setenv("BGR_TUNE_BUNDLE", "0")
-    monkeypatch.setenv("BGR_TUNE_GENERIC_BLOCK", block)   # 8 / 4 (default) / 2 / 1 rows of a tile per thread
+    monkeypatch.setenv("BGR_TUNE_GENERIC_BLOCK", block)   # interpreter: 8 / 4 (default) / 2 / 1 rows of a tile per thread
+    monkeypatch.setenv("BGR_TUNE_JIT_ROWS", {"64": "4", "128": "4", "256": "2", "512": "1"}[block])  # specialised kernel: 4 / 2 / 1
     r = run_particles_synctest_pair(n, d, ticks, seed=5, ttl_lo=3, ttl_hi=40, peek_check=True, z_fraction=0.3)
     assert r["fused"] and r["launches"] == ticks
     assert r["checksums_equal"] and r["state_equal"] and r["peek_equal"]
@@ -298,13 +299,14 @@ def test_particles_world_on_the_generic_program_matches_oracle(monkeypatch, n, d
 
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("grid,block", [("3", "128"), ("7", "256"), ("40", "64")])
-def test_generic_program_blocks_that_run_many_tiles(monkeypatch, grid, block):
+def test_generic_program_blocks_that_run_many_tiles(monkeypatch, generic_kernel, grid, block):
     """The generic one-launch program with far fewer blocks than tiles (BGR_TUNE_GRID): every block claims tile after
     tile from the global counter, reloads its shared-memory tile, and must wait for its own bulk stores before the
     buffer is overwritten.  (Without the cap a world needs > 1.2M entities before a block sees a second tile.)"""
     monkeypatch.setenv("BGR_TUNE_BUNDLE", "0")
     monkeypatch.setenv("BGR_TUNE_GRID", grid)
     monkeypatch.setenv("BGR_TUNE_GENERIC_BLOCK", block)
+    monkeypatch.setenv("BGR_TUNE_JIT_ROWS", {"64": "4", "128": "4", "256": "2"}[block])
     r = run_particles_synctest_pair(60_000, 4, 10, seed=23, ttl_lo=3, ttl_hi=40, peek_check=True, z_fraction=0.2)
     assert r["fused"] and r["launches"] == 10
     assert r["checksums_equal"] and r["state_equal"] and r["peek_equal"]
@@ -329,13 +331,14 @@ def test_both_work_item_sizes_match_the_oracle(monkeypatch, sub, n, d, spawn):
 @pytest.mark.timeout(180)
 @pytest.mark.timeout(180)
 @pytest.mark.parametrize("grid,block", [("3", "128"), ("7", "256"), ("40", "64")])
-def test_generic_program_blocks_that_run_many_tiles(monkeypatch, grid, block):
+def test_generic_program_blocks_that_run_many_tiles(monkeypatch, generic_kernel, grid, block):
     """The generic one-launch program with far fewer blocks than tiles (BGR_TUNE_GRID): every block claims tile after
     tile from the global counter, reloads its shared-memory tile, and must wait for its own bulk stores before the
     buffer is overwritten.  (Without the cap a world needs > 1.2M entities before a block sees a second tile.)"""
     monkeypatch.setenv("BGR_TUNE_BUNDLE", "0")
     monkeypatch.setenv("BGR_TUNE_GRID", grid)
     monkeypatch.setenv("BGR_TUNE_GENERIC_BLOCK", block)
+    monkeypatch.setenv("BGR_TUNE_JIT_ROWS", {"64": "4", "128": "4", "256": "2"}[block])
     r = run_particles_synctest_pair(60_000, 4, 10, seed=23, ttl_lo=3, ttl_hi=40, peek_check=True, z_fraction=0.2)
     assert r["fused"] and r["launches"] == 10
     assert r["checksums_equal"] and r["state_equal"] and r["peek_equal"]
