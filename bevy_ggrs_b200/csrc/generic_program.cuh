@@ -34,9 +34,10 @@
 namespace bgr {
 
 constexpr int kMaxGenericSys = 8;
-// threads per block: 256 (two rows per thread) for worlds with many tiles per SM, 512 (one row per thread, twice the
-// warps per tile) for small worlds, where a tick is one wave of blocks and latency-bound per warp (ncu, 100k entities:
-// 2.6 warps per scheduler, issue slots 24 % busy)
+// threads per block: 64 / 128 / 256 / 512 = 8 / 4 / 2 / 1 rows of the tile per thread; 128 is the default (four independent
+// hash chains interleaved per thread; profiles/r02_generic_block_sweep.txt).  This kernel is the INTERPRETER: it reads the
+// schema from its parameter block.  bgr_build also compiles the registration's own kernel with NVRTC when it can
+// (generic_program_jit.cuh, jit.hpp), and this one is then only the fallback.
 
 struct SysSpec {
     uint32_t id;      // bgr_system
