@@ -88,7 +88,8 @@ def run(w, ticks):
     for info, arr, n in vecs[12:]:
         w.submit_prepared(info, arr, n); w.collect()
     dt = (time.perf_counter() - t0) / ticks
-    out = {"sync_us_per_tick": dt * 1e6, "launches_per_tick": (w.launch_count() - l0) / ticks, "one_launch": w.last_path_fused()}
+    out = {"sync_us_per_tick": dt * 1e6, "launches_per_tick": (w.launch_count() - l0) / ticks, "one_launch": w.last_path_fused(),
+           "specialised_kernel": w.generic_specialised()}  # True: the registration's own NVRTC-compiled kernel ran
     if traced:
         tr = w.trace_read(ticks + 4)
         out["kernel_us_median"] = float(np.median((tr[:, 1].astype(np.int64) - tr[:, 0].astype(np.int64)) / 1e3))

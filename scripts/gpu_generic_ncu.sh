@@ -1,7 +1,10 @@
 #!/bin/bash
-# ncu full capture of the generic one-launch program (presence world, 100k and 1M) + the bench JSON next to it
+# ncu full captures of the generic one-launch program on the presence world (scripts/generic_world_bench.py):
+# the registration's own kernel (k_generic_jit, NVRTC) at 100k and 1M, and the interpreter kernel (BGR_TUNE_JIT=0) at 100k and 1M
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_generic_program -s 20 -c 2 -f -o gpurun_out/r02_prof_generic python scripts/generic_world_bench.py 100000 24 > gpurun_out/r02_ncu_generic.log 2>&1; echo "generic ncu rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_generic_program -s 20 -c 1 -f -o gpurun_out/r02_prof_generic_1m python scripts/generic_world_bench.py 1000000 24 > gpurun_out/r02_ncu_generic_1m.log 2>&1; echo "generic 1m ncu rc=$?"
-timeout 600 python scripts/generic_world_bench.py 100000 200 > gpurun_out/r02_generic_world.json 2> gpurun_out/r02_generic_world.err; echo "generic bench rc=$?"
-timeout 600 python scripts/generic_world_bench.py 1000000 200 > gpurun_out/r02_generic_world_1m.json 2> gpurun_out/r02_generic_world_1m.err; echo "generic bench 1m rc=$?"
+for n in 100000 1000000; do
+  s=$([ $n = 100000 ] && echo "" || echo "_1m")
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_generic_jit -s 20 -c 1 -f -o gpurun_out/r02_prof_generic_jit$s python scripts/generic_world_bench.py $n 24 > gpurun_out/r02_ncu_generic_jit$s.log 2>&1; echo "jit $n ncu rc=$?"
+  BGR_TUNE_JIT=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_generic_program -s 20 -c 1 -f -o gpurun_out/r02_prof_generic$s python scripts/generic_world_bench.py $n 24 > gpurun_out/r02_ncu_generic$s.log 2>&1; echo "interpreter $n ncu rc=$?"
+  timeout 600 python scripts/generic_world_bench.py $n 200 > gpurun_out/r02_generic_world$s.json 2> gpurun_out/r02_generic_world$s.err; echo "bench $n rc=$?"
+done
