@@ -774,7 +774,8 @@ void fill_generic_specs(const bgr_engine* e, GenericParams& gp) {
 // NVRTC specialisation of the generic program for this registration (jit.hpp, generic_program_jit.cuh); called by bgr_build
 void jit_specialise(bgr_engine* e) {
     e->jit = JitKernel{};
-    if (!e->generic_ok || e->tune_jit == 0 || (e->bundle_particles && e->tune_bundle)) return;  // the bundle has its own kernel
+    if (!e->generic_ok || !e->tune_generic || e->tune_jit == 0 || (e->cfg.flags & BGR_CFG_FORCE_STEPWISE)) return;
+    if (e->bundle_particles && e->tune_bundle) return;  // the bundle has its own kernel
     if (e->tune_jit == 1 && e->cfg.max_entities < 16384) return;  // small worlds: a tick is launch latency, not worth a compile
     GenericParams gp;
     std::memset(&gp, 0, sizeof gp);
