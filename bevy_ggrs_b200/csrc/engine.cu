@@ -223,7 +223,9 @@ struct bgr_engine {
     int generic_bps[4] = {0, 0, 0, 0};  // resident blocks per SM of k_generic_program<64 | 128 | 256 | 512> (occupancy query, cached)
     int tune_jit = 1;               // 0 never, 1 worlds of >= 16k entities, 2 always: NVRTC-specialised generic program (jit.hpp)
     int tune_jit_rows = 4;          // rows of a tile per thread in the specialised kernel (1, 2, 4; measured: scripts/gpu_jit.sh)
-    JitKernel jit;                  // fn == nullptr: the interpreter kernel runs
+    JitKernel jit;                  // fn == nullptr: the interpreter kernel runs.  Work item = a whole tile
+    JitKernel jit_small;            // the same kernel with quarter-tile work items: worlds of few tiles per SM (optional)
+    int tune_jit_item = 0;          // 0 auto (quarter tiles below 3 tiles per SM), 512 / 256 / 128 force the rows per work item
     int tune_generic_block = 0;     // 0 = 128; 64 / 256 / 512 force
     int tune_passive_early = -1;    // -1: early passive stores for single-wave grids (auto); 0 never; 1 always
     int tune_sub = 0;               // 128: the 128-row work-item variant of the fused kernel (experiment; default: whole tiles)
@@ -774,6 +776,7 @@ void fill_generic_specs(const bgr_engine* e, GenericParams& gp) {
 // NVRTC specialisation of the generic program for this registration (jit.hpp, generic_program_jit.cuh); called by bgr_build
 void jit_specialise(bgr_engine* e) {
     e->jit = JitKernel{};
+    e->jit_small = JitKernel{};
     if (!e->generic_ok || !e->tune_generic || e->tune_jit == 0 || (e->cfg.flags & BGR_CFG_FORCE_STEPWISE)) return;
     if (e->bundle_particles && e->tune_bundle) return;  // the bundle has its own kernel
     if (e->tune_jit == 1 && e->cfg.max_entities < 16384) return;  // small worlds: a tick is launch latency, not worth a compile
@@ -784,32 +787,40 @@ void jit_specialise(bgr_engine* e) {
     for (uint32_t c = 0; c < gp.n_hash; ++c)   // whole-word byte ranges only (every POD of u32 / f32 / u64 fields)
         if (((gp.hash[c].off | gp.hash[c].len) & 3u) != 0u || gp.hash[c].len < 4 || gp.hash[c].len > 64) return;
     const int rows = e->tune_jit_rows == 1 || e->tune_jit_rows == 2 ? e->tune_jit_rows : 4;
-    const int threads = int(kTileRows) / rows;
-    std::string pre;
-    auto def = [&](const char* name, unsigned long long v) { pre += "#define " + std::string(name) + " " + std::to_string(v) + "\n"; };
-    def("BGR_SYS_PARTICLES_UPDATE", BGR_SYS_PARTICLES_UPDATE); def("BGR_SYS_PARTICLES_DESPAWN", BGR_SYS_PARTICLES_DESPAWN);
-    def("BGR_SYS_BOX_MOVE", BGR_SYS_BOX_MOVE); def("BGR_SYS_U32_ADD", BGR_SYS_U32_ADD);
-    def("BGR_SYS_U32_SATSUB_DESPAWN", BGR_SYS_U32_SATSUB_DESPAWN); def("BGR_SYS_U32_STORE_CALL_COUNT", BGR_SYS_U32_STORE_CALL_COUNT);
-    def("BGR_SYS_PARTICLES_SPAWN", BGR_SYS_PARTICLES_SPAWN); def("BGR_SYS_DESPAWN_ON_INPUT", BGR_SYS_DESPAWN_ON_INPUT);
-    def("BGR_TILE_ROWS", kTileRows);
-    def("BGR_JIT_WORDS", e->words); def("BGR_JIT_ROWS", rows);
-    def("BGR_JIT_MINB", rows == 1 ? 1 : rows == 2 ? (e->words <= 8 ? 3 : 2) : (e->words <= 8 ? 4 : 2));
-    def("BGR_JIT_NSYS", gp.n_sys); def("BGR_JIT_NHASH", gp.n_hash);
-    auto u = [](uint32_t v) { return std::to_string(v) + "u"; };
-    pre += "#define BGR_JIT_SYS_LIST ";
-    for (uint32_t i = 0; i < gp.n_sys; ++i) {
-        const SysSpec& y = gp.sys[i];
-        pre += "{" + u(y.id) + "," + u(y.plane0) + "," + u(y.plane1) + "," + u(y.need) + "," + u(y.param) + "}, ";
-    }
-    pre += "{0u,0u,0u,0u,0u}\n#define BGR_JIT_HASH_LIST ";
-    for (uint32_t i = 0; i < gp.n_hash; ++i) {
-        const HashSpec& h = gp.hash[i];
-        pre += "{" + u(h.first_plane) + "," + u(h.off) + "," + u(h.len) + "," + u(h.finite) + "," + u(h.slot) + "," + u(h.absent) + "}, ";
-    }
-    pre += "{0u,0u,0u,0u,0u,0u}\n";
-    std::string why;
-    if (!jit_generic_program(pre, threads, reinterpret_cast<const void*>(&bgr_abi_version), &e->jit, &why) && std::getenv("BGR_JIT_VERBOSE"))
-        std::fprintf(stderr, "[bevy_ggrs_b200] generic program not specialised, the interpreter kernel runs: %s\n", why.c_str());
+    auto compile = [&](int item_rows, int rows, JitKernel* out) {
+        const int threads = item_rows / rows;
+        std::string pre;
+        auto def = [&](const char* name, unsigned long long v) { pre += "#define " + std::string(name) + " " + std::to_string(v) + "\n"; };
+        def("BGR_SYS_PARTICLES_UPDATE", BGR_SYS_PARTICLES_UPDATE); def("BGR_SYS_PARTICLES_DESPAWN", BGR_SYS_PARTICLES_DESPAWN);
+        def("BGR_SYS_BOX_MOVE", BGR_SYS_BOX_MOVE); def("BGR_SYS_U32_ADD", BGR_SYS_U32_ADD);
+        def("BGR_SYS_U32_SATSUB_DESPAWN", BGR_SYS_U32_SATSUB_DESPAWN); def("BGR_SYS_U32_STORE_CALL_COUNT", BGR_SYS_U32_STORE_CALL_COUNT);
+        def("BGR_SYS_PARTICLES_SPAWN", BGR_SYS_PARTICLES_SPAWN); def("BGR_SYS_DESPAWN_ON_INPUT", BGR_SYS_DESPAWN_ON_INPUT);
+        def("BGR_TILE_ROWS", kTileRows);
+        def("BGR_JIT_WORDS", e->words); def("BGR_JIT_ROWS", rows); def("BGR_JIT_ITEM_ROWS", item_rows);
+        // resident blocks the register allocation has to allow: ~512 threads per SM for narrow rows, ~256 for wide ones
+        def("BGR_JIT_MINB", std::max(1, (e->words <= 8 ? 512 : 256) / threads));
+        def("BGR_JIT_NSYS", gp.n_sys); def("BGR_JIT_NHASH", gp.n_hash);
+        auto u = [](uint32_t v) { return std::to_string(v) + "u"; };
+        pre += "#define BGR_JIT_SYS_LIST ";
+        for (uint32_t i = 0; i < gp.n_sys; ++i) {
+            const SysSpec& y = gp.sys[i];
+            pre += "{" + u(y.id) + "," + u(y.plane0) + "," + u(y.plane1) + "," + u(y.need) + "," + u(y.param) + "}, ";
+        }
+        pre += "{0u,0u,0u,0u,0u}\n#define BGR_JIT_HASH_LIST ";
+        for (uint32_t i = 0; i < gp.n_hash; ++i) {
+            const HashSpec& h = gp.hash[i];
+            pre += "{" + u(h.first_plane) + "," + u(h.off) + "," + u(h.len) + "," + u(h.finite) + "," + u(h.slot) + "," + u(h.absent) + "}, ";
+        }
+        pre += "{0u,0u,0u,0u,0u,0u}\n";
+        std::string why;
+        if (!jit_generic_program(pre, threads, reinterpret_cast<const void*>(&bgr_abi_version), out, &why) && std::getenv("BGR_JIT_VERBOSE"))
+            std::fprintf(stderr, "[bevy_ggrs_b200] generic program not specialised, the interpreter kernel runs: %s\n", why.c_str());
+        out->item_rows = item_rows;
+    };
+    const int forced = e->tune_jit_item == 512 || e->tune_jit_item == 256 || e->tune_jit_item == 128 ? e->tune_jit_item : 0;
+    compile(forced ? forced : int(kTileRows), std::min(rows, (forced ? forced : int(kTileRows)) / 32), &e->jit);  // a block is at least one warp
+    // worlds of few tiles per SM: quarter-tile items, two rows per thread (measured: profiles/r02_generic_jit_sweep.txt)
+    if (!forced && e->jit.fn) compile(128, 2, &e->jit_small);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -836,10 +847,13 @@ int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
     fill_generic_specs(e, gp);
     std::memcpy(gp.ops, pg.ops, sizeof(Op) * pg.n_ops);
     if (e->jit.fn) {  // the registration's own register-resident kernel
-        uint32_t grid = std::max(1u, std::min(gp.n_tiles, uint32_t(e->num_sms * e->jit.bps)));
+        // few tiles per SM: with whole tiles some SMs carry twice the rows of others and set the kernel's duration
+        const JitKernel& k = (e->jit_small.fn && gp.n_tiles < 3u * uint32_t(e->num_sms)) ? e->jit_small : e->jit;
+        const uint32_t n_items = gp.n_tiles * (kTileRows / uint32_t(k.item_rows));
+        uint32_t grid = std::max(1u, std::min(n_items, uint32_t(e->num_sms * k.bps)));
         if (e->tune_grid > 0) grid = std::min(grid, uint32_t(e->tune_grid));
         void* args[] = {&gp};
-        CUDA_TRY(cudaLaunchKernel(e->jit.fn, dim3(grid), dim3(e->jit.threads), args, 0, e->stream));
+        CUDA_TRY(cudaLaunchKernel(k.fn, dim3(grid), dim3(k.threads), args, 0, e->stream));
         CUDA_TRY(cudaGetLastError());
         e->launches += 1;
         return BGR_OK;
@@ -1240,6 +1254,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_generic_block = env_int("BGR_TUNE_GENERIC_BLOCK", 0);
     e->tune_jit = env_int("BGR_TUNE_JIT", 1);
     e->tune_jit_rows = env_int("BGR_TUNE_JIT_ROWS", 4);
+    e->tune_jit_item = env_int("BGR_TUNE_JIT_ITEM", 0);
     e->tune_passive_early = env_int("BGR_TUNE_PASSIVE_EARLY", -1);
     e->tune_stagger_ns = env_int("BGR_TUNE_STAGGER_NS", 800);
     e->tune_bundle = env_int("BGR_TUNE_BUNDLE", 1);

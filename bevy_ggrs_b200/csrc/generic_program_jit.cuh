@@ -25,7 +25,12 @@
 namespace bgr {
 
 constexpr int kJitWords = BGR_JIT_WORDS;  // word planes per row
-constexpr int kJitRows = BGR_JIT_ROWS;    // rows of a tile per thread
+constexpr int kJitRows = BGR_JIT_ROWS;    // rows of a work item per thread
+// rows per WORK ITEM: a tile (512) for worlds of many tiles per SM; 256 / 128 for small worlds — 100k entities are 196 tiles on
+// 148 SMs, so with whole tiles a third of the SMs carry two tiles and set the kernel's duration (they are bound by the integer
+// multiply pipe of the seahash, scripts/frame_cost_fit.py) while the others idle half of it; quarter tiles spread the rows evenly
+constexpr int kJitItemRows = BGR_JIT_ITEM_ROWS;
+constexpr int kJitSubs = int(kTileRows) / kJitItemRows;  // work items per tile
 constexpr int kJitNSys = BGR_JIT_NSYS;
 constexpr int kJitNHash = BGR_JIT_NHASH;
 constexpr SysSpec kJitSys[kJitNSys + 1] = {BGR_JIT_SYS_LIST};      // {id, plane0, plane1, need, param}, ... + one dummy
@@ -127,8 +132,8 @@ __device__ __forceinline__ void jit_hash_columns(const JitRows& r, unsigned int*
     }
 }
 
-extern "C" __global__ void __launch_bounds__(kTileRows / BGR_JIT_ROWS, BGR_JIT_MINB) k_generic_jit(const __grid_constant__ GenericParams p) {
-    constexpr int B = kTileRows / kJitRows;  // threads per tile
+extern "C" __global__ void __launch_bounds__(BGR_JIT_ITEM_ROWS / BGR_JIT_ROWS, BGR_JIT_MINB) k_generic_jit(const __grid_constant__ GenericParams p) {
+    constexpr int B = kJitItemRows / kJitRows;  // threads per work item
     __shared__ unsigned int s_acc[kMaxSaves * kAccStride * 2];
     __shared__ uint32_t s_next;
     __shared__ unsigned int s_last;
@@ -143,20 +148,22 @@ extern "C" __global__ void __launch_bounds__(kTileRows / BGR_JIT_ROWS, BGR_JIT_M
     constexpr uint32_t kTileBytes = kTileRows * (4u * kJitWords + 1u);
     constexpr uint32_t kAliveOff = uint32_t(kJitWords) * kPlaneBytes;  // the mask bytes follow the word planes inside a tile
 
-    for (uint32_t tile = blockIdx.x; tile < p.n_tiles;) {
+    const uint32_t n_items = p.n_tiles * uint32_t(kJitSubs);
+    for (uint32_t item = blockIdx.x; item < n_items;) {
         __syncthreads();  // every thread has read the previous s_next
         if (tid == 0) s_next = gridDim.x + atomicAdd(&p.ticket[1], 1u);
         __syncthreads();
-        const uint32_t next_tile = s_next;
+        const uint32_t next_item = s_next;
+        const uint32_t tile = item / uint32_t(kJitSubs), sub_row0 = (item % uint32_t(kJitSubs)) * uint32_t(kJitItemRows) + tid;  // first row of the thread inside the tile
         const size_t tile_off = size_t(tile) * kTileBytes;
-        const unsigned long long row0 = p.order_base + size_t(tile) * kTileRows + tid;
+        const unsigned long long row0 = p.order_base + size_t(tile) * kTileRows + sub_row0;
 
         JitRows r;
         auto load = [&](const uint8_t* img, uint32_t n_rows_src) {
             const uint8_t* t = img + tile_off;
 #pragma unroll
             for (int k = 0; k < kJitRows; ++k) {
-                const uint32_t row = tid + k * B;
+                const uint32_t row = sub_row0 + k * B;
 #pragma unroll
                 for (int j = 0; j < kJitWords; ++j) r.w[k][j] = *reinterpret_cast<const uint32_t*>(t + size_t(j) * kPlaneBytes + size_t(row) * 4u);
                 const uint32_t mm = t[kAliveOff + row];
@@ -167,7 +174,7 @@ extern "C" __global__ void __launch_bounds__(kTileRows / BGR_JIT_ROWS, BGR_JIT_M
             uint8_t* t = img + tile_off;
 #pragma unroll
             for (int k = 0; k < kJitRows; ++k) {
-                const uint32_t row = tid + k * B;
+                const uint32_t row = sub_row0 + k * B;
 #pragma unroll
                 for (int j = 0; j < kJitWords; ++j) *reinterpret_cast<uint32_t*>(t + size_t(j) * kPlaneBytes + size_t(row) * 4u) = r.w[k][j];
                 t[kAliveOff + row] = uint8_t(r.m[k]);
@@ -201,7 +208,7 @@ extern "C" __global__ void __launch_bounds__(kTileRows / BGR_JIT_ROWS, BGR_JIT_M
             }
         }
         if (p.flags & PF_WRITE_LIVE_ACTIVE) store(p.arena);
-        tile = next_tile;
+        item = next_item;
     }
 
     // ---- block partials -> global accumulators -> (last block) host-visible results: k_particles_program's protocol ----

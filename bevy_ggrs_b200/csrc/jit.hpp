@@ -27,6 +27,7 @@ namespace bgr {
 struct JitKernel {
     const void* fn = nullptr;  // cudaKernel_t, usable wherever the runtime takes a kernel's `const void* func`
     int threads = 0;
+    int item_rows = 0;         // rows per work item (set by the caller)
     int bps = 0;               // resident blocks per SM (occupancy query)
 };
 

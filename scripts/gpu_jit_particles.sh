@@ -1,7 +1,7 @@
 #!/bin/bash
 # the particles stress world itself on the NVRTC-specialised generic kernel (bundle off) next to the hand-written bundle
 mkdir -p gpurun_out
-SWEEP_EXTRA='[{"BGR_TUNE_BUNDLE":0,"BGR_TUNE_JIT":2,"BGR_TUNE_JIT_ROWS":1},{"BGR_TUNE_BUNDLE":0,"BGR_TUNE_JIT":2,"BGR_TUNE_JIT_ROWS":2},{"BGR_TUNE_BUNDLE":0,"BGR_TUNE_JIT":2,"BGR_TUNE_JIT_ROWS":4},{"BGR_TUNE_BUNDLE":0,"BGR_TUNE_JIT":0}]' \
+SWEEP_EXTRA='[{"BGR_TUNE_BUNDLE":0,"BGR_TUNE_JIT":2,"BGR_TUNE_JIT_ITEM":512},{"BGR_TUNE_BUNDLE":0,"BGR_TUNE_JIT":2,"BGR_TUNE_JIT_ITEM":256},{"BGR_TUNE_BUNDLE":0,"BGR_TUNE_JIT":2,"BGR_TUNE_JIT_ITEM":128},{"BGR_TUNE_BUNDLE":0,"BGR_TUNE_JIT":2,"BGR_TUNE_JIT_ITEM":128,"BGR_TUNE_JIT_ROWS":2}]' \
   BGR_JIT_VERBOSE=1 timeout 900 python scripts/sync_sweep.py stress_100k_d8 stress_1m_d8 > gpurun_out/jit_particles_sweep.jsonl 2> gpurun_out/jit_particles_sweep.err
 echo "rc=$?"
 python - <<'PY'

@@ -24,7 +24,10 @@ def oracle_lib():
 # kernel compiled by NVRTC at bgr_build (csrc/generic_program_jit.cuh, schema as compile-time constants, rows in
 # registers).  GPU test modules of the generic path opt in with `pytestmark = pytest.mark.usefixtures("generic_kernel")`
 # and then run every test on both.
-@pytest.fixture(params=["interpreter", "jit"])
+@pytest.fixture(params=["interpreter", "jit", "jit_quarter_tiles"])
 def generic_kernel(request, monkeypatch):
     monkeypatch.setenv("BGR_TUNE_JIT", "0" if request.param == "interpreter" else "2")
+    if request.param == "jit":
+        monkeypatch.setenv("BGR_TUNE_JIT_ITEM", "512")   # one tile per work item (what worlds of many tiles per SM run)
+    # "jit_quarter_tiles": the default for worlds of few tiles per SM — 128-row work items
     return request.param

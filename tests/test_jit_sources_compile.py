@@ -27,10 +27,10 @@ def _system_ids():
     return {m.group(1): int(m.group(2)) for m in re.finditer(r"(BGR_SYS_[A-Z0-9_]+)\s*=\s*(\d+)", hdr)}
 
 
-def _prelude(words, rows, systems, hashes):
+def _prelude(words, rows, systems, hashes, item_rows=512):
     ids = _system_ids()
     lines = [f"#define {k} {v}" for k, v in ids.items()]
-    lines += [f"#define BGR_TILE_ROWS 512", f"#define BGR_JIT_WORDS {words}", f"#define BGR_JIT_ROWS {rows}", "#define BGR_JIT_MINB 2",
+    lines += [f"#define BGR_TILE_ROWS 512", f"#define BGR_JIT_WORDS {words}", f"#define BGR_JIT_ROWS {rows}", f"#define BGR_JIT_ITEM_ROWS {item_rows}", "#define BGR_JIT_MINB 2",
               f"#define BGR_JIT_NSYS {len(systems)}", f"#define BGR_JIT_NHASH {len(hashes)}"]
     fmt = lambda t: "{" + ",".join(f"{int(v)}u" for v in t) + "}"
     lines.append("#define BGR_JIT_SYS_LIST " + ", ".join([fmt((ids[s[0]],) + tuple(s[1:])) for s in systems] + ["{0u,0u,0u,0u,0u}"]))
@@ -72,11 +72,11 @@ REGISTRATIONS = {
 }
 
 
-@pytest.mark.parametrize("rows", [1, 2, 4])
+@pytest.mark.parametrize("rows,item_rows", [(1, 512), (2, 512), (4, 512), (4, 128), (2, 256)])
 @pytest.mark.parametrize("name", list(REGISTRATIONS))
-def test_generated_kernel_compiles_for_sm_100a(name, rows):
+def test_generated_kernel_compiles_for_sm_100a(name, rows, item_rows):
     words, systems, hashes = REGISTRATIONS[name]
-    cubin = _compile(_prelude(words, rows, systems, hashes))
+    cubin = _compile(_prelude(words, rows, systems, hashes, item_rows))
     assert cubin[:4] == b"\x7fELF" and b"k_generic_jit" in cubin
 
 
