@@ -549,6 +549,12 @@ def run_ours(args):
         except Exception as exc:
             snap10 = {"error": repr(exc)}
         skip = skip_unchanged_bench(n, d, maxp, local_rank, ticks, fill, W, K, history)
+    generic = None
+    if rank == 0 and world_size == 1 and not args.no_snapshot_bench:
+        try:
+            generic = generic_world_leg(n)
+        except Exception as exc:  # an optional leg must not cost the headline line
+            generic = {"error": repr(exc)}
 
     if rank == 0:
         value = sum(shard_rows) / n_total * adv_total / (ms * 1e-3) if strong else world_size * adv_total / (ms * 1e-3)
@@ -622,6 +628,8 @@ def run_ours(args):
             line["snapshot_save_restore_10m"] = snap10
         if skip:
             line["opt_in_skip_unchanged_planes"] = skip
+        if generic:
+            line["generic_world"] = generic
         guard.emit(json.dumps(line))
     eng.close()
     if sharded:
@@ -629,6 +637,31 @@ def run_ours(args):
         dist.destroy_process_group()
     if not consistent:
         sys.exit(3)
+
+
+def generic_world_leg(n):
+    """A registration that is NOT the particles bundle (optional Score / Health + a 12-byte Tag, all checksummed, two u32
+    systems; scripts/generic_world_bench.py) at the headline entity count, synchronous SyncTest ticks (check_distance 8) driven
+    from Python: once on the kernel bgr_build compiled for it with NVRTC, once on the precompiled interpreter kernel."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import generic_world_bench as g
+    out = {"entities": n, "check_distance": 8, "world": "Score 4 B optional + Health 4 B optional (satsub-despawn) + Tag 12 B, all checksummed",
+           "note": "synchronous ticks from Python; kernel_us = device globaltimer, first block start .. last block end (median)"}
+    old = os.environ.get("BGR_TUNE_JIT")
+    try:
+        for name, jit in (("specialised_kernel", "2"), ("interpreter_kernel", "0")):
+            os.environ["BGR_TUNE_JIT"] = jit
+            w = g.presence_world(n, 0)
+            try:
+                out[name] = g.run(w, 100)
+            finally:
+                w.close()
+    finally:
+        if old is None:
+            os.environ.pop("BGR_TUNE_JIT", None)
+        else:
+            os.environ["BGR_TUNE_JIT"] = old
+    return out
 
 
 def verify_against_unsharded(shard_rows, d, maxp, device_index, tick_list, history):
