@@ -1,4 +1,4 @@
-// k_generic_program SPECIALISED AT RUN TIME for one registration (compiled by NVRTC inside bgr_build, engine.cu `JitProgram`).
+// k_generic_program SPECIALISED AT RUN TIME for one registration (compiled by NVRTC inside bgr_build: engine.cu `jit_specialise`, jit.hpp).
 //
 // The interpreter (generic_program.cuh) reads the schema — which planes a system touches, which byte ranges are hashed —
 // from its parameter block, so a tile has to live in shared memory (registers cannot be indexed at run time; the
