@@ -225,6 +225,9 @@ struct bgr_engine {
     int tune_jit_rows = 4;          // rows of a tile per thread in the specialised kernel (1, 2, 4; measured: scripts/gpu_jit.sh)
     JitKernel jit;                  // fn == nullptr: the interpreter kernel runs.  Work item = a whole tile
     JitKernel jit_small;            // the same kernel with quarter-tile work items: worlds of few tiles per SM (optional)
+    int tune_jit_tiledep = 0;       // 1: consecutive launches of the generated kernel overlap through per-item dependencies (queued submits)
+    unsigned int* d_item_done = nullptr;   // [4 * tiles] GenericParams::item_done (quarter-tile work items at most)
+    const void* jit_chain_kernel = nullptr;  // the signalling launch `tiledep_chain` refers to (its work-item partition must match)
     int tune_jit_item = 0;          // 0 auto (quarter tiles below 3 tiles per SM), 512 / 256 / 128 force the rows per work item
     int tune_generic_block = 0;     // 0 = 128; 64 / 256 / 512 force
     int tune_passive_early = -1;    // -1: early passive stores for single-wave grids (auto); 0 never; 1 always
@@ -828,6 +831,7 @@ void jit_specialise(bgr_engine* e) {
 // ---------------------------------------------------------------------------------------------
 int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
     e->main_dirty = true;
+    const bool prev_chain = e->tiledep_chain;  // the last operation on the stream was a signalling launch of the generated kernel
     e->tiledep_chain = false;
     GenericParams gp;
     std::memset(&gp, 0, sizeof gp);
@@ -852,10 +856,38 @@ int run_generic(bgr_engine* e, const Program& pg, uint32_t buf) {
         const uint32_t n_items = gp.n_tiles * (kTileRows / uint32_t(k.item_rows));
         uint32_t grid = std::max(1u, std::min(n_items, uint32_t(e->num_sms * k.bps)));
         if (e->tune_grid > 0) grid = std::min(grid, uint32_t(e->tune_grid));
+        // Overlap of consecutive launches: only when request vectors are queued behind each other (a synchronous caller
+        // collects before its next submit), only on a stream the engine owns, and only between launches of the SAME kernel
+        // over the SAME items (the per-item flags mean nothing across partitions: drain instead — rare, rows crossed a tile).
+        const bool tiledep = e->tune_jit_tiledep && e->d_item_done && e->own_stream && (e->tune_jit_tiledep > 1 || !e->pending.empty());
+        bool wait = false;
+        if (prev_chain) {
+            if (tiledep && e->jit_chain_kernel == k.fn && e->tiledep_tiles == n_items) wait = true;
+            else CUDA_TRY(cudaStreamSynchronize(e->stream));  // an earlier overlapping launch may still be running
+        }
+        if (tiledep) {
+            gp.flags |= PF_TILE_SIGNAL;
+            gp.item_done = e->d_item_done;
+            gp.done_seq = uint32_t(e->seq);
+            if (wait) { gp.flags |= PF_TILE_WAIT; gp.wait_seq = e->tiledep_seq; gp.wait_items = n_items; }
+            // overlapping launches must not share accumulators / tickets: one set per in-flight request vector (run_fused)
+            const uint32_t set = uint32_t(e->seq % bgr_engine::kBufs);
+            gp.accum = e->d_accum_c[set];
+            gp.ticket = e->d_ticket_c[set];
+        }
         void* args[] = {&gp};
-        CUDA_TRY(cudaLaunchKernel(k.fn, dim3(grid), dim3(k.threads), args, 0, e->stream));
+        cudaLaunchConfig_t cfg;
+        std::memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(k.threads); cfg.dynamicSmemBytes = 0; cfg.stream = e->stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = wait ? 1u : 0u;
+        CUDA_TRY(cudaLaunchKernelExC(&cfg, k.fn, args));
         CUDA_TRY(cudaGetLastError());
         e->launches += 1;
+        e->tiledep_chain = tiledep;
+        e->tiledep_seq = uint32_t(e->seq); e->tiledep_tiles = n_items; e->jit_chain_kernel = k.fn;
         return BGR_OK;
     }
     const size_t smem = size_t((e->tile_bytes + 127u) & ~127u);
@@ -1255,6 +1287,7 @@ BGR_API int bgr_engine_create(const bgr_config* cfg, bgr_engine** out) {
     e->tune_jit = env_int("BGR_TUNE_JIT", 1);
     e->tune_jit_rows = env_int("BGR_TUNE_JIT_ROWS", 4);
     e->tune_jit_item = env_int("BGR_TUNE_JIT_ITEM", 0);
+    e->tune_jit_tiledep = env_int("BGR_TUNE_JIT_TILEDEP", 0);
     e->tune_passive_early = env_int("BGR_TUNE_PASSIVE_EARLY", -1);
     e->tune_stagger_ns = env_int("BGR_TUNE_STAGGER_NS", 800);
     e->tune_bundle = env_int("BGR_TUNE_BUNDLE", 1);
@@ -1290,6 +1323,7 @@ BGR_API void bgr_engine_destroy(bgr_engine* e) {
     if (e->d_tma_ticket) cudaFree(e->d_tma_ticket);
     if (e->d_tile_done) cudaFree(e->d_tile_done);
     if (e->d_tile_cnt) cudaFree(e->d_tile_cnt);
+    if (e->d_item_done) cudaFree(e->d_item_done);
     for (auto& d : e->dl) {
         if (d.d_buf) cudaFree(d.d_buf);
         if (d.packed) cudaEventDestroy(d.packed);
@@ -1475,6 +1509,11 @@ BGR_API int bgr_build(bgr_engine* e) {
         e->generic_ok = ok;
     }
     jit_specialise(e);
+    if (e->jit.fn && e->tune_jit_tiledep) {
+        const size_t ni = size_t(e->tiles_for(e->cfg.max_entities)) * 4 + 4;
+        CUDA_TRY(cudaMalloc(&e->d_item_done, ni * sizeof(unsigned int)));
+        CUDA_TRY(cudaMemsetAsync(e->d_item_done, 0, ni * sizeof(unsigned int), e->stream));
+    }
     {   // TMA copy kernel: up to six one-tile stages in ~200 KB of shared memory, at least two
         uint32_t st = uint32_t(std::min<size_t>((200u * 1024u) / e->tile_bytes, size_t(kTmaMaxStages)));
         if (env_int("BGR_TUNE_TMA_STAGES", 0) > 0) st = std::min(st, uint32_t(env_int("BGR_TUNE_TMA_STAGES", 0)));

@@ -56,6 +56,10 @@ struct GenericParams {
     unsigned long long seq;
     unsigned long long* trace;
     uint32_t words, tile_bytes, n_ops, n_saves, n_tiles, live_rows, flags, n_hash, n_sys;
+    // overlap of consecutive launches (generated kernel only; the protocol of k_particles_program's PF_TILE_SIGNAL / PF_TILE_WAIT
+    // per WORK ITEM): item_done[i] = sequence number of the last signalling launch whose stores of item i are visible
+    unsigned int* item_done;
+    uint32_t done_seq, wait_seq, wait_items;
     HashSpec hash[kMaxHashCols];
     SysSpec sys[kMaxGenericSys];
     Op ops[kMaxOps];

@@ -139,8 +139,17 @@ extern "C" __global__ void __launch_bounds__(BGR_JIT_ITEM_ROWS / BGR_JIT_ROWS, B
     __shared__ unsigned int s_last;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    // Overlap of consecutive request vectors (bgr_submit_requests with others un-collected): work item i of tick k+1 only
+    // depends on work item i of tick k.  A signalling launch lets the next one be scheduled as its own blocks retire
+    // (griddepcontrol.launch_dependents); a waiting launch was started with programmatic stream serialisation, skips the
+    // grid-level wait and instead waits per item for item_done[i] >= wait_seq.  Both grids are at most one wave of resident
+    // blocks and every block of the earlier grid has started before the first block of the later one does, so the spin
+    // cannot starve what it waits for.  (k_particles_program's protocol, DESIGN.md "Overlapping consecutive ticks".)
+    const bool signal_items = (p.flags & PF_TILE_SIGNAL) != 0u, wait_items = (p.flags & PF_TILE_WAIT) != 0u;
+    if (signal_items || wait_items) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (p.trace && tid == 0) atomicMin(&p.trace[0], globaltimer_ns());
     for (uint32_t i = tid; i < p.n_saves * kAccStride * 2; i += B) s_acc[i] = 0u;
+    if (!wait_items) asm volatile("griddepcontrol.wait;" ::: "memory");  // a no-op unless launched as a programmatic dependent
     __syncthreads();
 
     const uint8_t* first_img = p.arena + ((p.flags & PF_READ_LIVE) ? size_t(0) : (size_t(p.ops[0].image_off256) << 8));
@@ -151,7 +160,11 @@ extern "C" __global__ void __launch_bounds__(BGR_JIT_ITEM_ROWS / BGR_JIT_ROWS, B
     const uint32_t n_items = p.n_tiles * uint32_t(kJitSubs);
     for (uint32_t item = blockIdx.x; item < n_items;) {
         __syncthreads();  // every thread has read the previous s_next
-        if (tid == 0) s_next = gridDim.x + atomicAdd(&p.ticket[1], 1u);
+        if (tid == 0) {
+            s_next = gridDim.x + atomicAdd(&p.ticket[1], 1u);
+            if (wait_items && item < p.wait_items)
+                while (int32_t(ld_acquire_gpu(&p.item_done[item]) - p.wait_seq) < 0) {}  // the previous tick's stores of this item are visible
+        }
         __syncthreads();
         const uint32_t next_item = s_next;
         const uint32_t tile = item / uint32_t(kJitSubs), sub_row0 = (item % uint32_t(kJitSubs)) * uint32_t(kJitItemRows) + tid;  // first row of the thread inside the tile
@@ -165,8 +178,8 @@ extern "C" __global__ void __launch_bounds__(BGR_JIT_ITEM_ROWS / BGR_JIT_ROWS, B
             for (int k = 0; k < kJitRows; ++k) {
                 const uint32_t row = sub_row0 + k * B;
 #pragma unroll
-                for (int j = 0; j < kJitWords; ++j) r.w[k][j] = *reinterpret_cast<const uint32_t*>(t + size_t(j) * kPlaneBytes + size_t(row) * 4u);
-                const uint32_t mm = t[kAliveOff + row];
+                for (int j = 0; j < kJitWords; ++j) r.w[k][j] = __ldcg(reinterpret_cast<const uint32_t*>(t + size_t(j) * kPlaneBytes + size_t(row) * 4u));
+                const uint32_t mm = __ldcg(t + kAliveOff + row);  // .cg: L2 only — overlapping grids share an SM's L1 without a kernel boundary in between
                 r.m[k] = (tile * kTileRows + row < n_rows_src) ? mm : 0u;  // rows the image never contained come back dead
             }
         };
@@ -208,6 +221,11 @@ extern "C" __global__ void __launch_bounds__(BGR_JIT_ITEM_ROWS / BGR_JIT_ROWS, B
             }
         }
         if (p.flags & PF_WRITE_LIVE_ACTIVE) store(p.arena);
+        if (signal_items) {  // every thread's stores of this item are visible at gpu scope, then one release store announces it
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) st_release_gpu(&p.item_done[item], p.done_seq);
+        }
         item = next_item;
     }
 

@@ -94,6 +94,28 @@ def run(w, ticks):
         tr = w.trace_read(ticks + 4)
         out["kernel_us_median"] = float(np.median((tr[:, 1].astype(np.int64) - tr[:, 0].astype(np.int64)) / 1e3))
         w.trace_enable(0)
+    # pipelined: up to four request vectors un-collected (the same vectors again: a SyncTest tick is Load + re-simulate)
+    if os.environ.get("GENERIC_BENCH_PIPELINED"):
+        more = []
+        for t in range(ticks):
+            for h in range(2):
+                sess.add_local_input(h, 0)
+            reqs = sess.advance_frame()
+            for r in reqs:
+                if r.kind == SAVE:
+                    sess.save_cell(r.frame, 0)
+            more.append((capi.make_session_info(sess.info()), capi.make_requests(reqs), len(reqs)))
+        w.synchronize()
+        t0 = time.perf_counter()
+        inflight = 0
+        for info, arr, n in more:
+            w.submit_prepared(info, arr, n)
+            inflight += 1
+            if inflight == 4:
+                w.collect(); inflight -= 1
+        while inflight:
+            w.collect(); inflight -= 1
+        out["pipelined_us_per_tick"] = (time.perf_counter() - t0) / ticks * 1e6
     return out
 
 

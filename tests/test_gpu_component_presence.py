@@ -145,6 +145,57 @@ def test_presence_world_with_many_tiles_per_block(monkeypatch, grid):
     assert 0 < orc.read_alive(0, n).sum() < n
 
 
+@pytest.mark.timeout(180)
+@pytest.mark.parametrize("tiledep", ["0", "1", "2"])
+@pytest.mark.parametrize("n", [3000, 120_000])
+def test_pipelined_submits_on_the_generic_program(monkeypatch, generic_kernel, tiledep, n):
+    """Four request vectors in flight (bgr_submit_requests / bgr_collect) on a world that is not the bundle.  With
+    BGR_TUNE_JIT_TILEDEP=1 consecutive launches of the generated kernel overlap on the GPU — work item i of tick k+1 starts
+    when item i of tick k has signalled (=2: also on synchronous calls).  Every tick's checksums, the final world and a
+    snapshot equal the oracle's.  A dependency bug hangs or corrupts: bounded by pytest-timeout."""
+    from bevy_ggrs_b200.session import SyncTestSession
+    monkeypatch.setenv("BGR_TUNE_JIT_TILEDEP", tiledep)
+    d, n_ticks = 3, 30 if n < 100_000 else 14
+    eng, orc, cols = _pair(n, depth=8)
+    score, health, tag = cols
+    for w in (eng, orc):
+        for r in range(0, n, 41):
+            w.remove_component(score, r)
+    sess = SyncTestSession(2, d, 8, input_delay=2)
+    vectors = []
+    for t in range(n_ticks):
+        sess.add_local_input(0, 0); sess.add_local_input(1, 0)
+        reqs = sess.advance_frame()
+        for r in reqs:
+            if r.kind == SAVE:
+                sess.save_cell(r.frame, 0)
+        vectors.append(reqs)
+    got, want, inflight = [], [], 0
+    for v in vectors:
+        eng.submit_requests(sess.info(), v)
+        inflight += 1
+        if inflight == 4:
+            got += eng.collect()
+            inflight -= 1
+        want += orc.handle_requests(sess.info(), v)
+    while inflight:
+        got += eng.collect()
+        inflight -= 1
+    assert got == want and len(got) >= n_ticks
+    assert eng.last_path_fused()
+    _same(eng, orc, cols, n)
+    f = eng.snapshot_frames()[-1]
+    pe, po = eng.peek(f, tag, 0, n), orc.peek(f, tag, 0, n)
+    m = po[1].astype(bool)
+    assert np.array_equal(pe[1].astype(bool), m) and np.array_equal(pe[0][m], po[0][m])
+    # synchronous calls after the pipelined ones: the chain state must not leak
+    nxt = eng.rollback_frame_count() + 1
+    a, b = [w.handle_requests(NOSESS, [Request(ADVANCE, 0, [0, 0]), Request(SAVE, nxt)]) for w in (eng, orc)]
+    assert a == b
+    _same(eng, orc, cols, n)
+    eng.close(); orc.close()
+
+
 def test_build_compiles_the_registrations_own_kernel(generic_kernel):
     """BGR_TUNE_JIT=2: bgr_build hands the registration to NVRTC (csrc/jit.hpp) and every request vector then runs on
     that kernel; =0: the interpreter kernel.  A registration the specialised kernel does not cover (a checksum over a byte
